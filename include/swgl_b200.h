@@ -1,0 +1,82 @@
+/*
+ * include/swgl_b200.h -- extension entry points of libswgl_b200.so (none exist in the
+ * reference; they cover what the reference exposes only as file-scope globals, plus device
+ * control).  The reference-compatible API is in swgl.h.
+ */
+#ifndef SWGL_B200_H
+#define SWGL_B200_H
+
+#include "swgl.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+{
+	uint64_t draws;            /* draw calls executed since glInit */
+	uint64_t triangles_in;     /* last draw: input triangles */
+	uint64_t prims_out;        /* last draw: triangles after the near clip */
+	uint64_t tested;           /* last draw: fragments evaluated (reference: Barycentric calls) */
+	uint64_t shaded;           /* last draw: fragments that passed the depth test (FS runs) */
+	uint64_t tile_pairs;       /* last draw: (tile, primitive) bin entries */
+	uint64_t bands;            /* last draw: band-entry records */
+} swglStats;
+
+/* The reference keeps depth in GlobalFramebuffer->DepthAttachment (swgl.c:3165) with no
+ * accessor; this returns the pinned host mirror, refreshed like glGetFramePtr. */
+float* swglGetDepthPtr(void);
+
+/* Block until all queued device work is done (the reference is synchronous). */
+void swglFinish(void);
+
+/* "" when no error is pending.  CUDA failures, unsupported-viewport and shader-compile
+ * diagnostics land here; the reference-compatible entry points keep their silent returns. */
+const char* swglGetLastError(void);
+
+/* Fragment / primitive counters of the last draw (synchronises). */
+void swglGetStats(swglStats* out);
+
+/* Select the CUDA device used by the NEXT glInit (default: $LOCAL_RANK, else 0). */
+void swglSetDevice(int ordinal);
+
+/* cudaStream_t (as void*) on which glClear / glDraw* queue their kernels. */
+void* swglGetStream(void);
+
+/* Device addresses of the colour (uint32 [H][W]) and depth (float [H][W]) attachments. */
+uint64_t swglGetColorDevicePtr(void);
+uint64_t swglGetDepthDevicePtr(void);
+
+/* Fill the WHOLE framebuffer (glInit leaves it uninitialised, swgl.c:3720-3723; glClear
+ * only touches the viewport rectangle). */
+void swglFillFramebuffer(uint32_t color_word, float depth);
+
+/* Replace the contents of the buffer bound to `target` (GL_ARRAY_BUFFER or
+ * GL_ELEMENT_ARRAY_BUFFER).  The reference's glBufferData ignores re-specification
+ * (swgl.c:3140); streaming geometry therefore needs this extension.  Size may differ. */
+void swglBufferRespecify(GLenum target, GLsizei size, const void* data);
+
+/* Sort-first sharding: this process rasterises only tile-row bands b with b % n_ranks == rank
+ * (band = band_tile_rows rows of 32-pixel tiles).  Geometry is replicated. */
+void swglSetStripe(GLuint rank, GLuint n_ranks, GLuint band_tile_rows);
+
+/* Peer colour target (device address valid in this process, e.g. from cudaIpcOpenMemHandle):
+ * raster write-back also stores each finished tile row into it.  0 disables. */
+void swglSetPeerColorTarget(uint64_t device_ptr);
+
+/* Tuning / test hooks: "raster_path" (0 auto, 1 pixel-owner, 2 fragment-parallel),
+ * "fuse_clear" (0/1), "count_fragments" (0/1), "nan_canonical" (0/1). */
+void swglSetOption(const char* name, int64_t value);
+int64_t swglGetOption(const char* name);
+
+/* Text dump of a compiled shader's IR and of the shape it was recognised as. Returns the
+ * number of bytes that the full dump needs (excluding the terminator). */
+size_t swglDebugShaderIR(GLuint shader, char* buf, size_t buf_len);
+/* 1 if glCompileShader produced executable IR, 0 if the source is outside the subset. */
+int swglGetShaderCompiled(GLuint shader);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SWGL_B200_H */

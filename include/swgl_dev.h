@@ -1,0 +1,146 @@
+/*
+ * include/swgl_dev.h -- the thin C-ABI device layer under the GL-style entry points.
+ *
+ * The host side of libswgl_b200.so is plain C (swgl_host.c + swgl_glsl.c): it owns the GL
+ * object tables and the shader front-end and reaches CUDA only through the functions below
+ * (plain pointers, sizes and POD structs; no C++ or torch types).  Each function names the
+ * part of the reference's draw path it replaces.
+ *
+ * Applications normally use swgl.h; this header is what a maintainer binds when wiring the
+ * reference's own C file to the CUDA path call by call.
+ */
+#ifndef SWGL_DEV_H
+#define SWGL_DEV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swgldev_ctx swgldev_ctx;   /* one device context: framebuffer + scratch + stream */
+typedef uint64_t swgldev_ptr;             /* device address */
+
+/* One entry per (VAO attribute, matching layout variable) pair, GL_FLOAT attributes only
+ * (reference: attribute fetch, swgl.c:3618-3639). */
+typedef struct
+{
+	uint32_t src_offset;   /* byte offset inside a vertex */
+	uint32_t stride;       /* bytes between vertices (0 = every vertex reads the same bytes) */
+	uint32_t n_floats;     /* floats copied (already clamped to the variable's size) */
+	uint32_t dst_word;     /* destination word in the VS variable file */
+} swgldev_fetch;
+
+/* One linked varying (reference: VertexFragInOut pairs, swgl.c:2983-3005, 3648-3666). */
+typedef struct
+{
+	uint32_t vs_word;      /* VS out variable, word offset in the VS variable file */
+	uint32_t fs_word;      /* FS in variable, word offset in the FS variable file */
+	uint32_t n_floats;     /* 1..4 */
+	uint32_t slot;         /* float offset inside the packed per-vertex varying record */
+	/* SWVS_PASS / SWVS_MATRIX only: the attribute bytes the VS out is a copy of */
+	uint32_t src_offset, src_stride, src_floats;
+	uint32_t _pad;
+} swgldev_varying;
+
+typedef struct
+{
+	swgldev_ptr data;      /* texels: uint8 [h][w][fpp] or float [h][w][fpp]  (swgl.c:2107-2118) */
+	int32_t  width, height;
+	int32_t  fpp;          /* channels per texel, 1..4 (swgl.c:2099-2102) */
+	int32_t  is_float;     /* 0: bytes, converted with /255.0f at sample time; 1: floats */
+	int32_t  wrap_s_repeat, wrap_t_repeat;
+} swgldev_texture;
+
+struct swgl_ir_code;       /* swgl_ir.h */
+
+/* Everything a draw needs, by value: the reference reads the same facts from its globals
+ * (ActiveProgram, ActiveVertexArray, Viewport*, TextureUnits) inside glDrawArrays. */
+typedef struct
+{
+	/* viewport (swgl.c:3151-3154) */
+	int32_t  vx, vy;
+	uint32_t vw, vh;
+	/* geometry */
+	swgldev_ptr vbo;  uint64_t vbo_bytes;
+	swgldev_ptr ibo;  uint64_t ibo_bytes;     /* ibo == 0: glDrawArrays */
+	int32_t  first;                           /* glDrawArrays `first`, or first index (elements) */
+	uint32_t count;                           /* vertices in the stream */
+	uint32_t n_vertices;                      /* indexed: vertices [0, n_vertices) are shaded once */
+	/* program */
+	int32_t  vs_kind, fs_kind;                /* SWVS_*, SWFS_* */
+	const struct swgl_ir_code* vs_code;       /* host pointers; uploaded and cached by the layer */
+	const struct swgl_ir_code* fs_code;
+	uint64_t vs_code_id, fs_code_id;          /* cache keys (unique per compiled shader) */
+	const uint32_t* vs_image; uint32_t vs_words;  /* initial VS variable file (uniforms set) */
+	const uint32_t* fs_image; uint32_t fs_words;
+	uint32_t pos_word;                        /* gl_Position, word offset in the VS file */
+	uint32_t out_word; uint32_t out_floats;   /* first FS `out` variable (swgl.c:3412-3426) */
+	swgldev_fetch   fetch[16];   uint32_t n_fetch;
+	swgldev_varying varying[8];  uint32_t n_varying;
+	uint32_t varying_floats;                  /* packed varying record size, floats */
+	/* SWVS_PASS / SWVS_MATRIX */
+	uint32_t pos_src_offset, pos_src_stride, pos_src_floats;
+	float    pos_matrix[16];                  /* effective row-major matrix, load quirk applied */
+	/* SWFS_VARYING / SWFS_TEXTURE */
+	uint32_t fs_slot;                         /* float offset of the varying the FS consumes */
+	uint32_t fs_slot_floats;
+	uint32_t fs_swz_u, fs_swz_v;              /* component picks for the texture coordinate */
+	int32_t  fs_tex_unit;
+	swgldev_texture tex[8];                   /* texture units (swgl.c:2035) */
+} swgldev_draw;
+
+typedef struct
+{
+	uint64_t draws;
+	uint64_t triangles_in;     /* input triangles of the last draw */
+	uint64_t prims_out;        /* after near clip */
+	uint64_t tested;           /* fragments evaluated (Barycentric calls in the reference) */
+	uint64_t shaded;           /* fragments that passed the depth test */
+	uint64_t tile_pairs;       /* (tile, primitive) bin entries */
+	uint64_t bands;            /* band-entry records */
+} swgldev_stats;
+
+/* context ------------------------------------------------------------------------------ */
+/* glInit (swgl.c:3713-3736): device = CUDA ordinal, or -1 for the current / LOCAL_RANK one. */
+swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height);
+void         swgldev_destroy(swgldev_ctx* c);
+const char*  swgldev_last_error(swgldev_ctx* c);      /* "" when none; sticky until read */
+void*        swgldev_stream(swgldev_ctx* c);          /* cudaStream_t all work is queued on */
+int          swgldev_sync(swgldev_ctx* c);
+
+/* memory: glBufferData / glTexImage2D copies (swgl.c:3142-3144, 2107-2118) ---------------- */
+swgldev_ptr  swgldev_alloc(swgldev_ctx* c, uint64_t bytes);
+int          swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes);
+void         swgldev_free(swgldev_ctx* c, swgldev_ptr p);
+
+/* glClear (swgl.c:3183-3214): rectangle is viewport ∩ framebuffer, already resolved. */
+int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,
+                  int32_t x0, int32_t y0, int32_t x1, int32_t y1);
+
+/* glDrawArrays(GL_TRIANGLES) / glDrawElements (swgl.c:3609-3710 + DrawTriangle 3314-3473). */
+int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d);
+
+/* glGetFramePtr (swgl.c:3738): refreshes and returns the pinned host mirror. */
+uint32_t* swgldev_map_color(swgldev_ctx* c);
+float*    swgldev_map_depth(swgldev_ctx* c);
+swgldev_ptr swgldev_color_devptr(swgldev_ctx* c);
+swgldev_ptr swgldev_depth_devptr(swgldev_ctx* c);
+void      swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth); /* whole framebuffer */
+
+void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out);
+
+/* sort-first stripes: this context rasterises only tile rows r with (r / band_rows) % n == rank */
+void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_t band_tile_rows);
+/* peer colour target: finished tiles are also stored to this (peer-mapped) colour buffer */
+void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color);
+/* tuning / test hooks */
+void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value);
+int64_t swgldev_get_option(swgldev_ctx* c, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SWGL_DEV_H */

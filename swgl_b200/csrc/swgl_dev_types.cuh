@@ -1,0 +1,112 @@
+/*
+ * swgl_dev_types.cuh -- device-side data layout shared by the kernels of swgl_dev.cu.
+ *
+ * HBM layout of one draw (all scratch is grow-only and reused across draws):
+ *
+ *   clip[V]            float4   clip-space gl_Position of every shaded vertex
+ *   vary[V + 2T][NVF]  float    packed varyings; the last 2T records are the vertices the near
+ *                               clipper creates (at most two per input triangle)
+ *   prims[2T]          64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
+ *                               record ids; slot 2t+k keeps submission order
+ *   prim_band[2T]      uint2    first band-entry index, topmost tile row  (x = 0xffffffff: dead)
+ *   bands[...]         16 B     per (primitive, tile row): span-walk state (x0, x1) on entering the
+ *                               row band + the tile-column range the walk touches there
+ *   tile_count/off[Nt] u32      bin sizes / exclusive scan
+ *   pairs[...]         u32      per-tile primitive lists (unordered; sorted in the raster CTA)
+ *   color/depth[H][W]  u32/f32  the framebuffer, row 0 = top (swgl.c:3156-3166)
+ */
+#ifndef SWGL_DEV_TYPES_CUH
+#define SWGL_DEV_TYPES_CUH
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "swgl_dev.h"
+#include "swgl_ir.h"
+
+#define SWGL_TILE        32
+#define SWGL_TILE_SHIFT  5
+#define SWGL_RASTER_THREADS 256
+#define SWGL_BATCH       256      /* primitives staged per raster batch */
+#define SWGL_SORT_CAP    2048     /* tile lists up to this length are sorted in shared memory */
+#define SWGL_CTR_SLOTS   64
+
+struct Prim
+{
+	float4   v[3];      /* (float)X, (float)Y, clip z, clip w -- submission order (swgl.c:3688-3691) */
+	uint32_t vid[3];    /* varying record of each vertex */
+	uint32_t pad;
+};
+
+struct BandEntry
+{
+	float    x0, x1;    /* walk state before the first row of the band (swgl.c:3351-3356) */
+	uint32_t prim;
+	uint32_t cols;      /* first tile column | last tile column << 16; 0xffffffff = touches nothing */
+};
+
+struct Counters
+{
+	uint32_t band_cursor;       /* band entries requested */
+	uint32_t pair_total;        /* bin entries requested */
+	uint32_t overflow;          /* 1: scratch too small, draw dropped (re-issued by the host) */
+	uint32_t prims_out;
+	unsigned long long tested[SWGL_CTR_SLOTS];
+	unsigned long long shaded[SWGL_CTR_SLOTS];
+};
+
+struct DevTex
+{
+	const void* data;
+	int32_t w, h, fpp, is_float, rep_s, rep_t;
+};
+
+struct ClearParams
+{
+	uint32_t flags;             /* bit0 colour, bit1 depth; 0 = nothing pending */
+	uint32_t word;
+	int32_t  x0, y0, x1, y1;    /* framebuffer rectangle, rows NOT flipped (swgl.c:3193-3209) */
+};
+
+struct DrawParams
+{
+	/* framebuffer */
+	uint32_t* color; float* depth; uint32_t* peer_color;
+	uint32_t W, H;
+	/* viewport and derived constants */
+	int32_t vx, vy; uint32_t vw, vh;
+	float hw, hh;               /* (float)(VW/2u), (float)(VH/2u)            swgl.c:3685-3686 */
+	float fvx, fvy;             /* (float)VX, (float)VY */
+	float xlimit, ylimit;       /* (float)(uint32)(VX+VW), (float)(uint32)(VY+VH) */
+	int32_t ytop;               /* VH-1+2*VY: storage row = ytop - y           swgl.c:3386 */
+	uint32_t tiles_x, tiles_y;
+	uint32_t rank, n_ranks, band_rows;
+	/* geometry */
+	const uint8_t* vbo; unsigned long long vbo_bytes;
+	const uint32_t* ibo; unsigned long long ibo_count;
+	int32_t first; uint32_t count, ntri, n_shade;
+	/* scratch */
+	float4* clip; float* vary; uint32_t nvf; uint32_t clip_vid_base;
+	Prim* prims; uint2* prim_band; BandEntry* bands; uint32_t cap_bands;
+	uint32_t* tile_count; uint32_t* tile_off; uint32_t* pairs; uint32_t cap_pairs;
+	Counters* ctr;
+	/* shaders */
+	int32_t vs_kind, fs_kind;
+	const swgl_ir_op* vs_ops; uint32_t vs_nops; uint32_t vs_words;
+	const swgl_ir_op* fs_ops; uint32_t fs_nops; uint32_t fs_words;
+	uint32_t pos_word, out_word, out_floats;
+	swgldev_fetch fetch[SWGL_MAX_FETCH]; uint32_t n_fetch;
+	swgldev_varying varying[8]; uint32_t n_varying;
+	uint32_t pos_src_offset, pos_src_stride, pos_src_floats;
+	float pos_matrix[16];
+	uint32_t fs_slot, fs_slot_floats, fs_swz_u, fs_swz_v; int32_t fs_tex_unit;
+	DevTex tex[SWGL_MAX_TEX_UNITS];
+	/* fused clear */
+	ClearParams clear;
+	uint32_t count_fragments;
+	/* initial variable files (uniform values) for the generic evaluator */
+	uint32_t vs_image[SWGL_MAX_VAR_WORDS];
+	uint32_t fs_image[SWGL_MAX_VAR_WORDS];
+};
+
+#endif
