@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the swgl draw-call path on B200.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # CUDA path (this repo)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's CPU path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one frame of the workload: glClear(COLOR|DEPTH) + one indexed draw of BASELINE
+config 4 (4K, 1,002,528 small depth-tested triangles) unless --config says otherwise.
+
+Own arm, one JSON line on rank 0:
+  value        triangles/s with every input resident in HBM; per-step CUDA events on the
+               library's stream, L2 flushed (256 MiB write) between steps, max over ranks
+  e2e          the same frame through the C ABI with HOST buffers: pinned vertex/index arrays
+               re-specified every step (H2D), clear + draw, glGetFramePtr (D2H of the image)
+  roofline     dominant kernel (k_raster): algorithmic bytes per launch (W*H*8: colour + depth
+               written once with the clear fused) / its CUDA-event duration,
+               against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the unmodified reference (oracle/_ref) on one host core, bounded sample
+N > 1: sort-first by tile-row bands; geometry replicated; every rank stores its finished tiles
+straight into rank 0's colour buffer over NVLink (CUDA IPC peer mapping), torch.distributed
+(NCCL) provides the barriers and the max-over-ranks reduction.  Same frame at every N
+(strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "triangles/s"
+STAGES = ["k_vertex", "k_setup_bin", "k_scan_tiles", "k_fill_bins", "k_raster"]
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        with open(self.tmp.name) as f:
+            rows = [r.strip().split(",") for r in f if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, n in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return dist, rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    import swgl_b200 as sw
+    from swgl_b200 import gl as G, scenes as S
+    from swgl_b200 import multigpu
+
+    dist, rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    api = sw.load()
+    scene = S.config(args.config)
+    api.swglSetDevice(local)
+    api.glInit(scene.width, scene.height)
+    err = api.swglGetLastError().decode()
+    if err:
+        raise RuntimeError(f"swgl_b200: {err}")  # no CPU fallback: fail loudly
+    st = G.setup_scene(api, scene, indexed=True, init=False)
+    n_draw = st["n_draw"]
+    n_tris = scene.n_triangles
+
+    band_rows = 1
+    peer = None
+    if world > 1:
+        tiles_y = (scene.height + 31) // 32
+        band_rows = max(1, tiles_y // (world * 8))   # >= 8 interleaved bands per rank
+        api.swglSetStripe(rank, world, band_rows)
+        peer = multigpu.PeerColorTarget(api, dist, rank, world)
+
+    stream = torch.cuda.ExternalStream(api.swglGetStream(), device=torch.device("cuda", local))
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=f"cuda:{local}")
+
+    def frame():
+        api.glClear(G.GL_COLOR_BUFFER_BIT | G.GL_DEPTH_BUFFER_BIT)
+        api.glDrawElements(G.GL_TRIANGLES, n_draw, G.GL_UNSIGNED_INT, None)
+
+    def barrier():
+        api.swglFinish()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    barrier()
+    launches0 = api.swglGetOption(b"kernel_launches")
+
+    # ---- value: device-resident frames, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        a.record(stream)
+        frame()
+        b.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = api.swglGetOption(b"kernel_launches") - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_tris / (ms_per_step * 1e-3)
+
+    stats = sw.swglStats()
+    api.swglGetStats(C.byref(stats))
+    sd = stats.as_dict()
+    shaded, tested = sd["shaded"], sd["tested"]
+    if dist is not None:
+        t = torch.tensor([shaded, tested], device=f"cuda:{local}", dtype=torch.int64)
+        dist.all_reduce(t)
+        shaded, tested = int(t[0].item()), int(t[1].item())
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA events inside the library ----
+    api.swglSetOption(b"stage_timing", 1)
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        frame()
+    api.swglFinish()
+    nd = max(1, api.swglGetOption(b"stage_draws"))
+    stage_us = {n: api.swglGetOption(f"stage_ns_{i}".encode()) / 1e3 / nd for i, n in enumerate(STAGES)}
+    api.swglSetOption(b"stage_timing", 0)
+    peak, peak_src = measured_peaks()
+    dom = max(stage_us, key=stage_us.get)
+    fb_bytes = scene.width * scene.height * 8 // world
+    dom_bytes = fb_bytes if dom == "k_raster" else scene.algorithmic_bytes()
+    achieved = dom_bytes / (stage_us[dom] * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj.get(f"C{args.config}", {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes,
+                "kernel_us": stage_us[dom], "stage_us": stage_us,
+                "frame_algorithmic_bytes": scene.algorithmic_bytes(),
+                "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    verts = torch.from_numpy(np.ascontiguousarray(scene.vertices)).pin_memory()
+    idx = torch.from_numpy(np.ascontiguousarray(scene.indices).view(np.int32)).pin_memory()
+
+    def e2e_step():
+        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.numel() * 4, C.c_void_p(verts.data_ptr()))
+        api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.numel() * 4, C.c_void_p(idx.data_ptr()))
+        frame()
+        if dist is not None:
+            api.swglFinish()
+            dist.barrier()
+        if rank == 0:
+            api.glGetFramePtr()   # sync + D2H of the assembled colour image into the pinned mirror
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": n_tris / e2e_s, "unit": METRIC, "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(verts.numel() * 4 + idx.numel() * 4) * world,
+           "d2h_bytes_per_step": scene.width * scene.height * 4}
+
+    # ---- CPU baseline: the unmodified reference on one host core, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(scene, target_seconds=12.0)
+
+    if peer is not None:
+        peer.close()
+    err = api.swglGetLastError().decode()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": S.CONFIG_NAMES[args.config], "triangles": n_tris,
+                       "framebuffer": f"{scene.width}x{scene.height} RGBA8 + f32 depth",
+                       "l2": "flushed between steps (256 MiB write, untimed)",
+                       "parallelism": f"sort-first tile-row bands x{world}" + (f", band={band_rows} tile rows, peer stores to rank 0" if world > 1 else "")},
+            "shaded_fragments_per_s": shaded / (ms_per_step * 1e-3),
+            "tested_fragments_per_s": tested / (ms_per_step * 1e-3),
+            "frame_ms": ms_per_step, "shaded_fragments": shaded, "tested_fragments": tested,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if err:
+            line["error"] = err
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _timed_cpu(scene, tris, ref, O):
+    import copy
+
+    sample = copy.copy(scene)
+    if scene.indices is not None:
+        sample.indices = scene.indices[: 3 * tris]
+    else:
+        sample.vertices = scene.vertices[: 3 * tris]
+    if ref is not None:
+        return ref.timed_frame(sample)
+    dt, _ = O.Restatement().timed_frame(sample)
+    return dt, None
+
+
+def cpu_reference_sample(scene, target_seconds: float, tris: int | None = None, reps: int | None = None):
+    """Time the compiled reference (oracle/_ref; else the C port) on one host core.
+
+    The sample is the first `tris` triangles of the workload drawn into the full-size
+    framebuffer (glClear + glDrawArrays), repeated `reps` times; both are sized from a short
+    calibration draw so the whole call costs about `target_seconds` of CPU work."""
+    from oracle import pyoracle as O
+
+    kind = "reference"
+    try:
+        ref = O.Reference()
+    except Exception:
+        ref = None
+        kind = "port"
+    n_tris = scene.n_triangles
+    if tris is None:
+        cal = min(n_tris, 20000)
+        dt, _ = _timed_cpu(scene, cal, ref, O)
+        rate = cal / max(dt, 1e-6)
+        tris = int(min(n_tris, max(2000, target_seconds * rate)))
+        reps = max(1, int(round(target_seconds / (tris / rate)))) if reps is None else reps
+    reps = reps or 1
+    times, clear_s = [], None
+    for _ in range(reps):
+        dt, clear_s = _timed_cpu(scene, tris, ref, O)
+        times.append(dt)
+    dt = statistics.mean(times)
+    return {"value": tris / dt, "unit": METRIC, "cores": 1, "kind": kind,
+            "sample": f"first {tris} of {n_tris} triangles of the same scene, full-size framebuffer, "
+                      f"glClear+glDrawArrays x{reps} (mean {dt:.2f} s per frame, clear {clear_s if clear_s is None else round(clear_s, 3)} s)",
+            "seconds": dt, "tris": tris, "reps": reps, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from swgl_b200 import scenes as S
+
+    scene = S.config(args.config)
+    total = max(1, args.steps + args.warmup)
+    cal = cpu_reference_sample(scene, 0.0, tris=min(scene.n_triangles, 20000), reps=1)
+    budget = 90.0 / total                                   # whole run about 1.5 minutes
+    tris = int(min(scene.n_triangles, max(2000, budget * cal["value"])))
+    res = None
+    times = []
+    for i in range(total):
+        res = cpu_reference_sample(scene, 0.0, tris=tris, reps=1)
+        if i >= args.warmup:
+            times.append(res["seconds"])
+    dt = statistics.mean(times)
+    value = tris / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": S.CONFIG_NAMES[args.config], "triangles": scene.n_triangles,
+                   "framebuffer": f"{scene.width}x{scene.height} RGBA8 + f32 depth"},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": 1, "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", type=int, default=4, help="BASELINE.json config 1..5 (default 4: 4K, 1M triangles)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,8 +64,17 @@ void swglSetStripe(GLuint rank, GLuint n_ranks, GLuint band_tile_rows);
  * raster write-back also stores each finished tile row into it.  0 disables. */
 void swglSetPeerColorTarget(uint64_t device_ptr);
 
+/* CUDA IPC plumbing for the peer colour target (one process per GPU): rank 0 exports its colour
+ * attachment as a 64-byte handle, the other ranks open it and pass the address to
+ * swglSetPeerColorTarget.  Return 0 / an address on success. */
+int      swglIpcExportColor(void* handle64);
+uint64_t swglIpcOpen(const void* handle64);
+void     swglIpcClose(uint64_t device_ptr);
+
 /* Tuning / test hooks: "raster_path" (0 auto, 1 pixel-owner, 2 fragment-parallel),
- * "fuse_clear" (0/1), "count_fragments" (0/1), "nan_canonical" (0/1). */
+ * "fuse_clear" (0/1), "count_fragments" (0/1), "stage_timing" (0/1: per-kernel CUDA-event timing, synchronous);
+ * read-only: "kernel_launches", "stage_ns_0".."stage_ns_4" (vertex, setup+bin, scan, fill,
+ * raster), "stage_draws", "tile_size", "device". */
 void swglSetOption(const char* name, int64_t value);
 int64_t swglGetOption(const char* name);
 

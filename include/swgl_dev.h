@@ -135,6 +135,11 @@ void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out);
 void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_t band_tile_rows);
 /* peer colour target: finished tiles are also stored to this (peer-mapped) colour buffer */
 void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color);
+/* CUDA IPC for the peer colour target: export this context's colour attachment (64-byte
+ * cudaIpcMemHandle_t), open / close a handle exported by another process */
+int         swgldev_ipc_export_color(swgldev_ctx* c, void* handle64);
+swgldev_ptr swgldev_ipc_open(swgldev_ctx* c, const void* handle64);
+void        swgldev_ipc_close(swgldev_ctx* c, swgldev_ptr p);
 /* tuning / test hooks */
 void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value);
 int64_t swgldev_get_option(swgldev_ctx* c, const char* name);

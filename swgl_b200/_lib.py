@@ -38,6 +38,9 @@ EXTENSION_EXPORTS = {
     "swglBufferRespecify": (None, [C.c_uint32, C.c_uint32, C.c_void_p]),
     "swglSetStripe": (None, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "swglSetPeerColorTarget": (None, [C.c_uint64]),
+    "swglIpcExportColor": (C.c_int, [C.c_void_p]),
+    "swglIpcOpen": (C.c_uint64, [C.c_void_p]),
+    "swglIpcClose": (None, [C.c_uint64]),
     "swglSetOption": (None, [C.c_char_p, C.c_int64]),
     "swglGetOption": (C.c_int64, [C.c_char_p]),
     "swglDebugShaderIR": (C.c_size_t, [C.c_uint32, C.c_char_p, C.c_size_t]),

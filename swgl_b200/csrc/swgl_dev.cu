@@ -67,7 +67,11 @@ struct swgldev_ctx
 	int last_raster_path;
 
 	/* options */
-	int opt_fuse_clear, opt_count_fragments, opt_raster_path;
+	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing;
+	uint64_t n_launches;                 /* kernels launched since creation */
+	cudaEvent_t stage_ev[8];
+	double stage_us[8];                  /* accumulated per-stage device time (stage timing mode) */
+	uint64_t stage_draws;
 
 	swgldev_stats stats;
 	uint64_t n_draws;
@@ -761,7 +765,9 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
 	c->tile_count = nullptr; c->tile_off = nullptr; c->ctr = nullptr; c->h_ctr = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
-	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0;
+	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0;
+	c->n_launches = 0; c->stage_draws = 0;
+	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->n_draws = 0; c->error[0] = 0;
@@ -778,6 +784,9 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMalloc((void**)&c->ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->ctr_event, cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreate(&c->stage_ev[0]) == cudaSuccess && cudaEventCreate(&c->stage_ev[1]) == cudaSuccess
+	       && cudaEventCreate(&c->stage_ev[2]) == cudaSuccess && cudaEventCreate(&c->stage_ev[3]) == cudaSuccess
+	       && cudaEventCreate(&c->stage_ev[4]) == cudaSuccess && cudaEventCreate(&c->stage_ev[5]) == cudaSuccess
 	       && cudaMemset(c->tile_count, 0, (ntiles + 1) * 4) == cudaSuccess
 	       && cudaMemset(c->ctr, 0, sizeof(Counters)) == cudaSuccess;
 	if (!ok)
@@ -812,6 +821,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->bands) cudaFree(c->bands);
 	if (c->pairs) cudaFree(c->pairs);
 	if (c->ctr_event) cudaEventDestroy(c->ctr_event);
+	for (int i = 0; i < 8; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	cudaGetLastError();
 	delete c;
@@ -896,6 +906,7 @@ static int flush_clear(swgldev_ctx* c)
 	if (cp.x1 <= cp.x0 || cp.y1 <= cp.y0) return 0;
 	dim3 block(128), grid(((uint32_t)(cp.x1 - cp.x0) + 511u) / 512u, (uint32_t)(cp.y1 - cp.y0));
 	k_clear<<<grid, block, 0, c->stream>>>(c->color, c->depth, c->W, cp);
+	c->n_launches++;
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -958,20 +969,40 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	P.bands = c->bands; P.pairs = c->pairs;
 	c->last_draw = P; c->last_draw_valid = 1;
 
+	const bool timing = c->opt_stage_timing != 0;
+#define STAGE(i) do { if (timing) cudaEventRecord(c->stage_ev[i], c->stream); } while (0)
 	const uint32_t vb = (P.n_shade + 255u) / 256u;
+	STAGE(0);
 	if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	STAGE(1);
 	k_setup_bin<<<(P.ntri + 127u) / 128u, 128, 0, c->stream>>>(P);
+	STAGE(2);
 	k_scan_tiles<<<1, 1024, 0, c->stream>>>(P);
+	STAGE(3);
 	CK(cudaMemcpyAsync(c->h_ctr, c->ctr, 16, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaEventRecord(c->ctr_event, c->stream));
 	c->ctr_pending = 1;
 	k_fill_bins<<<148 * 8, 256, 0, c->stream>>>(P);
+	STAGE(4);
 	if (P.fs_kind == SWFS_VARYING) launch_raster<SWFS_VARYING>(c, P);
 	else if (P.fs_kind == SWFS_TEXTURE) launch_raster<SWFS_TEXTURE>(c, P);
 	else launch_raster<SWFS_GENERIC>(c, P);
+	STAGE(5);
+#undef STAGE
+	c->n_launches += 5;
 	CK(cudaGetLastError());
+	if (timing)
+	{
+		CK(cudaEventSynchronize(c->stage_ev[5]));
+		for (int i = 0; i < 5; i++)
+		{
+			float ms = 0.0f;
+			if (cudaEventElapsedTime(&ms, c->stage_ev[i], c->stage_ev[i + 1]) == cudaSuccess) c->stage_us[i] += 1000.0 * ms;
+		}
+		c->stage_draws++;
+	}
 	return 0;
 }
 
@@ -1110,12 +1141,43 @@ void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color)
 	c->peer_color = (uint32_t*)(uintptr_t)peer_color;
 }
 
+int swgldev_ipc_export_color(swgldev_ctx* c, void* handle64)
+{
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, c->color));
+	memcpy(handle64, &h, sizeof(h));
+	return 0;
+}
+
+swgldev_ptr swgldev_ipc_open(swgldev_ctx* c, const void* handle64)
+{
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	void* p = nullptr;
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) { set_err(c, "cudaIpcOpenMemHandle", e); return 0; }
+	return (swgldev_ptr)(uintptr_t)p;
+}
+
+void swgldev_ipc_close(swgldev_ctx* c, swgldev_ptr p)
+{
+	swgldev_sync(c);
+	if (c->peer_color == (uint32_t*)(uintptr_t)p) c->peer_color = nullptr;
+	cudaIpcCloseMemHandle((void*)(uintptr_t)p);
+}
+
 void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 {
 	swgldev_sync(c);
 	if (!strcmp(name, "fuse_clear")) c->opt_fuse_clear = (int)value;
 	else if (!strcmp(name, "count_fragments")) c->opt_count_fragments = (int)value;
 	else if (!strcmp(name, "raster_path")) c->opt_raster_path = (int)value;
+	else if (!strcmp(name, "stage_timing"))
+	{
+		c->opt_stage_timing = (int)value;
+		for (int i = 0; i < 8; i++) c->stage_us[i] = 0.0;
+		c->stage_draws = 0;
+	}
 }
 
 int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
@@ -1125,6 +1187,10 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "raster_path")) return c->opt_raster_path;
 	if (!strcmp(name, "last_raster_path")) return c->last_raster_path;
 	if (!strcmp(name, "tile_size")) return SWGL_TILE;
+	if (!strcmp(name, "kernel_launches")) return (int64_t)c->n_launches;
+	if (!strcmp(name, "stage_draws")) return (int64_t)c->stage_draws;
+	if (!strncmp(name, "stage_ns_", 9)) { int i = atoi(name + 9); return (i >= 0 && i < 5) ? (int64_t)(c->stage_us[i] * 1000.0) : -1; }
+	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "sizeof_draw_params")) return (int64_t)sizeof(DrawParams);
 	return -1;
 }

@@ -216,6 +216,9 @@ uint64_t swglGetDepthDevicePtr(void) { return G.dev ? swgldev_depth_devptr(G.dev
 void swglFillFramebuffer(uint32_t color_word, float depth) { if (G.dev) swgldev_fill(G.dev, color_word, depth); }
 void swglSetStripe(GLuint rank, GLuint n_ranks, GLuint band_tile_rows) { if (G.dev) swgldev_set_stripe(G.dev, rank, n_ranks, band_tile_rows); }
 void swglSetPeerColorTarget(uint64_t p) { if (G.dev) swgldev_set_peer_color(G.dev, p); }
+int swglIpcExportColor(void* handle64) { return G.dev ? swgldev_ipc_export_color(G.dev, handle64) : -1; }
+uint64_t swglIpcOpen(const void* handle64) { return G.dev ? swgldev_ipc_open(G.dev, handle64) : 0; }
+void swglIpcClose(uint64_t p) { if (G.dev) swgldev_ipc_close(G.dev, p); }
 void swglSetOption(const char* name, int64_t value) { if (G.dev) swgldev_set_option(G.dev, name, value); }
 int64_t swglGetOption(const char* name) { return G.dev ? swgldev_get_option(G.dev, name) : -1; }
 

@@ -184,6 +184,18 @@ def setup_scene(gl: GLApi, scene, *, indexed: bool, init: bool = True):
             m = np.ascontiguousarray(scene.matrix, np.float32)
             gl.glUniformMatrix4fv(loc, 1, GL_FALSE, m.ctypes.data_as(C.POINTER(_f32)))
 
+    for name, (kind, vals) in getattr(scene, "uniforms", {}).items():
+        loc = gl.glGetUniformLocation(prog, name.encode())
+        if loc < 0:
+            continue
+        if kind == "1i":
+            gl.glUniform1i(loc, int(vals[0]))
+        elif kind in ("1f", "2f", "3f", "4f"):
+            getattr(gl, "glUniform" + kind)(loc, *[float(v) for v in vals])
+        else:
+            m = np.ascontiguousarray(vals, np.float32)
+            getattr(gl, f"glUniformMatrix{kind[1]}fv")(loc, 1, GL_FALSE, m.ctypes.data_as(C.POINTER(_f32)))
+
     vp = scene.viewport or (0, 0, scene.width, scene.height)
     gl.glViewport(*vp)
     gl.glClearColor(*scene.clear_color)

@@ -1,0 +1,122 @@
+"""Sort-first multi-GPU plumbing: one process per GPU, torch.distributed for the control plane.
+
+The frame is split by tile-row bands dealt round-robin to the ranks (``swglSetStripe``);
+geometry is replicated, so there is no exchange until the image is assembled on rank 0.
+Two ways to assemble it:
+
+* ``PeerColorTarget`` -- rank 0 exports its colour attachment through CUDA IPC, every other rank
+  maps it and the raster kernel's 128-bit write-back stores each finished strip straight into
+  rank 0's framebuffer over NVLink (the collective is fused into the kernel epilogue; only a
+  barrier remains);
+* ``gather_color`` -- plain NCCL: every rank contributes its band rows, rank 0 receives them
+  (the baseline the fused variant is measured against).
+
+``owner_of_tile_row`` is the pure partition function; CPU tests exercise it with gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+TILE = 32
+
+
+def owner_of_tile_row(tile_row: int, n_ranks: int, band_tile_rows: int) -> int:
+    """Rank that rasterises ``tile_row`` (mirrors owns_tile_row() in swgl_dev.cu)."""
+    return (tile_row // max(1, band_tile_rows)) % max(1, n_ranks)
+
+
+def rows_of_rank(height: int, rank: int, n_ranks: int, band_tile_rows: int):
+    """Framebuffer row ranges [(r0, r1), ...] owned by ``rank`` (storage rows, row 0 = top)."""
+    tiles_y = (height + TILE - 1) // TILE
+    out = []
+    for tr in range(tiles_y):
+        if owner_of_tile_row(tr, n_ranks, band_tile_rows) != rank:
+            continue
+        r0, r1 = tr * TILE, min(height, (tr + 1) * TILE)
+        if out and out[-1][1] == r0:
+            out[-1] = (out[-1][0], r1)
+        else:
+            out.append((r0, r1))
+    return out
+
+
+def assemble(stripes, height: int, width: int, n_ranks: int, band_tile_rows: int) -> np.ndarray:
+    """Host-side assembly of per-rank full-size images into one (what the collective computes)."""
+    out = np.zeros((height, width), dtype=stripes[0].dtype)
+    for r in range(n_ranks):
+        for r0, r1 in rows_of_rank(height, r, n_ranks, band_tile_rows):
+            out[r0:r1] = stripes[r][r0:r1]
+    return out
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def color_tensor(api, height: int, width: int, device):
+    """torch view (int32 [H, W]) of the library's colour attachment -- no copy."""
+    import torch
+
+    return torch.as_tensor(_DevArray(api.swglGetColorDevicePtr(), (height, width), "<i4"), device=device)
+
+
+class PeerColorTarget:
+    """Map rank 0's colour attachment into every other rank and make it their store target."""
+
+    def __init__(self, api, dist, rank: int, world: int):
+        self.api, self.rank, self.ptr = api, rank, 0
+        handle = (C.c_ubyte * 64)()
+        if rank == 0:
+            rc = api.swglIpcExportColor(handle)
+            if rc != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed: " + api.swglGetLastError().decode())
+        box = [bytes(handle)]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            buf = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            self.ptr = api.swglIpcOpen(buf)
+            if not self.ptr:
+                raise RuntimeError("cudaIpcOpenMemHandle failed: " + api.swglGetLastError().decode())
+            api.swglSetPeerColorTarget(self.ptr)
+        dist.barrier()
+
+    def close(self):
+        if self.ptr:
+            self.api.swglSetPeerColorTarget(0)
+            self.api.swglIpcClose(self.ptr)
+            self.ptr = 0
+
+
+def gather_rows(img, dist, rank: int, world: int, height: int, band_tile_rows: int):
+    """Assemble the band rows of every rank into ``img`` on rank 0 (grouped send/recv).
+
+    ``img`` is a [H, W] tensor on any device torch.distributed can move (CUDA with NCCL, CPU
+    with gloo); rank 0's own rows are already in place."""
+    ops = []
+    if rank == 0:
+        for r in range(1, world):
+            for r0, r1 in rows_of_rank(height, r, world, band_tile_rows):
+                ops.append(dist.P2POp(dist.irecv, img[r0:r1], r))
+    else:
+        for r0, r1 in rows_of_rank(height, rank, world, band_tile_rows):
+            ops.append(dist.P2POp(dist.isend, img[r0:r1], 0))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return img
+
+
+def gather_color(api, dist, rank: int, world: int, height: int, width: int, band_tile_rows: int, device):
+    """NCCL assembly on rank 0, in place in the library's colour attachment."""
+    import torch
+
+    img = color_tensor(api, height, width, device)
+    api.swglFinish()
+    gather_rows(img, dist, rank, world, height, band_tile_rows)
+    torch.cuda.synchronize()
+    return img

@@ -107,6 +107,7 @@ class Scene:
     matrix: Optional[np.ndarray] = None  # float32 [16] handed to glUniformMatrix4fv(GL_FALSE)
     viewport: Optional[tuple] = None  # (x, y, w, h); default = full framebuffer
     clear_color: tuple = (0.0, 0.0, 0.0, 1.0)
+    uniforms: dict = field(default_factory=dict)  # name -> ("1f"|"2f"|"3f"|"4f"|"1i"|"m2"|"m3"|"m4", values)
     meta: dict = field(default_factory=dict)
 
     @property

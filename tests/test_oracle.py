@@ -1,0 +1,71 @@
+"""CPU: pin the C restatement (oracle/swgl_oracle.c) against the compiled, unmodified reference
+and against golden hashes (tests/golden/oracle_kats.json, produced by tests/golden/make_golden.py
+from the compiled reference; K0/K1/K2 also equal SURVEY.md appendix C)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from swgl_b200 import scenes as S
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_kats.json")
+
+
+def golden_scenes():
+    sc = {
+        "k0_single": S.single_triangle(),
+        "k1_config1": S.random_triangles(),
+        "k2_config1_tex": S.random_triangles(textured=True),
+        "near_clip_alpha": S.random_triangles(2000, near_cross=True, alpha=None, centre_range=1.3, seed=7),
+        "grid32": S.grid_mesh(32, 320, 200),
+        "grid32_tex": S.grid_mesh(32, 320, 200, textured=True),
+        "grid40_matrix_a05": S.grid_mesh(40, 333, 211, alpha=0.5, use_matrix=True),
+    }
+    vp = S.random_triangles(1500, near_cross=True, alpha=None, centre_range=1.3, seed=99)
+    vp.viewport = (37, 11, 301, 257)
+    sc["viewport_37_11"] = vp
+    return sc
+
+
+with open(GOLDEN) as f:
+    KATS = json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(KATS))
+def test_restatement_matches_golden(restatement, name):
+    scene = golden_scenes()[name]
+    col, dep, stats = restatement.render(scene)
+    k = KATS[name]
+    assert f"{restatement.fnv(col):016x}" == k["color_fnv"]
+    assert f"{restatement.fnv(dep):016x}" == k["depth_fnv"]
+    assert int((dep.view(np.uint32) != 0).sum()) == k["covered"]
+    assert stats["tested"] == k["tested"] and stats["shaded"] == k["shaded"]
+
+
+@pytest.mark.parametrize("name", ["k0_single", "k1_config1", "near_clip_alpha", "grid32_tex", "viewport_37_11"])
+def test_restatement_matches_compiled_reference(restatement, reference, name):
+    scene = golden_scenes()[name]
+    c1, d1, _ = restatement.render(scene)
+    c2, d2 = reference.render(scene)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+
+
+def test_survey_kats():
+    """SURVEY.md appendix C values, measured independently during the survey."""
+    assert KATS["k0_single"]["color_fnv"] == "5e2ecfac3685e7ef" and KATS["k0_single"]["covered"] == 1008
+    assert KATS["k1_config1"]["color_fnv"] == "c448a459df88d572"
+    assert KATS["k1_config1"]["depth_fnv"] == "00fd259510614c5e"
+    assert KATS["k1_config1"]["covered"] == 304414
+    assert KATS["k1_config1"]["tested"] == 1878617 and KATS["k1_config1"]["shaded"] == 723510
+    assert KATS["k2_config1_tex"]["color_fnv"] == "ebe51dc3610b6c83"
+
+
+def test_no_clear_and_partial_draw(restatement, reference):
+    scene = S.random_triangles(300, 320, 240, seed=5, alpha=0.5)
+    c1, d1, _ = restatement.render(scene, clear=False, fill=(0x80402010, 0.0), first=30, count=600)
+    c2, d2 = reference.render(scene, clear=False, fill=(0x80402010, 0.0), first=30, count=600)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
