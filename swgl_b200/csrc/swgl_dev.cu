@@ -424,34 +424,27 @@ __global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ DrawP
 struct FragIn
 {
 	float u, v, w;                /* perspective-corrected weights */
-	uint32_t vid0, vid1, vid2;    /* varying records */
-	const float* sv;              /* staged varyings of the primitive in shared memory (fast shapes) */
-	uint32_t sv_stride;
+	uint32_t vid0, vid1, vid2;    /* varying records (generic shape) */
+	/* fast shapes: the varying the shader consumes, per vertex; component k is at [k * stride]
+	 * (stride 1 = straight from the packed records, SWGL_BATCH = staged in shared memory) */
+	const float* a; const float* b; const float* c;
+	uint32_t stride;
 };
+
+/* InterpolateLinearEx (swgl.c:3270-3297): a*u + b*v + c*w, left to right */
+__device__ __forceinline__ float lerp3(const FragIn& f, uint32_t k)
+{
+	return f.a[k * f.stride] * f.u + f.b[k * f.stride] * f.v + f.c[k * f.stride] * f.w;
+}
 
 template <int FS>
 __device__ __forceinline__ float4 run_fragment(const DrawParams& P, const FragIn& f)
 {
-	if (FS == SWFS_VARYING)
-	{
-		/* InterpolateLinearEx (swgl.c:3270-3297): a*u + b*v + c*w, left to right */
-		float o[4];
-		for (int k = 0; k < 4; k++)
-		{
-			float a = f.sv[k * f.sv_stride], b = f.sv[(4 + k) * f.sv_stride], c = f.sv[(8 + k) * f.sv_stride];
-			o[k] = a * f.u + b * f.v + c * f.w;
-		}
-		return make_float4(o[0], o[1], o[2], o[3]);
-	}
+	if (FS == SWFS_VARYING) return make_float4(lerp3(f, 0), lerp3(f, 1), lerp3(f, 2), lerp3(f, 3));
 	if (FS == SWFS_TEXTURE)
 	{
-		float o[4];
-		for (int k = 0; k < 4; k++)
-		{
-			float a = f.sv[k * f.sv_stride], b = f.sv[(4 + k) * f.sv_stride], c = f.sv[(8 + k) * f.sv_stride];
-			o[k] = a * f.u + b * f.v + c * f.w;
-		}
-		return sample_nearest(P.tex[P.fs_tex_unit], o[P.fs_swz_u], o[P.fs_swz_v]);
+		const float tu = lerp3(f, P.fs_swz_u), tv = lerp3(f, P.fs_swz_v);
+		return sample_nearest(P.tex[P.fs_tex_unit], tu, tv);
 	}
 	/* generic: interpolate every linked varying into the FS variable file, run the op list */
 	uint32_t V[SWGL_MAX_VAR_WORDS];
@@ -687,7 +680,7 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 							dep[kk] = z;
 							n_shaded++;
 							f.vid0 = S.vid[0][j]; f.vid1 = S.vid[1][j]; f.vid2 = S.vid[2][j];
-							f.sv = &S.sv[0][j]; f.sv_stride = SWGL_BATCH;
+							f.a = &S.sv[0][j]; f.b = &S.sv[4][j]; f.c = &S.sv[8][j]; f.stride = SWGL_BATCH;
 							const float4 o = run_fragment<FS>(P, f);
 							col[kk] = blend_pack(o.x, o.y, o.z, o.w, col[kk]);
 							dirty = true;
@@ -736,11 +729,17 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 /* ========================================================================================
  * host side of the C ABI
  * ====================================================================================== */
+#include "swgl_raster_frag.cuh"
+
+/* raster_path: 1 = pixel-owner (k_raster), 2 = fragment-parallel (k_raster_frag), 0 = default */
 template <int FS>
 static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 {
 	dim3 grid(c->tiles_x, c->tiles_y);
-	k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
+	const int path = c->opt_raster_path == 1 ? 1 : 2;
+	c->last_raster_path = path;
+	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
+	else k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
 }
 
 extern "C" {
@@ -802,6 +801,10 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	cudaFuncSetAttribute(k_raster<SWFS_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaFuncSetAttribute(k_raster<SWFS_VARYING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaFuncSetAttribute(k_raster<SWFS_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	const int smem_f = (int)sizeof(FragShared);
+	cudaFuncSetAttribute(k_raster_frag<SWFS_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+	cudaFuncSetAttribute(k_raster_frag<SWFS_VARYING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
+	cudaFuncSetAttribute(k_raster_frag<SWFS_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
 	return c;
 }
 

@@ -1,0 +1,393 @@
+/*
+ * swgl_raster_frag.cuh -- per-tile rasteriser, fragment-parallel form (included by swgl_dev.cu).
+ *
+ * The pixel-owner kernel (k_raster) spends a whole warp on every primitive that touches its
+ * four rows; with ~6-pixel triangles that leaves ~8 % of the lanes busy.  Here the tile's
+ * colour and depth are staged in shared memory and the work is re-shaped in three phases per
+ * batch of primitives:
+ *
+ *   A  one thread per primitive: replay the span walk over the tile's rows (swgl.c:3356-3361,
+ *      3466-3471) and record [xa, xb) per row plus a running fragment count;
+ *   S  block-wide exclusive scan of the fragment counts;
+ *   B  one thread per FRAGMENT (dense, chunks of 256): binary-search the owning primitive and
+ *      row, evaluate Barycentric + perspective correction + z (swgl.c:3365-3382), then commit.
+ *
+ * Commit keeps the reference's per-pixel submission order: fragments are numbered in
+ * (primitive, row, x) order, so among the fragments of one chunk that hit the same pixel the
+ * lowest thread index is the earliest primitive.  Each round every pending fragment does an
+ * atomicMin of its thread index on the pixel's slot; the winner runs the depth test, shades,
+ * blends into shared memory and releases the slot; losers retry.  Small meshes need two
+ * rounds (the reference double-covers shared diagonals), large triangles one.
+ *
+ * The finished tile leaves with 128-bit coalesced stores, to local HBM and, when a peer
+ * colour target is set, straight into rank 0's framebuffer over NVLink.
+ */
+#ifndef SWGL_RASTER_FRAG_CUH
+#define SWGL_RASTER_FRAG_CUH
+
+#define FRAG_THREADS   256
+#define FRAG_BATCH     256      /* primitives per batch */
+#define FRAG_SPAN_POOL 3072     /* (primitive, row) spans per batch */
+#define FRAG_SORT_CAP  2048     /* lists up to this length are sorted in shared memory */
+
+struct FragShared
+{
+	uint32_t color[SWGL_TILE * SWGL_TILE];
+	float    depth[SWGL_TILE * SWGL_TILE];
+	uint32_t owner[SWGL_TILE * SWGL_TILE];     /* commit arbitration slot per pixel */
+	float    lut[256];                         /* byte / 255.0f (swgl.c:3434-3437) */
+	uint32_t ids[FRAG_BATCH];                  /* this batch, ascending primitive id */
+	uint32_t frag_off[FRAG_BATCH + 1];         /* exclusive scan of fragment counts */
+	uint32_t span_base[FRAG_BATCH + 1];        /* exclusive scan of row counts */
+	uint32_t row0[FRAG_BATCH];                 /* first tile row of the primitive's spans */
+	union
+	{
+		struct
+		{
+			uint16_t span[FRAG_SPAN_POOL];     /* xa | xb << 8, tile-local columns */
+			uint16_t row_pre[FRAG_SPAN_POOL];  /* fragments of the primitive before this row */
+		} s;
+		uint32_t sort_buf[FRAG_SORT_CAP];      /* whole-list sort, before the first batch */
+	} u;
+	uint32_t scan_tmp[FRAG_THREADS / 32];
+	uint32_t scan_total;
+	uint32_t batch_count;
+	unsigned long long red[2][FRAG_THREADS / 32];
+};
+
+/* exclusive block scan of one value per thread; returns the exclusive prefix, total in *total */
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_tmp, uint32_t* total_out)
+{
+	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+	if (lane == 31) warp_tmp[wid] = x;
+	__syncthreads();
+	if (wid == 0)
+	{
+		uint32_t s = lane < (FRAG_THREADS / 32) ? warp_tmp[lane] : 0u;
+#pragma unroll
+		for (int o = 1; o < FRAG_THREADS / 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane >= o) s += y; }
+		if (lane < (FRAG_THREADS / 32)) warp_tmp[lane] = s;
+		if (lane == (FRAG_THREADS / 32) - 1) *total_out = s;
+	}
+	__syncthreads();
+	return (wid ? warp_tmp[wid - 1] : 0u) + (x - v);
+}
+
+/* blend with the destination unpacked through the byte/255.0f table */
+__device__ __forceinline__ uint32_t blend_pack_lut(float r, float g, float b, float a, uint32_t cur, const float* lut)
+{
+	r = RMIN(RMAX(r, 0.0f), 1.0f);
+	g = RMIN(RMAX(g, 0.0f), 1.0f);
+	b = RMIN(RMAX(b, 0.0f), 1.0f);
+	a = RMIN(RMAX(a, 0.0f), 1.0f);
+	const float cr = lut[(cur >> 24) & 0xFF], cg = lut[(cur >> 16) & 0xFF];
+	const float cb = lut[(cur >> 8) & 0xFF], ca = lut[cur & 0xFF];
+	r = cr + a * (r - cr);
+	g = cg + a * (g - cg);
+	b = cb + a * (b - cb);
+	a = ca + a * (a - ca);
+	uint32_t word = 0;
+	word |= (uint32_t)(int)(r * 255.0f) << 24;
+	word |= (uint32_t)(int)(g * 255.0f) << 16;
+	word |= (uint32_t)(int)(b * 255.0f) << 8;
+	word |= (uint32_t)(int)(a * 255.0f);
+	return word;
+}
+
+template <int FS>
+__global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_constant__ DrawParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	FragShared& S = *reinterpret_cast<FragShared*>(smem_raw);
+
+	if (P.ctr->overflow) return;
+	const uint32_t tx = blockIdx.x, ty = blockIdx.y;
+	if (!owns_tile_row(P, ty)) return;
+	const uint32_t tile = ty * P.tiles_x + tx;
+	const uint32_t list_off = P.tile_off[tile];
+	const uint32_t n_list = P.tile_off[tile + 1] - list_off;
+	const ClearParams cp = P.clear;
+	if (n_list == 0 && !cp.flags) return;
+
+	const uint32_t tid = threadIdx.x;
+	const int tile_x0 = (int)(tx << SWGL_TILE_SHIFT), tile_r0 = (int)(ty << SWGL_TILE_SHIFT);
+
+	/* ---- stage the tile: 4x1 strip per thread, 4 passes of 8 rows ---- */
+	bool tile_dirty = false;
+	{
+		const uint32_t q = tid & 7u;
+		for (uint32_t r = tid >> 3; r < SWGL_TILE; r += FRAG_THREADS / 8)
+		{
+			const int row = tile_r0 + (int)r, px0 = tile_x0 + (int)(q << 2);
+			uint32_t c4[4] = { 0u, 0u, 0u, 0u }; float d4[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+			if (row < (int)P.H)
+			{
+				const size_t pix = (size_t)row * P.W + (size_t)px0;
+				const bool in_row = cp.flags && row >= cp.y0 && row < cp.y1;
+				bool all_c = true, all_d = true;
+				for (int k = 0; k < 4; k++)
+				{
+					const bool inside = in_row && (px0 + k) >= cp.x0 && (px0 + k) < cp.x1;
+					tile_dirty |= inside;
+					all_c &= inside && (cp.flags & 1u);
+					all_d &= inside && (cp.flags & 2u);
+				}
+				if (px0 + 3 < (int)P.W && ((pix & 3u) == 0))
+				{
+					if (!all_c) { uint4 v = *(const uint4*)(P.color + pix); c4[0] = v.x; c4[1] = v.y; c4[2] = v.z; c4[3] = v.w; }
+					if (!all_d) { float4 v = *(const float4*)(P.depth + pix); d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w; }
+				}
+				else
+					for (int k = 0; k < 4; k++)
+						if (px0 + k < (int)P.W) { c4[k] = P.color[pix + k]; d4[k] = P.depth[pix + k]; }
+				for (int k = 0; k < 4; k++)
+				{
+					const bool inside = in_row && (px0 + k) >= cp.x0 && (px0 + k) < cp.x1;
+					if (inside && (cp.flags & 1u)) c4[k] = cp.word;
+					if (inside && (cp.flags & 2u)) d4[k] = 0.0f;
+				}
+			}
+			const uint32_t s = r * SWGL_TILE + (q << 2);
+			*(uint4*)&S.color[s] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+			*(float4*)&S.depth[s] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+			*(uint4*)&S.owner[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+		}
+		S.lut[tid] = (float)tid / 255.0f;
+	}
+
+	uint32_t n_tested = 0, n_shaded = 0;
+
+	if (n_list > 0)
+	{
+		/* ---- ascending primitive id = submission order ---- */
+		uint32_t* gl_ids = P.pairs + list_off;
+		if (n_list <= FRAG_BATCH)
+		{
+			/* rank sort: ids are unique, every thread counts the smaller ones */
+			if (tid < n_list) S.u.sort_buf[tid] = gl_ids[tid];
+			__syncthreads();
+			if (tid < n_list)
+			{
+				const uint32_t mine = S.u.sort_buf[tid];
+				uint32_t rank = 0;
+				for (uint32_t j = 0; j < n_list; j++) rank += (S.u.sort_buf[j] < mine) ? 1u : 0u;
+				S.ids[rank] = mine;
+				gl_ids[rank] = mine;    /* a batch cut short by the span pool reloads from here */
+			}
+		}
+		else if (n_list <= FRAG_SORT_CAP)
+		{
+			for (uint32_t i = tid; i < n_list; i += FRAG_THREADS) S.u.sort_buf[i] = gl_ids[i];
+			uint32_t n_pow2 = 1; while (n_pow2 < n_list) n_pow2 <<= 1;
+			sort_ids_shared(S.u.sort_buf, n_list, n_pow2);
+			for (uint32_t i = tid; i < n_list; i += FRAG_THREADS) gl_ids[i] = S.u.sort_buf[i];
+		}
+		else sort_ids_global(gl_ids, n_list);
+		__syncthreads();
+
+		const int band_last_y = P.ytop - tile_r0;                 /* raster y of tile row 0 */
+		const int band_first_y = band_last_y - (SWGL_TILE - 1);
+
+		uint32_t base = 0;
+		while (base < n_list)
+		{
+			uint32_t nb = min((uint32_t)FRAG_BATCH, n_list - base);
+			if (n_list > FRAG_BATCH || base > 0)
+			{
+				if (tid < nb) S.ids[tid] = gl_ids[base + tid];
+				__syncthreads();
+			}
+
+			/* ---- phase A1: rows each primitive has inside this tile ---- */
+			Prim pr;
+			TriWalk w;
+			int y_in = 0, y_out = -1;
+			if (tid < nb)
+			{
+				const uint32_t pid = S.ids[tid];
+				pr.v[0] = P.prims[pid].v[0]; pr.v[1] = P.prims[pid].v[1]; pr.v[2] = P.prims[pid].v[2];
+				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
+				y_in = max(w.ys, band_first_y);
+				y_out = min(w.ye - 1, band_last_y);
+			}
+			const uint32_t my_rows = (tid < nb && y_out >= y_in) ? (uint32_t)(y_out - y_in + 1) : 0u;
+			uint32_t rows_total;
+			const uint32_t my_span_base = block_scan_excl(my_rows, S.scan_tmp, &S.scan_total);
+			rows_total = S.scan_total;
+			if (rows_total > FRAG_SPAN_POOL)
+			{
+				/* too many spans for one batch: keep the longest prefix that fits (always >= 1
+				 * primitive, a primitive has at most 32 rows here) */
+				if (tid == 0) S.batch_count = nb;
+				__syncthreads();
+				if (tid < nb && my_span_base + my_rows > FRAG_SPAN_POOL) atomicMin(&S.batch_count, tid);
+				__syncthreads();
+				nb = S.batch_count;
+			}
+
+			/* ---- phase A2: replay the walk, record spans and fragment counts ---- */
+			uint32_t my_frags = 0;
+			if (tid < nb)
+			{
+				float x0, x1;
+				if (y_in == w.ys) { x0 = w.c0x; x1 = w.c0x; }        /* starts in this band */
+				else
+				{
+					const uint2 pb = P.prim_band[S.ids[tid]];
+					const BandEntry be = P.bands[pb.x + (pb.y - ty)];
+					x0 = be.x0; x1 = be.x1;
+				}
+				bool switched = (y_in > w.ys) && ((float)y_in >= w.c1y);
+				float s1 = switched ? w.s2 : w.s1;
+				S.row0[tid] = (uint32_t)(band_last_y - y_out);       /* smallest tile row index */
+				for (int y = y_in; y <= y_out; y++)
+				{
+					int xa, xb;
+					row_span(x0, x1, P, xa, xb);
+					xa = max(xa, tile_x0) - tile_x0;
+					xb = min(xb, tile_x0 + SWGL_TILE) - tile_x0;
+					if (xb < xa) xb = xa;
+					/* spans are stored by ascending tile row = descending y */
+					const uint32_t slot = my_span_base + (uint32_t)(y_out - y);
+					S.u.s.span[slot] = (uint16_t)(xa | (xb << 8));
+					my_frags += (uint32_t)(xb - xa);
+					if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+					x0 += w.s0; x1 += s1;
+				}
+				S.span_base[tid] = my_span_base;
+			}
+			uint32_t frag_total;
+			const uint32_t my_frag_off = block_scan_excl(my_frags, S.scan_tmp, &S.scan_total);
+			frag_total = S.scan_total;
+			if (tid < nb)
+			{
+				S.frag_off[tid] = my_frag_off;
+				/* per-row prefix inside the primitive, in the stored (ascending tile row) order */
+				uint32_t acc = 0;
+				for (uint32_t k = 0; k < my_rows; k++)
+				{
+					const uint32_t sp = S.u.s.span[my_span_base + k];
+					S.u.s.row_pre[my_span_base + k] = (uint16_t)acc;
+					acc += (sp >> 8) - (sp & 0xffu);
+				}
+			}
+			if (tid == nb) { S.frag_off[nb] = my_frag_off; S.span_base[nb] = my_span_base; }
+			if (nb == FRAG_THREADS && tid == 0) { S.frag_off[nb] = frag_total; S.span_base[nb] = rows_total; }
+			__syncthreads();
+			frag_total = S.frag_off[nb];
+
+			/* ---- phase B: one thread per fragment, chunks of 256 in submission order ---- */
+			for (uint32_t fbase = 0; fbase < frag_total; fbase += FRAG_THREADS)
+			{
+				const uint32_t f = fbase + tid;
+				bool pending = f < frag_total;
+				uint32_t pix = 0, pid = 0;
+				float z = 0.0f;
+				FragIn fi;
+				if (pending)
+				{
+					/* owning primitive: largest i with frag_off[i] <= f */
+					uint32_t lo = 0, hi = nb;
+					while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.frag_off[mid] <= f) lo = mid; else hi = mid; }
+					const uint32_t g = f - S.frag_off[lo];
+					/* row: largest k with row_pre[k] <= g among rows that are not empty past g */
+					const uint32_t sb = S.span_base[lo], nr = S.span_base[lo + 1] - sb;
+					uint32_t rl = 0, rh = nr;
+					while (rh - rl > 1) { const uint32_t mid = (rl + rh) >> 1; if (S.u.s.row_pre[sb + mid] <= g) rl = mid; else rh = mid; }
+					const uint32_t sp = S.u.s.span[sb + rl];
+					const uint32_t lx = (sp & 0xffu) + (g - S.u.s.row_pre[sb + rl]);
+					const uint32_t r = S.row0[lo] + rl;
+					pix = r * SWGL_TILE + lx;
+					pid = S.ids[lo];
+					const float4 a = P.prims[pid].v[0], b = P.prims[pid].v[1], c = P.prims[pid].v[2];
+					BaryConst k;
+					bary_setup(a, b, c, k);
+					frag_weights(k, (float)(tile_x0 + (int)lx), (float)(band_last_y - (int)r), fi.u, fi.v, fi.w, z);
+					n_tested++;
+				}
+				/* ordered commit */
+				while (__syncthreads_or(pending ? 1 : 0))
+				{
+					if (pending) atomicMin(&S.owner[pix], tid);
+					__syncthreads();
+					if (pending && S.owner[pix] == tid)
+					{
+						const float cur = S.depth[pix];
+						if (cur == 0.0f || cur >= z)     /* swgl.c:3387 */
+						{
+							S.depth[pix] = z;
+							n_shaded++;
+							const Prim* q = P.prims + pid;
+							fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
+							fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
+							fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
+							fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
+							fi.stride = 1;
+							const float4 o = run_fragment<FS>(P, fi);
+							S.color[pix] = blend_pack_lut(o.x, o.y, o.z, o.w, S.color[pix], S.lut);
+							tile_dirty = true;
+						}
+						S.owner[pix] = 0xffffffffu;
+						pending = false;
+					}
+				}
+			}
+			base += nb;
+			__syncthreads();
+		}
+	}
+
+	/* ---- write-back: 128-bit stores of the finished tile ---- */
+	const bool dirty_any = __syncthreads_or(tile_dirty ? 1 : 0);
+	if (dirty_any)
+	{
+		const uint32_t q = tid & 7u;
+		for (uint32_t r = tid >> 3; r < SWGL_TILE; r += FRAG_THREADS / 8)
+		{
+			const int row = tile_r0 + (int)r, px0 = tile_x0 + (int)(q << 2);
+			if (row >= (int)P.H) continue;
+			const size_t pix = (size_t)row * P.W + (size_t)px0;
+			const uint32_t s = r * SWGL_TILE + (q << 2);
+			uint4 c4 = *(const uint4*)&S.color[s];
+			float4 d4 = *(const float4*)&S.depth[s];
+			d4.x = canon_nan(d4.x); d4.y = canon_nan(d4.y); d4.z = canon_nan(d4.z); d4.w = canon_nan(d4.w);
+			if (px0 + 3 < (int)P.W && ((pix & 3u) == 0))
+			{
+				*(uint4*)(P.color + pix) = c4;
+				*(float4*)(P.depth + pix) = d4;
+				if (P.peer_color) *(uint4*)(P.peer_color + pix) = c4;
+			}
+			else
+			{
+				const uint32_t cc[4] = { c4.x, c4.y, c4.z, c4.w };
+				const float dd[4] = { d4.x, d4.y, d4.z, d4.w };
+				for (int k = 0; k < 4; k++)
+					if (px0 + k < (int)P.W)
+					{
+						P.color[pix + k] = cc[k]; P.depth[pix + k] = dd[k];
+						if (P.peer_color) P.peer_color[pix + k] = cc[k];
+					}
+			}
+		}
+	}
+
+	if (P.count_fragments)
+	{
+		unsigned long long a = n_tested, b = n_shaded;
+		for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+		if ((tid & 31u) == 0) { S.red[0][tid >> 5] = a; S.red[1][tid >> 5] = b; }
+		__syncthreads();
+		if (tid == 0)
+		{
+			unsigned long long ta = 0, tb = 0;
+			for (int i = 0; i < FRAG_THREADS / 32; i++) { ta += S.red[0][i]; tb += S.red[1][i]; }
+			if (ta) atomicAdd(&P.ctr->tested[tile % SWGL_CTR_SLOTS], ta);
+			if (tb) atomicAdd(&P.ctr->shaded[tile % SWGL_CTR_SLOTS], tb);
+		}
+	}
+}
+
+#endif

@@ -32,9 +32,14 @@ def _small_scenes():
     return out
 
 
+PATHS = {1: "pixel_owner", 2: "fragment_parallel"}
+
+
+@pytest.mark.parametrize("path", sorted(PATHS), ids=lambda p: PATHS[p])
 @pytest.mark.parametrize("scene", _small_scenes(), ids=lambda s: s.name)
-def test_matches_reference_and_restatement(gpu_api, restatement, reference, scene):
-    col, dep, stats, err = gpu_render(gpu_api, scene, indexed=scene.indices is not None)
+def test_matches_reference_and_restatement(gpu_api, restatement, reference, scene, path):
+    col, dep, stats, err = gpu_render(gpu_api, scene, indexed=scene.indices is not None,
+                                      options={"raster_path": path})
     assert err == "", err
     rc, rd, rstats = restatement.render(scene)
     assert_bit_exact(O.compare(col, dep, rc, rd), "vs restatement")
@@ -76,3 +81,15 @@ def test_two_draws_keep_order(gpu_api, restatement):
     assert err == ""
     rc, rd, _ = restatement.render(scene)
     assert_bit_exact(O.compare(col, dep, rc, rd))
+
+
+def test_long_tile_lists_and_span_pool_cuts(gpu_api, restatement):
+    """Many large overlapping triangles: tile lists longer than one batch (256), more spans than
+    the per-batch pool, and lists beyond the shared-memory sort capacity (2048)."""
+    scene = S.random_triangles(6000, 256, 192, seed=77, extent=0.9, alpha=0.5)
+    rc, rd, rstats = restatement.render(scene)
+    for path in (1, 2):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+        assert err == ""
+        assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
+        assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
