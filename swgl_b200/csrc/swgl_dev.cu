@@ -221,33 +221,35 @@ __device__ __forceinline__ void lerp_vary(const DrawParams& P, uint32_t dst, uin
 __device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P)
 {
 	/* swgl.c:3685-3691: int <- x / w * (VW/2) + (VW/2) + VX, stored back as float */
-	int X = cvt_x86(((p.x / p.w) * P.hw + P.hw) + P.fvx);
-	int Y = cvt_x86(((p.y / p.w) * P.hh + P.hh) + P.fvy);
+	int X = cvt_x86((fdiv(p.x, p.w) * P.hw + P.hw) + P.fvx);
+	int Y = cvt_x86((fdiv(p.y, p.w) * P.hh + P.hh) + P.fvy);
 	return make_float4((float)X, (float)Y, p.z, p.w);
 }
 
 __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawParams P)
 {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= P.ntri) return;
+	const bool active = t < P.ntri;      /* no early return: the warp allocates band entries together */
 
 	/* stream positions 3t, 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611) */
-	uint32_t sid[3];
+	uint32_t sid[3] = { 0u, 0u, 0u };
 	float4 p[3];
 	for (int j = 0; j < 3; j++)
 	{
 		uint32_t s = 3u * t + (uint32_t)j;
+		p[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		if (!active) continue;
 		if (P.ibo)
 		{
 			unsigned long long at = (unsigned long long)(long long)P.first + s;
 			uint32_t idx = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
 			sid[j] = idx;
-			p[j] = (idx < P.n_shade) ? P.clip[idx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (idx < P.n_shade) p[j] = P.clip[idx];
 		}
 		else
 		{
 			sid[j] = s;
-			p[j] = (s < P.n_shade) ? P.clip[s] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (s < P.n_shade) p[j] = P.clip[s];
 		}
 	}
 
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 	{
 		if (p[j].z >= -p[j].w) in_idx[n_in++] = j; else out_idx[n_out++] = j;
 	}
+	if (!active) n_in = 0;
 
 	Prim pr[2];
 	int n_prims = 0;
@@ -292,63 +295,83 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 		n_prims = 2;
 	}
 
+	/* divide + viewport snap, triangle set-up, band counts for both primitives */
+	TriWalk wk[2];
+	uint32_t tr_hi[2] = { 0u, 0u }, nbv[2] = { 0u, 0u };
 	for (int k = 0; k < 2; k++)
 	{
-		const uint32_t pid = 2u * t + (uint32_t)k;
-		uint2 pb = make_uint2(0xffffffffu, 0u);
-		if (k < n_prims)
+		if (k >= n_prims) continue;
+		Prim& q = pr[k];
+		for (int j = 0; j < 3; j++) q.v[j] = to_screen(q.v[j], P);
+		q.pad = 0;
+		if (tri_setup(q.v[0], q.v[1], q.v[2], P, wk[k]))
 		{
-			Prim& q = pr[k];
-			for (int j = 0; j < 3; j++) q.v[j] = to_screen(q.v[j], P);
-			q.pad = 0;
-			TriWalk w;
-			if (tri_setup(q.v[0], q.v[1], q.v[2], P, w))
+			/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
+			tr_hi[k] = (uint32_t)(P.ytop - wk[k].ys) >> SWGL_TILE_SHIFT;
+			const uint32_t tr_lo = (uint32_t)(P.ytop - (wk[k].ye - 1)) >> SWGL_TILE_SHIFT;
+			nbv[k] = tr_hi[k] - tr_lo + 1u;
+		}
+	}
+
+	/* one atomic per warp allocates the band entries of all its primitives */
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t need = nbv[0] + nbv[1];
+	uint32_t incl = need;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += y; }
+	const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t warp_base = 0;
+	if (lane == 31 && warp_total)
+	{
+		warp_base = atomicAdd(&P.ctr->band_cursor, warp_total);
+	}
+	warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+	const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, nbv[0] != 0u)) + __popc(__ballot_sync(0xffffffffu, nbv[1] != 0u));
+	if (lane == 0 && n_live) atomicAdd(&P.ctr->prims_out, n_live);
+	if ((unsigned long long)warp_base + warp_total > (unsigned long long)P.cap_bands)
+	{
+		if (lane == 0 && warp_total) P.ctr->overflow = 1u;   /* the draw is dropped and re-issued */
+		return;
+	}
+	uint32_t base = warp_base + incl - need;
+
+	for (int k = 0; k < 2; k++)
+	{
+		if (nbv[k] == 0u) continue;              /* dead slots are never referenced: nothing to write */
+		const uint32_t pid = 2u * t + (uint32_t)k;
+		const TriWalk& w = wk[k];
+		P.prim_band[pid] = make_uint2(base, tr_hi[k]);
+		P.prims[pid] = pr[k];
+		/* the walk (swgl.c:3356-3361, 3466-3471), recording the state at every band entry */
+		float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
+		bool switched = false;
+		uint32_t tr = tr_hi[k];
+		int band_last_y = P.ytop - (int)(tr << SWGL_TILE_SHIFT);   /* last raster row of this band */
+		float ex0 = x0, ex1 = x1;
+		int cmin = 0x7fffffff, cmax = -1;
+		for (int y = w.ys; y < w.ye; y++)
+		{
+			int xa, xb;
+			row_span(x0, x1, P, xa, xb);
+			if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
+			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+			x0 += w.s0; x1 += s1;
+			if (y == band_last_y || y == w.ye - 1)
 			{
-				/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
-				const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> SWGL_TILE_SHIFT;
-				const uint32_t tr_lo = (uint32_t)(P.ytop - (w.ye - 1)) >> SWGL_TILE_SHIFT;
-				const uint32_t nb = tr_hi - tr_lo + 1u;
-				const uint32_t base = atomicAdd(&P.ctr->band_cursor, nb);
-				const bool fits = (unsigned long long)base + nb <= (unsigned long long)P.cap_bands;
-				if (!fits) P.ctr->overflow = 1u;
-				else
+				BandEntry e;
+				e.x0 = ex0; e.x1 = ex1; e.prim = pid; e.cols = 0xffffffffu;
+				if (cmax >= 0 && owns_tile_row(P, tr))
 				{
-					pb = make_uint2(base, tr_hi);
-					P.prims[pid] = q;
-					/* the walk (swgl.c:3356-3361, 3466-3471), recording the state at every band entry */
-					float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
-					bool switched = false;
-					uint32_t tr = tr_hi;
-					int band_last_y = P.ytop - (int)(tr << SWGL_TILE_SHIFT);   /* last raster row of this band */
-					float ex0 = x0, ex1 = x1;
-					int cmin = 0x7fffffff, cmax = -1;
-					for (int y = w.ys; y < w.ye; y++)
-					{
-						int xa, xb;
-						row_span(x0, x1, P, xa, xb);
-						if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
-						if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-						x0 += w.s0; x1 += s1;
-						if (y == band_last_y || y == w.ye - 1)
-						{
-							BandEntry e;
-							e.x0 = ex0; e.x1 = ex1; e.prim = pid; e.cols = 0xffffffffu;
-							if (cmax >= 0 && owns_tile_row(P, tr))
-							{
-								const uint32_t c0 = (uint32_t)cmin >> SWGL_TILE_SHIFT, c1 = (uint32_t)cmax >> SWGL_TILE_SHIFT;
-								e.cols = c0 | (c1 << 16);
-								for (uint32_t cx = c0; cx <= c1; cx++) atomicAdd(&P.tile_count[tr * P.tiles_x + cx], 1u);
-							}
-							P.bands[base + (tr_hi - tr)] = e;
-							tr--; band_last_y += SWGL_TILE;
-							ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
-						}
-					}
-					atomicAdd(&P.ctr->prims_out, 1u);
+					const uint32_t c0 = (uint32_t)cmin >> SWGL_TILE_SHIFT, c1 = (uint32_t)cmax >> SWGL_TILE_SHIFT;
+					e.cols = c0 | (c1 << 11) | (tr << 22);
+					for (uint32_t cx = c0; cx <= c1; cx++) atomicAdd(&P.tile_count[tr * P.tiles_x + cx], 1u);
 				}
+				P.bands[base + (tr_hi[k] - tr)] = e;
+				tr--; band_last_y += SWGL_TILE;
+				ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
 			}
 		}
-		P.prim_band[pid] = pb;
+		base += nbv[k];
 	}
 }
 
@@ -407,9 +430,7 @@ __global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ DrawP
 	{
 		const BandEntry be = P.bands[e];
 		if (be.cols == 0xffffffffu) continue;
-		const uint2 pb = P.prim_band[be.prim];
-		const uint32_t tr = pb.y - (e - pb.x);
-		const uint32_t c0 = be.cols & 0xffffu, c1 = be.cols >> 16;
+		const uint32_t c0 = be.cols & 0x7ffu, c1 = (be.cols >> 11) & 0x7ffu, tr = be.cols >> 22;
 		for (uint32_t cx = c0; cx <= c1; cx++)
 		{
 			const uint32_t tile = tr * P.tiles_x + cx;
@@ -440,7 +461,17 @@ __device__ __forceinline__ float lerp3(const FragIn& f, uint32_t k)
 template <int FS>
 __device__ __forceinline__ float4 run_fragment(const DrawParams& P, const FragIn& f)
 {
-	if (FS == SWFS_VARYING) return make_float4(lerp3(f, 0), lerp3(f, 1), lerp3(f, 2), lerp3(f, 3));
+	if (FS == SWFS_VARYING)
+	{
+		if (f.stride == 1 && (((uintptr_t)f.a | (uintptr_t)f.b | (uintptr_t)f.c) & 15u) == 0)
+		{
+			/* packed vec4 records: three 128-bit loads */
+			const float4 a = __ldg((const float4*)f.a), b = __ldg((const float4*)f.b), c = __ldg((const float4*)f.c);
+			return make_float4(a.x * f.u + b.x * f.v + c.x * f.w, a.y * f.u + b.y * f.v + c.y * f.w,
+			                   a.z * f.u + b.z * f.v + c.z * f.w, a.w * f.u + b.w * f.v + c.w * f.w);
+		}
+		return make_float4(lerp3(f, 0), lerp3(f, 1), lerp3(f, 2), lerp3(f, 3));
+	}
 	if (FS == SWFS_TEXTURE)
 	{
 		const float tu = lerp3(f, P.fs_swz_u), tv = lerp3(f, P.fs_swz_v);
@@ -1018,7 +1049,8 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	/* The tile mapping needs storage row = VH-1+2*VY-y to be a bijection on the viewport rows,
 	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
 	 * several raster rows onto row Height-1, swgl.c:3386). */
-	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu)
+	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
+	    || c->tiles_x > 2047u || c->tiles_y > 1023u)
 	{
 		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
 		return flush_clear(c);

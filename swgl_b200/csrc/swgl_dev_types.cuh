@@ -42,7 +42,8 @@ struct BandEntry
 {
 	float    x0, x1;    /* walk state before the first row of the band (swgl.c:3351-3356) */
 	uint32_t prim;
-	uint32_t cols;      /* first tile column | last tile column << 16; 0xffffffff = touches nothing */
+	uint32_t cols;      /* first tile column (11 bits) | last tile column << 11 | tile row << 22;
+	                       0xffffffff = touches nothing */
 };
 
 struct Counters

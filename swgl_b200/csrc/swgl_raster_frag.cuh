@@ -29,6 +29,7 @@
 #define FRAG_BATCH     256      /* primitives per batch */
 #define FRAG_SPAN_POOL 3072     /* (primitive, row) spans per batch */
 #define FRAG_SORT_CAP  2048     /* lists up to this length are sorted in shared memory */
+#define FRAG_MAX_FRAGS 16384    /* fragments per batch (start-bit map size) */
 
 struct FragShared
 {
@@ -40,6 +41,11 @@ struct FragShared
 	uint32_t frag_off[FRAG_BATCH + 1];         /* exclusive scan of fragment counts */
 	uint32_t span_base[FRAG_BATCH + 1];        /* exclusive scan of row counts */
 	uint32_t row0[FRAG_BATCH];                 /* first tile row of the primitive's spans */
+	/* fragment -> primitive map: bit f is set where a primitive's fragments start; own0[w] is the
+	 * rank (among primitives with fragments) of the owner of fragment 32*w; nonempty[rank] = slot */
+	uint32_t start_bits[FRAG_MAX_FRAGS / 32];
+	uint16_t own0[FRAG_MAX_FRAGS / 32];
+	uint16_t nonempty[FRAG_BATCH];
 	union
 	{
 		struct
@@ -98,7 +104,7 @@ __device__ __forceinline__ uint32_t blend_pack_lut(float r, float g, float b, fl
 }
 
 template <int FS>
-__global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_constant__ DrawParams P)
+__global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_constant__ DrawParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	FragShared& S = *reinterpret_cast<FragShared*>(smem_raw);
@@ -166,16 +172,35 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 		uint32_t* gl_ids = P.pairs + list_off;
 		if (n_list <= FRAG_BATCH)
 		{
-			/* rank sort: ids are unique, every thread counts the smaller ones */
-			if (tid < n_list) S.u.sort_buf[tid] = gl_ids[tid];
+			/* every warp sorts 32 ids with a shuffle network, then each id finds its final place as
+			 * (its position in its own run) + (ids below it in the other runs, by binary search) */
+			const uint32_t lane = tid & 31u, wid = tid >> 5;
+			uint32_t x = tid < n_list ? gl_ids[tid] : 0xffffffffu;
+#pragma unroll
+			for (uint32_t k = 2; k <= 32; k <<= 1)
+#pragma unroll
+				for (uint32_t j = k >> 1; j > 0; j >>= 1)
+				{
+					const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+					const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+					x = keep_min ? min(x, y) : max(x, y);
+				}
+			S.u.sort_buf[tid] = x;
 			__syncthreads();
-			if (tid < n_list)
+			if (x != 0xffffffffu)
 			{
-				const uint32_t mine = S.u.sort_buf[tid];
-				uint32_t rank = 0;
-				for (uint32_t j = 0; j < n_list; j++) rank += (S.u.sort_buf[j] < mine) ? 1u : 0u;
-				S.ids[rank] = mine;
-				gl_ids[rank] = mine;    /* a batch cut short by the span pool reloads from here */
+				uint32_t rank = lane;
+				const uint32_t n_runs = (n_list + 31u) >> 5;
+				for (uint32_t r = 0; r < n_runs; r++)
+				{
+					if (r == wid) continue;
+					const uint32_t* run = &S.u.sort_buf[r << 5];
+					uint32_t lo = 0, hi = 32;    /* first position whose id is >= x */
+					while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (run[mid] < x) lo = mid + 1; else hi = mid; }
+					rank += lo;
+				}
+				S.ids[rank] = x;
+				gl_ids[rank] = x;        /* a batch cut short by a pool limit reloads from here */
 			}
 		}
 		else if (n_list <= FRAG_SORT_CAP)
@@ -259,9 +284,23 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 				}
 				S.span_base[tid] = my_span_base;
 			}
+			/* one scan carries both the fragment offsets (low 20 bits) and the rank among the
+			 * primitives that have fragments (high bits) */
+			S.start_bits[tid] = 0u; S.start_bits[tid + FRAG_THREADS] = 0u;
 			uint32_t frag_total;
-			const uint32_t my_frag_off = block_scan_excl(my_frags, S.scan_tmp, &S.scan_total);
-			frag_total = S.scan_total;
+			const uint32_t packed = block_scan_excl(my_frags | (my_frags ? (1u << 20) : 0u), S.scan_tmp, &S.scan_total);
+			uint32_t my_frag_off = packed & 0xfffffu;
+			const uint32_t my_rank = packed >> 20;
+			frag_total = S.scan_total & 0xfffffu;
+			if (frag_total > FRAG_MAX_FRAGS)
+			{
+				/* keep the longest prefix whose fragments fit the start-bit map (>= 1 primitive) */
+				if (tid == 0) S.batch_count = nb;
+				__syncthreads();
+				if (tid < nb && my_frag_off + my_frags > FRAG_MAX_FRAGS) atomicMin(&S.batch_count, tid);
+				__syncthreads();
+				nb = S.batch_count;
+			}
 			if (tid < nb)
 			{
 				S.frag_off[tid] = my_frag_off;
@@ -272,6 +311,13 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 					const uint32_t sp = S.u.s.span[my_span_base + k];
 					S.u.s.row_pre[my_span_base + k] = (uint16_t)acc;
 					acc += (sp >> 8) - (sp & 0xffu);
+				}
+				if (my_frags)
+				{
+					atomicOr(&S.start_bits[my_frag_off >> 5], 1u << (my_frag_off & 31u));
+					const uint32_t w_last = (my_frag_off + my_frags - 1u) >> 5;
+					for (uint32_t wd = (my_frag_off + 31u) >> 5; wd <= w_last; wd++) S.own0[wd] = (uint16_t)my_rank;
+					S.nonempty[my_rank] = (uint16_t)tid;
 				}
 			}
 			if (tid == nb) { S.frag_off[nb] = my_frag_off; S.span_base[nb] = my_span_base; }
@@ -284,14 +330,17 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 			{
 				const uint32_t f = fbase + tid;
 				bool pending = f < frag_total;
-				uint32_t pix = 0, pid = 0;
+				uint32_t pix = 0;
 				float z = 0.0f;
-				FragIn fi;
+				float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				bool shaded_early = false;
+				uint32_t pid = 0;
 				if (pending)
 				{
-					/* owning primitive: largest i with frag_off[i] <= f */
-					uint32_t lo = 0, hi = nb;
-					while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.frag_off[mid] <= f) lo = mid; else hi = mid; }
+					/* owning primitive from the start-bit map */
+					const uint32_t wd = f >> 5, bt = f & 31u;
+					const uint32_t rank = (uint32_t)S.own0[wd] + __popc(S.start_bits[wd] & 0xfffffffeu & (0xffffffffu >> (31u - bt)));
+					const uint32_t lo = S.nonempty[rank];
 					const uint32_t g = f - S.frag_off[lo];
 					/* row: largest k with row_pre[k] <= g among rows that are not empty past g */
 					const uint32_t sb = S.span_base[lo], nr = S.span_base[lo + 1] - sb;
@@ -302,11 +351,29 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 					const uint32_t r = S.row0[lo] + rl;
 					pix = r * SWGL_TILE + lx;
 					pid = S.ids[lo];
-					const float4 a = P.prims[pid].v[0], b = P.prims[pid].v[1], c = P.prims[pid].v[2];
+					const Prim* q = P.prims + pid;
+					const float4 a = q->v[0], b = q->v[1], c = q->v[2];
 					BaryConst k;
 					bary_setup(a, b, c, k);
+					FragIn fi;
 					frag_weights(k, (float)(tile_x0 + (int)lx), (float)(band_last_y - (int)r), fi.u, fi.v, fi.w, z);
 					n_tested++;
+					/* The fragment shader does not read the framebuffer, so it runs here, before the
+					 * ordered part (depth test + blend).  It is skipped when the fragment fails against
+					 * the depth stored right now -- it then almost always fails in submission order too
+					 * (a stored depth only decreases); the exception (an earlier fragment of this chunk
+					 * storing exactly 0.0 = "empty") is caught in the commit loop, which shades late. */
+					const float cur = S.depth[pix];
+					if (cur == 0.0f || cur >= z)
+					{
+						fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
+						fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
+						fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
+						fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
+						fi.stride = 1;
+						o = run_fragment<FS>(P, fi);
+						shaded_early = true;
+					}
 				}
 				/* ordered commit */
 				while (__syncthreads_or(pending ? 1 : 0))
@@ -320,13 +387,22 @@ __global__ void __launch_bounds__(FRAG_THREADS) k_raster_frag(const __grid_const
 						{
 							S.depth[pix] = z;
 							n_shaded++;
-							const Prim* q = P.prims + pid;
-							fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
-							fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
-							fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
-							fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
-							fi.stride = 1;
-							const float4 o = run_fragment<FS>(P, fi);
+							if (!shaded_early)
+							{
+								/* rare: recompute the weights (same arithmetic, same bits) and shade now */
+								const Prim* q_prim = P.prims + pid;
+								BaryConst k;
+								bary_setup(q_prim->v[0], q_prim->v[1], q_prim->v[2], k);
+								FragIn fi;
+								float z2;
+								frag_weights(k, (float)(tile_x0 + (int)(pix & (SWGL_TILE - 1))), (float)(band_last_y - (int)(pix >> SWGL_TILE_SHIFT)), fi.u, fi.v, fi.w, z2);
+								fi.vid0 = q_prim->vid[0]; fi.vid1 = q_prim->vid[1]; fi.vid2 = q_prim->vid[2];
+								fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
+								fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
+								fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
+								fi.stride = 1;
+								o = run_fragment<FS>(P, fi);
+							}
 							S.color[pix] = blend_pack_lut(o.x, o.y, o.z, o.w, S.color[pix], S.lut);
 							tile_dirty = true;
 						}

@@ -93,3 +93,18 @@ def test_long_tile_lists_and_span_pool_cuts(gpu_api, restatement):
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
+
+
+def test_depth_zero_reopens_pixels(gpu_api, restatement):
+    """z == 0.0 stored as depth means "empty" again (swgl.c:3387): later fragments that would
+    fail against the previous depth pass.  Exercises the late-shade path of the commit loop."""
+    scene = S.random_triangles(1500, 320, 240, seed=31, extent=0.5, alpha=0.5)
+    v = scene.vertices.reshape(-1, 3, 8)
+    v[::3, :, 2] = 0.0          # every third triangle lies exactly on z = 0
+    v[1::7, :, 2] = -0.25       # some negative depths too
+    rc, rd, rstats = restatement.render(scene)
+    for path in (1, 2):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+        assert err == ""
+        assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
+        assert stats["shaded"] == rstats["shaded"]
