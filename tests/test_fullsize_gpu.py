@@ -1,0 +1,78 @@
+"""GPU, BASELINE sizes: properties that do not need the (slow) CPU oracle at full size, plus one
+full-size oracle comparison through the fast C restatement."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from swgl_b200 import gl as G, multigpu, scenes as S
+
+from util import assert_bit_exact, gpu_render
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c4():
+    return S.config(4)
+
+
+def test_c4_fragment_parallel_equals_pixel_owner_and_elements_equal_arrays(gpu_api, c4):
+    """Two independent raster kernels and two draw entry points must agree bit for bit at 4K/1M."""
+    a = gpu_render(gpu_api, c4, options={"raster_path": 2})
+    b = gpu_render(gpu_api, c4, options={"raster_path": 1})
+    assert a[3] == "" and b[3] == ""
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert a[2]["tested"] == b[2]["tested"] == 6_367_476       # SURVEY.md section 6 (gprof count)
+    assert a[2]["shaded"] == b[2]["shaded"] == 5_785_205
+    d = gpu_render(gpu_api, c4, indexed=False)
+    assert np.array_equal(a[0], d[0]) and np.array_equal(a[1].view(np.uint32), d[1].view(np.uint32))
+    assert int((a[1].view(np.uint32) != 0).sum()) == 5_202_381  # SURVEY.md appendix C, K4 "covered"
+
+
+def test_c4_matches_restatement_at_full_size(gpu_api, restatement, c4):
+    col, dep, stats, err = gpu_render(gpu_api, c4)
+    rc, rd, rstats = restatement.render(c4)
+    assert_bit_exact(O.compare(col, dep, rc, rd), "C4 full size")
+    assert f"{restatement.fnv(rc):016x}" == "56d0d4e1a9cd44f1"   # SURVEY.md appendix C, K4 colour hash
+    # (the survey's K3/K4 *depth* hashes are not reproduced by the compiled reference itself on
+    # these scenes -- colour hashes, coverage and fragment counts are -- so they are not pinned)
+
+
+@pytest.mark.parametrize("n_ranks,band", [(2, 1), (4, 2), (8, 1)])
+def test_stripe_emulation_equals_single_gpu(gpu_api, n_ranks, band):
+    """Sort-first sharding is a pure function of (tile row, N): rendering the N stripes one after
+    the other on one GPU and assembling them must equal the unsharded frame bit for bit."""
+    scene = S.config(2)
+    full = gpu_render(gpu_api, scene)
+    stripes = []
+    total_shaded = 0
+    for r in range(n_ranks):
+        col, dep, stats, err = gpu_render(gpu_api, scene, stripe=(r, n_ranks, band), fill=(0xDEADBEEF, 0.0))
+        assert err == ""
+        stripes.append(col)
+        total_shaded += stats["shaded"]
+    img = multigpu.assemble(stripes, scene.height, scene.width, n_ranks, band)
+    assert np.array_equal(img, full[0])
+    assert total_shaded == full[2]["shaded"]
+
+
+def test_buffer_respecify_streams_new_geometry(gpu_api, restatement):
+    """swglBufferRespecify (extension) replaces buffer contents; glBufferData ignores a second
+    specification like the reference does (swgl.c:3140)."""
+    a, b = S.random_triangles(300, 320, 240, seed=1), S.random_triangles(500, 320, 240, seed=2)
+    api = gpu_api
+    api.glInit(a.width, a.height)
+    st = G.setup_scene(api, a, indexed=False, init=False)
+    vb = np.ascontiguousarray(b.vertices)
+    api.glBufferData(G.GL_ARRAY_BUFFER, vb.nbytes, vb.ctypes.data_as(C.c_void_p), G.GL_STATIC_DRAW)  # ignored
+    api.glClear(3)
+    api.glDrawArrays(G.GL_TRIANGLES, 0, st["n_draw"])
+    col = G.frame_color(api, a.width, a.height)
+    assert np.array_equal(col, restatement.render(a)[0])
+    api.swglBufferRespecify(G.GL_ARRAY_BUFFER, vb.nbytes, vb.ctypes.data_as(C.c_void_p))
+    api.glClear(3)
+    api.glDrawArrays(G.GL_TRIANGLES, 0, len(vb))
+    col = G.frame_color(api, a.width, a.height)
+    assert np.array_equal(col, restatement.render(b)[0])
