@@ -256,6 +256,22 @@ def run_own(args):
            "h2d_bytes_per_step": int(verts.numel() * 4 + idx.numel() * 4) * world,
            "d2h_bytes_per_step": scene.width * scene.height * 4}
 
+    # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
+    mg_check = None
+    if world > 1:
+        barrier()
+        frame()
+        barrier()
+        if rank == 0:
+            multi = G.frame_color(api, scene.width, scene.height)
+            api.swglSetStripe(0, 1, 1)
+            frame()
+            single = G.frame_color(api, scene.width, scene.height)
+            api.swglSetStripe(rank, world, band_rows)
+            mg_check = {"equal_to_single_gpu": bool(np.array_equal(multi, single)),
+                        "mismatching_pixels": int((multi != single).sum())}
+        barrier()
+
     # ---- CPU baseline: the unmodified reference on one host core, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -280,6 +296,8 @@ def run_own(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if mg_check is not None:
+            line["multi_gpu_check"] = mg_check
         if err:
             line["error"] = err
         print(json.dumps(line))

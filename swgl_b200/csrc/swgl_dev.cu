@@ -310,6 +310,13 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 			tr_hi[k] = (uint32_t)(P.ytop - wk[k].ys) >> SWGL_TILE_SHIFT;
 			const uint32_t tr_lo = (uint32_t)(P.ytop - (wk[k].ye - 1)) >> SWGL_TILE_SHIFT;
 			nbv[k] = tr_hi[k] - tr_lo + 1u;
+			if (P.n_ranks > 1)
+			{
+				/* sort-first: a primitive none of whose tile rows belong to this rank is dropped here */
+				bool mine = false;
+				for (uint32_t tr = tr_lo; tr <= tr_hi[k] && !mine; tr++) mine = owns_tile_row(P, tr);
+				if (!mine) nbv[k] = 0u;
+			}
 		}
 	}
 
