@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -178,7 +178,6 @@ def run_own(args):
         frame()
         b.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else {}
     launches = api.swglGetOption(b"kernel_launches") - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
@@ -255,6 +254,8 @@ def run_own(args):
     e2e = {"value": n_tris / e2e_s, "unit": METRIC, "ms_per_step": e2e_s * 1e3,
            "h2d_bytes_per_step": int(verts.numel() * 4 + idx.numel() * 4) * world,
            "d2h_bytes_per_step": scene.width * scene.height * 4}
+
+    clocks = sampler.stop() if rank == 0 else {}   # sampled across the value, roofline and e2e legs
 
     # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
     mg_check = None

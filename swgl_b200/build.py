@@ -62,7 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run([CC] + C_FLAGS + ["-c", src, "-o", obj], check=True)
         objs.append(obj)
     if force or _newer(objs, OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-Xlinker", "-Bsymbolic", "-lcudart"]
+        cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
+        cmd = [os.environ.get("CXX", "g++"), "-shared", "-o", OUT] + objs + [
+            "-Wl,-Bsymbolic", "-L" + cuda_lib, "-Wl,-rpath," + cuda_lib, "-lcudart", "-lstdc++"]
         subprocess.run(cmd, check=True)
     return OUT
 
