@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "triangles/s"
-STAGES = ["k_vertex", "k_setup_bin", "k_scan_tiles", "k_fill_bins", "k_raster"]
+STAGES = ["k_vertex", "k_setup_bin", "k_raster"]
 L2_FLUSH_BYTES = 256 << 20
 
 

@@ -73,8 +73,9 @@ void     swglIpcClose(uint64_t device_ptr);
 
 /* Tuning / test hooks: "raster_path" (0 auto, 1 pixel-owner, 2 fragment-parallel),
  * "fuse_clear" (0/1), "count_fragments" (0/1), "stage_timing" (0/1: per-kernel CUDA-event timing, synchronous);
- * read-only: "kernel_launches", "stage_ns_0".."stage_ns_4" (vertex, setup+bin, scan, fill,
- * raster), "stage_draws", "tile_size", "device". */
+ * "bin_cap" (per-tile list capacity, test hook), "bin_limit_bytes";
+ * read-only: "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
+ * "stage_draws", "tile_size", "device". */
 void swglSetOption(const char* name, int64_t value);
 int64_t swglGetOption(const char* name);
 

@@ -5,11 +5,9 @@
  *   k_clear          glClear                       swgl.c:3183-3214
  *   k_vertex         attribute fetch + VS + varying capture, one thread per vertex
  *                                                  swgl.c:3618-3666
- *   k_setup_bin      near clip, divide + viewport snap, triangle set-up, span walk, band
- *                    entries and tile counts, one thread per input triangle
- *                                                  swgl.c:499-697, 3683-3692, 3316-3361, 3466-3471
- *   k_scan_tiles     exclusive scan of the tile counts
- *   k_fill_bins      per-tile primitive lists
+ *   k_setup_bin      near clip, divide + viewport snap, triangle set-up, span walk and
+ *                    single-pass binning into fixed-capacity per-tile lists, one thread per
+ *                    input triangle         swgl.c:499-697, 3683-3692, 3316-3361, 3466-3471
  *   k_raster         per-tile: sort the list by primitive id, then per pixel Barycentric,
  *                    perspective correction, depth test, varying interpolation, fragment
  *                    shader, blend, pack; 128-bit write-back
@@ -50,11 +48,13 @@ struct swgldev_ctx
 	float4* clip; size_t cap_clip;
 	float* vary; size_t cap_vary;        /* floats */
 	Prim* prims; size_t cap_prims;
-	uint2* prim_band; size_t cap_prim_band;
 	BandEntry* bands; size_t cap_bands;
-	uint32_t* pairs; size_t cap_pairs;
-	uint32_t* tile_count; uint32_t* tile_off;
+	uint32_t* pairs; size_t cap_pairs;   /* tiles * bin_cap entries */
+	uint32_t bin_cap;                    /* K */
+	uint32_t* tile_count;
 	Counters* ctr; Counters* h_ctr;      /* device counters, pinned snapshot */
+	cudaStream_t side;                   /* counter snapshots travel here, off the critical path */
+	cudaEvent_t setup_event;             /* set-up kernel of the last draw finished */
 	cudaEvent_t ctr_event;
 	int ctr_pending;                     /* a snapshot copy is in flight for last_draw */
 
@@ -67,7 +67,8 @@ struct swgldev_ctx
 	int last_raster_path;
 
 	/* options */
-	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing;
+	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag;
+	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
 	cudaEvent_t stage_ev[8];
 	double stage_us[8];                  /* accumulated per-stage device time (stage timing mode) */
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 	if (v == 0 && blockIdx.x == 0)
 	{
 		/* per-draw counters: this kernel is the first of the draw */
-		P.ctr->band_cursor = 0; P.ctr->pair_total = 0; P.ctr->overflow = 0; P.ctr->prims_out = 0;
+		P.ctr->band_cursor = 0; P.ctr->max_list = 0; P.ctr->overflow = 0; P.ctr->prims_out = 0; P.ctr->pair_total = 0ull;
 	}
 	if (v < SWGL_CTR_SLOTS && blockIdx.x == 0) { P.ctr->tested[v] = 0ull; P.ctr->shaded[v] = 0ull; }
 	if (v >= P.n_shade) return;
@@ -226,225 +227,203 @@ __device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P
 	return make_float4((float)X, (float)Y, p.z, p.w);
 }
 
+/* list slot for primitive `pid` in `tile`, from the tile's atomic cursor */
+__device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, uint32_t pid)
+{
+	const uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
+	if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = pid;
+	else atomicOr(&P.ctr->overflow, 1u);
+}
+
+/* One primitive: divide + viewport snap, set-up, span walk.  Returns 1 if the primitive is live
+ * (reaches the rasteriser on this rank).
+ *   tall (> SWGL_SHORT_ROWS rows): one BandEntry per tile row (walk state + tile columns);
+ *        k_bin_tall turns the entries into list insertions, one thread per entry;
+ *   short (<= 3 tile rows): the tile columns of each band come back in pk[0..2]
+ *        (c0 | c1 << 16, 0xffffffff = none) for the warp-aggregated insertion of the caller,
+ *        or are inserted right here when INLINE_INSERT. */
+template <bool INLINE_INSERT>
+__device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t pid, float4 a, float4 b, float4 c,
+                                                   uint32_t va, uint32_t vb, uint32_t vc,
+                                                   uint32_t& tr_top, uint32_t& pk0, uint32_t& pk1, uint32_t& pk2)
+{
+	a = to_screen(a, P); b = to_screen(b, P); c = to_screen(c, P);
+	TriWalk w;
+	if (!tri_setup(a, b, c, P, w)) return 0u;
+	/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
+	const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> SWGL_TILE_SHIFT;
+	const uint32_t tr_lo = (uint32_t)(P.ytop - (w.ye - 1)) >> SWGL_TILE_SHIFT;
+	if (P.n_ranks > 1)
+	{
+		/* sort-first: a primitive none of whose tile rows belong to this rank is dropped here */
+		bool mine = false;
+		for (uint32_t tr = tr_lo; tr <= tr_hi && !mine; tr++) mine = owns_tile_row(P, tr);
+		if (!mine) return 0u;
+	}
+	uint32_t band = 0xffffffffu;
+	if (w.ye - w.ys > SWGL_SHORT_ROWS)
+	{
+		const uint32_t nb = tr_hi - tr_lo + 1u;
+		band = atomicAdd(&P.ctr->band_cursor, nb);
+		if ((unsigned long long)band + nb > (unsigned long long)P.cap_bands) { atomicOr(&P.ctr->overflow, 2u); return 0u; }
+	}
+	Prim* out = P.prims + pid;
+	if (!(P.diag & 2u))
+	{
+		out->v[0] = a; out->v[1] = b; out->v[2] = c;
+		*(uint4*)out->vid = make_uint4(va, vb, vc, band);
+	}
+	tr_top = tr_hi;
+
+	/* the walk (swgl.c:3356-3361, 3466-3471) */
+	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
+	bool switched = false;
+	uint32_t tr = tr_hi;
+	int band_last_y = P.ytop - (int)(tr << SWGL_TILE_SHIFT);   /* last raster row of this band */
+	float ex0 = x0, ex1 = x1;
+	int cmin = 0x7fffffff, cmax = -1;
+	for (int y = w.ys; y < w.ye; y++)
+	{
+		int xa, xb;
+		row_span(x0, x1, P, xa, xb);
+		if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
+		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+		x0 += w.s0; x1 += s1;
+		if (y == band_last_y || y == w.ye - 1)
+		{
+			/* span-exact tile columns of this band */
+			const bool hit = cmax >= 0 && owns_tile_row(P, tr) && !(P.diag & 1u);
+			const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
+			if (band != 0xffffffffu)
+			{
+				BandEntry e;
+				e.x0 = ex0; e.x1 = ex1; e.prim = pid;
+				e.cols = hit ? (c0 | (c1 << 11) | (tr << 22)) : 0xffffffffu;
+				P.bands[band + (tr_hi - tr)] = e;
+			}
+			else if (hit)
+			{
+				if (INLINE_INSERT) { for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, pid); }
+				else
+				{
+					const uint32_t pk = c0 | (c1 << 16);
+					const uint32_t bi = tr_hi - tr;
+					if (bi == 0) pk0 = pk; else if (bi == 1) pk1 = pk; else pk2 = pk;
+				}
+			}
+			tr--; band_last_y += SWGL_TILE;
+			ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
+		}
+	}
+	return 1u;
+}
+
+/* near-plane clipping of a triangle that is not entirely inside (swgl.c:563-696): rare, kept out
+ * of line so the common path stays in registers */
+__device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, const float4* p, const uint32_t* sid, uint32_t in_mask)
+{
+	int in_idx[3], out_idx[3], n_in = 0, n_out = 0;
+	for (int j = 0; j < 3; j++) { if ((in_mask >> j) & 1u) in_idx[n_in++] = j; else out_idx[n_out++] = j; }
+	const uint32_t new0 = P.clip_vid_base + 2u * t, new1 = new0 + 1u;
+	float t0, t1;
+	uint32_t d0, d1, d2, d3;
+	if (n_in == 1)
+	{
+		const int a = in_idx[0];
+		const float4 q1 = near_intersect(p[a], p[out_idx[0]], t0);
+		const float4 q2 = near_intersect(p[a], p[out_idx[1]], t1);
+		lerp_vary(P, new0, sid[a], sid[out_idx[0]], t0);
+		lerp_vary(P, new1, sid[a], sid[out_idx[1]], t1);
+		return setup_one_prim<true>(P, 2u * t, p[a], q1, q2, sid[a], new0, new1, d0, d1, d2, d3);
+	}
+	if (n_in == 2)
+	{
+		const int a = in_idx[0], b = in_idx[1], o = out_idx[0];
+		const float4 q0 = near_intersect(p[a], p[o], t0);
+		const float4 q1 = near_intersect(p[b], p[o], t1);
+		lerp_vary(P, new0, sid[a], sid[o], t0);
+		lerp_vary(P, new1, sid[b], sid[o], t1);
+		uint32_t live = setup_one_prim<true>(P, 2u * t, p[a], p[b], q0, sid[a], sid[b], new0, d0, d1, d2, d3);
+		live += setup_one_prim<true>(P, 2u * t + 1u, p[b], q0, q1, sid[b], new0, new1, d0, d1, d2, d3);
+		return live;
+	}
+	return 0u;
+}
+
 __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawParams P)
 {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = t < P.ntri;      /* no early return: the warp allocates band entries together */
-
-	/* stream positions 3t, 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611) */
-	uint32_t sid[3] = { 0u, 0u, 0u };
-	float4 p[3];
-	for (int j = 0; j < 3; j++)
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t live = 0, tr_top = 0, pk[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu };
+	if (t < P.ntri)
 	{
-		uint32_t s = 3u * t + (uint32_t)j;
-		p[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		if (!active) continue;
+		/* stream positions 3t, 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611) */
+		uint32_t s0 = 3u * t, s1 = s0 + 1u, s2 = s0 + 2u;
 		if (P.ibo)
 		{
-			unsigned long long at = (unsigned long long)(long long)P.first + s;
-			uint32_t idx = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
-			sid[j] = idx;
-			if (idx < P.n_shade) p[j] = P.clip[idx];
+			const unsigned long long at = (unsigned long long)(long long)P.first + s0;
+			s0 = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
+			s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
+			s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
 		}
-		else
+		const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		const float4 p0 = (s0 < P.n_shade) ? P.clip[s0] : zero;
+		const float4 p1 = (s1 < P.n_shade) ? P.clip[s1] : zero;
+		const float4 p2 = (s2 < P.n_shade) ? P.clip[s2] : zero;
+		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
+		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
+		if (in_mask == 7u) live = setup_one_prim<false>(P, 2u * t, p0, p1, p2, s0, s1, s2, tr_top, pk[0], pk[1], pk[2]);
+		else if (in_mask != 0u)
 		{
-			sid[j] = s;
-			if (s < P.n_shade) p[j] = P.clip[s];
+			const float4 p[3] = { p0, p1, p2 };
+			const uint32_t sid[3] = { s0, s1, s2 };
+			live = setup_clipped(P, t, p, sid, in_mask);
 		}
 	}
 
-	/* ClipTriangleAgainstNearPlane (swgl.c:532-696): inside iff z >= -w */
-	int in_idx[3], out_idx[3], n_in = 0, n_out = 0;
-	for (int j = 0; j < 3; j++)
-	{
-		if (p[j].z >= -p[j].w) in_idx[n_in++] = j; else out_idx[n_out++] = j;
-	}
-	if (!active) n_in = 0;
-
-	Prim pr[2];
-	int n_prims = 0;
-	const uint32_t new0 = P.clip_vid_base + 2u * t, new1 = new0 + 1u;
-	if (n_in == 3)
-	{
-		for (int j = 0; j < 3; j++) { pr[0].v[j] = p[j]; pr[0].vid[j] = sid[j]; }
-		n_prims = 1;
-	}
-	else if (n_in == 1)
-	{
-		float t0, t1;
-		const int a = in_idx[0];
-		pr[0].v[0] = p[a]; pr[0].vid[0] = sid[a];
-		pr[0].v[1] = near_intersect(p[a], p[out_idx[0]], t0); pr[0].vid[1] = new0;
-		pr[0].v[2] = near_intersect(p[a], p[out_idx[1]], t1); pr[0].vid[2] = new1;
-		lerp_vary(P, new0, sid[a], sid[out_idx[0]], t0);
-		lerp_vary(P, new1, sid[a], sid[out_idx[1]], t1);
-		n_prims = 1;
-	}
-	else if (n_in == 2)
-	{
-		float t0, t1;
-		const int a = in_idx[0], b = in_idx[1], o = out_idx[0];
-		pr[0].v[0] = p[a]; pr[0].vid[0] = sid[a];
-		pr[0].v[1] = p[b]; pr[0].vid[1] = sid[b];
-		pr[0].v[2] = near_intersect(p[a], p[o], t0); pr[0].vid[2] = new0;
-		pr[1].v[0] = p[b]; pr[1].vid[0] = sid[b];
-		pr[1].v[1] = pr[0].v[2]; pr[1].vid[1] = new0;
-		pr[1].v[2] = near_intersect(p[b], p[o], t1); pr[1].vid[2] = new1;
-		lerp_vary(P, new0, sid[a], sid[o], t0);
-		lerp_vary(P, new1, sid[b], sid[o], t1);
-		n_prims = 2;
-	}
-
-	/* divide + viewport snap, triangle set-up, band counts for both primitives */
-	TriWalk wk[2];
-	uint32_t tr_hi[2] = { 0u, 0u }, nbv[2] = { 0u, 0u };
-	for (int k = 0; k < 2; k++)
-	{
-		if (k >= n_prims) continue;
-		Prim& q = pr[k];
-		for (int j = 0; j < 3; j++) q.v[j] = to_screen(q.v[j], P);
-		q.pad = 0;
-		if (tri_setup(q.v[0], q.v[1], q.v[2], P, wk[k]))
-		{
-			/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
-			tr_hi[k] = (uint32_t)(P.ytop - wk[k].ys) >> SWGL_TILE_SHIFT;
-			const uint32_t tr_lo = (uint32_t)(P.ytop - (wk[k].ye - 1)) >> SWGL_TILE_SHIFT;
-			nbv[k] = tr_hi[k] - tr_lo + 1u;
-			if (P.n_ranks > 1)
-			{
-				/* sort-first: a primitive none of whose tile rows belong to this rank is dropped here */
-				bool mine = false;
-				for (uint32_t tr = tr_lo; tr <= tr_hi[k] && !mine; tr++) mine = owns_tile_row(P, tr);
-				if (!mine) nbv[k] = 0u;
-			}
-		}
-	}
-
-	/* one atomic per warp allocates the band entries of all its primitives */
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t need = nbv[0] + nbv[1];
-	uint32_t incl = need;
+	/* warp-aggregated list insertion for the short, unclipped primitives: neighbouring triangles
+	 * mostly land in the same tile, so lanes that want the same tile share one atomicAdd */
 #pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += y; }
-	const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-	uint32_t warp_base = 0;
-	if (lane == 31 && warp_total)
+	for (int k = 0; k < 3; k++)
 	{
-		warp_base = atomicAdd(&P.ctr->band_cursor, warp_total);
-	}
-	warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
-	const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, nbv[0] != 0u)) + __popc(__ballot_sync(0xffffffffu, nbv[1] != 0u));
-	if (lane == 0 && n_live) atomicAdd(&P.ctr->prims_out, n_live);
-	if ((unsigned long long)warp_base + warp_total > (unsigned long long)P.cap_bands)
-	{
-		if (lane == 0 && warp_total) P.ctr->overflow = 1u;   /* the draw is dropped and re-issued */
-		return;
-	}
-	uint32_t base = warp_base + incl - need;
-
-	for (int k = 0; k < 2; k++)
-	{
-		if (nbv[k] == 0u) continue;              /* dead slots are never referenced: nothing to write */
-		const uint32_t pid = 2u * t + (uint32_t)k;
-		const TriWalk& w = wk[k];
-		P.prim_band[pid] = make_uint2(base, tr_hi[k]);
-		P.prims[pid] = pr[k];
-		/* the walk (swgl.c:3356-3361, 3466-3471), recording the state at every band entry */
-		float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
-		bool switched = false;
-		uint32_t tr = tr_hi[k];
-		int band_last_y = P.ytop - (int)(tr << SWGL_TILE_SHIFT);   /* last raster row of this band */
-		float ex0 = x0, ex1 = x1;
-		int cmin = 0x7fffffff, cmax = -1;
-		for (int y = w.ys; y < w.ye; y++)
+		const uint32_t c1 = pk[k] >> 16;
+		uint32_t cx = pk[k] & 0xffffu;
+		const bool valid = pk[k] != 0xffffffffu;
+		while (__any_sync(0xffffffffu, valid && cx <= c1))
 		{
-			int xa, xb;
-			row_span(x0, x1, P, xa, xb);
-			if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
-			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-			x0 += w.s0; x1 += s1;
-			if (y == band_last_y || y == w.ye - 1)
+			const bool have = valid && cx <= c1;
+			const uint32_t tile = have ? (tr_top - (uint32_t)k) * P.tiles_x + cx : 0xffffffffu;
+			const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+			const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+			uint32_t base = 0;
+			if (have && lane == leader) base = atomicAdd(&P.tile_count[tile], (uint32_t)__popc(peers));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (have)
 			{
-				BandEntry e;
-				e.x0 = ex0; e.x1 = ex1; e.prim = pid; e.cols = 0xffffffffu;
-				if (cmax >= 0 && owns_tile_row(P, tr))
-				{
-					const uint32_t c0 = (uint32_t)cmin >> SWGL_TILE_SHIFT, c1 = (uint32_t)cmax >> SWGL_TILE_SHIFT;
-					e.cols = c0 | (c1 << 11) | (tr << 22);
-					for (uint32_t cx = c0; cx <= c1; cx++) atomicAdd(&P.tile_count[tr * P.tiles_x + cx], 1u);
-				}
-				P.bands[base + (tr_hi[k] - tr)] = e;
-				tr--; band_last_y += SWGL_TILE;
-				ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
+				const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+				if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = 2u * t;
+				else atomicOr(&P.ctr->overflow, 1u);
 			}
+			cx++;
 		}
-		base += nbv[k];
 	}
+
+	/* primitives that reached the rasteriser: one atomic per warp */
+	for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+	if (lane == 0 && live) atomicAdd(&P.ctr->prims_out, live);
 }
 
-/* ---- exclusive scan of the tile counts (one CTA) ---- */
-__global__ void __launch_bounds__(1024) k_scan_tiles(const __grid_constant__ DrawParams P)
+/* ---- list insertion for tall primitives: one thread per band entry ---- */
+__global__ void __launch_bounds__(256) k_bin_tall(const __grid_constant__ DrawParams P)
 {
-	__shared__ uint32_t warp_sums[32];
-	__shared__ uint32_t carry_s;
-	const uint32_t n = P.tiles_x * P.tiles_y;
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-	if (tid == 0) carry_s = 0;
-	__syncthreads();
-	const bool dropped = P.ctr->overflow != 0;
-	for (uint32_t base = 0; base < n; base += 1024u)
-	{
-		uint32_t i = base + tid;
-		uint32_t c = (i < n) ? P.tile_count[i] : 0u;
-		if (dropped && i < n) P.tile_count[i] = 0u;
-		uint32_t x = c;
-		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
-		if (lane == 31) warp_sums[wid] = x;
-		__syncthreads();
-		if (wid == 0)
-		{
-			uint32_t s = warp_sums[lane];
-			for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane >= o) s += y; }
-			warp_sums[lane] = s;
-		}
-		__syncthreads();
-		const uint32_t carry = carry_s;
-		uint32_t excl = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - c);
-		if (i < n) P.tile_off[i] = excl;
-		__syncthreads();
-		if (tid == 1023) carry_s = carry + warp_sums[31];
-		__syncthreads();
-	}
-	if (tid == 0)
-	{
-		const uint32_t total = carry_s;
-		P.tile_off[n] = total;
-		P.ctr->pair_total = total;
-		if (total > P.cap_pairs) P.ctr->overflow = 1u;
-	}
-	/* a dropped draw must leave the counts zero for the next one */
-	__syncthreads();
-	if (!dropped && P.ctr->overflow)
-		for (uint32_t i = tid; i < n; i += 1024u) P.tile_count[i] = 0u;
-}
-
-/* ---- per-tile primitive lists: one thread per band entry ---- */
-__global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ DrawParams P)
-{
-	if (P.ctr->overflow) return;
+	if (P.ctr->overflow & 2u) return;
 	const uint32_t total = P.ctr->band_cursor;
 	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
 	{
 		const BandEntry be = P.bands[e];
 		if (be.cols == 0xffffffffu) continue;
 		const uint32_t c0 = be.cols & 0x7ffu, c1 = (be.cols >> 11) & 0x7ffu, tr = be.cols >> 22;
-		for (uint32_t cx = c0; cx <= c1; cx++)
-		{
-			const uint32_t tile = tr * P.tiles_x + cx;
-			/* counting back down to zero re-arms tile_count for the next draw */
-			const uint32_t slot = atomicSub(&P.tile_count[tile], 1u) - 1u;
-			P.pairs[P.tile_off[tile] + slot] = be.prim;
-		}
+		for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, be.prim);
 	}
 }
 
@@ -500,6 +479,46 @@ __device__ __forceinline__ float4 run_fragment(const DrawParams& P, const FragIn
 	float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 	for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
 	return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+/* The tile's list length; the cursor is re-armed (zeroed) for the next draw.  Whole CTA calls it. */
+__device__ __forceinline__ uint32_t take_tile_list(const DrawParams& P, uint32_t tile)
+{
+	__shared__ uint32_t n_s;
+	if (threadIdx.x == 0)
+	{
+		const uint32_t n = P.tile_count[tile];
+		if (n) P.tile_count[tile] = 0u;
+		if (n > P.bin_cap) atomicMax(&P.ctr->max_list, n);
+		else if (n && P.count_fragments) atomicAdd(&P.ctr->pair_total, (unsigned long long)n);
+		n_s = n;
+	}
+	__syncthreads();
+	return min(n_s, P.bin_cap);
+}
+
+/* Walk state (x0, x1, s1, switched) of a primitive on entering row y_in of tile row `ty`
+ * (swgl.c:3350-3356, 3466-3471): from the band entry for tall primitives, by replaying the
+ * additions from the first row for short ones. */
+__device__ __forceinline__ void walk_to_row(const DrawParams& P, const TriWalk& w, uint32_t band, uint32_t ty, int y_in,
+                                            float& x0, float& x1, float& s1, bool& switched)
+{
+	if (y_in == w.ys) { x0 = w.c0x; x1 = w.c0x; s1 = w.s1; switched = false; return; }
+	if (band != 0xffffffffu)
+	{
+		const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> SWGL_TILE_SHIFT;
+		const BandEntry be = P.bands[band + (tr_hi - ty)];
+		x0 = be.x0; x1 = be.x1;
+		switched = (float)y_in >= w.c1y;
+		s1 = switched ? w.s2 : w.s1;
+		return;
+	}
+	x0 = w.c0x; x1 = w.c0x; s1 = w.s1; switched = false;
+	for (int y = w.ys; y < y_in; y++)
+	{
+		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+		x0 += w.s0; x1 += s1;
+	}
 }
 
 /* ---- per-tile rasteriser, pixel-owner form ----
@@ -567,14 +586,13 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RasterShared& S = *reinterpret_cast<RasterShared*>(smem_raw);
 
-	if (P.ctr->overflow) return;
 	const uint32_t tx = blockIdx.x, ty = blockIdx.y;
 	if (!owns_tile_row(P, ty)) return;
 	const uint32_t tile = ty * P.tiles_x + tx;
-	const uint32_t list_off = P.tile_off[tile];
-	const uint32_t n_list = P.tile_off[tile + 1] - list_off;
-
 	const uint32_t tid = threadIdx.x;
+	const uint32_t n_list = take_tile_list(P, tile);
+	if (P.ctr->overflow || P.diag) return;
+	const size_t list_off = (size_t)tile * P.bin_cap;
 	const uint32_t q = tid & 7u, r = tid >> 3;             /* strip column group, tile row */
 	const int px0 = (int)(tx << SWGL_TILE_SHIFT) + (int)(q << 2);
 	const int row = (int)(ty << SWGL_TILE_SHIFT) + (int)r; /* storage row */
@@ -644,15 +662,13 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 			{
 				const uint32_t pid = ids[base + tid];
 				const Prim pr = P.prims[pid];
-				const uint2 pb = P.prim_band[pid];
-				const BandEntry be = P.bands[pb.x + (pb.y - ty)];
 				TriWalk w;
 				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
 				const int y_in = max(w.ys, band_first_y);
 				const int y_out = min(w.ye - 1, band_last_y);
-				float x0 = be.x0, x1 = be.x1;
-				bool switched = (y_in > w.ys) && ((float)y_in >= w.c1y);
-				float s1 = switched ? w.s2 : w.s1;
+				float x0, x1, s1;
+				bool switched;
+				walk_to_row(P, w, pr.band, ty, y_in, x0, x1, s1, switched);
 				uint32_t mask = 0;
 				for (int rr = 0; rr < SWGL_TILE; rr++) S.span[rr][tid] = 0;
 				for (int y = y_in; y <= y_out; y++)
@@ -798,11 +814,11 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->stream = nullptr; c->color = nullptr; c->depth = nullptr; c->h_color = nullptr; c->h_depth = nullptr;
 	c->peer_color = nullptr; c->rank = 0; c->n_ranks = 1; c->band_rows = 1;
 	c->clip = nullptr; c->cap_clip = 0; c->vary = nullptr; c->cap_vary = 0;
-	c->prims = nullptr; c->cap_prims = 0; c->prim_band = nullptr; c->cap_prim_band = 0;
+	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
-	c->tile_count = nullptr; c->tile_off = nullptr; c->ctr = nullptr; c->h_ctr = nullptr;
+	c->tile_count = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
-	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0;
+	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
 	c->n_launches = 0; c->stage_draws = 0;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
@@ -817,7 +833,8 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMallocHost((void**)&c->h_color, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_depth, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->tile_count, (ntiles + 1) * 4) == cudaSuccess
-	       && cudaMalloc((void**)&c->tile_off, (ntiles + 2) * 4) == cudaSuccess
+	       && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->setup_event, cudaEventDisableTiming) == cudaSuccess
 	       && cudaMalloc((void**)&c->ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->ctr_event, cudaEventDisableTiming) == cudaSuccess
@@ -854,11 +871,12 @@ void swgldev_destroy(swgldev_ctx* c)
 	for (void* p : c->allocations) cudaFree(p);
 	for (auto& kv : c->code_cache) cudaFree(kv.second);
 	cudaFree(c->color); cudaFree(c->depth); cudaFreeHost(c->h_color); cudaFreeHost(c->h_depth);
-	cudaFree(c->tile_count); cudaFree(c->tile_off); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
+	cudaFree(c->tile_count); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
+	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+	if (c->setup_event) cudaEventDestroy(c->setup_event);
 	if (c->clip) cudaFree(c->clip);
 	if (c->vary) cudaFree(c->vary);
 	if (c->prims) cudaFree(c->prims);
-	if (c->prim_band) cudaFree(c->prim_band);
 	if (c->bands) cudaFree(c->bands);
 	if (c->pairs) cudaFree(c->pairs);
 	if (c->ctr_event) cudaEventDestroy(c->ctr_event);
@@ -915,28 +933,67 @@ int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t by
  * its scratch was too small, grow and re-issue it before anything later is queued ---- */
 static int launch_draw(swgldev_ctx* c, DrawParams& P);
 
+/* per-tile lists may take up to opt_bin_limit bytes (default 6 GiB); beyond that draws are split */
+
+/* Snapshot of the previous draw's counters (taken right after its set-up kernel, on the side
+ * stream).  If its binning scratch was too small every kernel after set-up has exited without
+ * touching the framebuffer; grow and run it again before anything later is queued.  A draw whose
+ * lists cannot fit at all is split in two halves by triangles -- consecutive sub-draws keep the
+ * per-pixel submission order, so the result is the same. */
+static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth);
+
 static int settle_last_draw(swgldev_ctx* c)
 {
-	int guard = 0;
-	while (c->ctr_pending)
+	if (!c->ctr_pending) return 0;
+	CK(cudaEventSynchronize(c->ctr_event));
+	c->ctr_pending = 0;
+	if (!c->h_ctr->overflow || !c->last_draw_valid) return 0;
+	const DrawParams P = c->last_draw;
+	c->last_draw_valid = 0;
+	return resolve_and_reissue(c, P, 0);
+}
+
+/* Launch `P` and wait for it; resolve overflows until it has been drawn. */
+static int issue_sync(swgldev_ctx* c, DrawParams P, int depth)
+{
+	if (launch_draw(c, P)) return -1;
+	c->ctr_pending = 0;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaStreamSynchronize(c->side));
+	if (!c->h_ctr->overflow) return 0;
+	return resolve_and_reissue(c, P, depth + 1);
+}
+
+/* Precondition: the last attempt at `P` was dropped by the device (overflow flag set). */
+static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
+{
+	if (depth > 64) { set_err(c, "draw dropped: binning scratch could not be sized", cudaSuccess); return -1; }
+	CK(cudaStreamSynchronize(c->stream));
+	Counters h;
+	CK(cudaMemcpy(&h, c->ctr, sizeof(h), cudaMemcpyDeviceToHost));
+	if (h.overflow & 2u)
+		if (grow(c, &c->bands, &c->cap_bands, (size_t)h.band_cursor + (size_t)h.band_cursor / 4 + 1024)) return -1;
+	if (h.overflow & 1u)
 	{
-		CK(cudaEventSynchronize(c->ctr_event));
-		c->ctr_pending = 0;
-		const Counters& h = *c->h_ctr;
-		c->stats.prims_out = h.prims_out;
-		c->stats.tile_pairs = h.pair_total;
-		c->stats.bands = h.band_cursor;
-		if (!h.overflow || !c->last_draw_valid) break;
-		if (++guard > 6) { set_err(c, "draw dropped: binning scratch could not be sized", cudaSuccess); break; }
-		/* grow to what the dropped draw asked for, then run it again */
-		size_t need_bands = (size_t)h.band_cursor + 1024, need_pairs = (size_t)h.pair_total + 1024;
-		if (h.band_cursor > c->cap_bands) need_pairs = need_pairs < c->cap_pairs * 2 ? c->cap_pairs * 2 : need_pairs;
-		if (grow(c, &c->bands, &c->cap_bands, need_bands)) return -1;
-		if (grow(c, &c->pairs, &c->cap_pairs, need_pairs)) return -1;
-		DrawParams P = c->last_draw;
-		if (launch_draw(c, P)) return -1;
+		const size_t ntiles = (size_t)c->tiles_x * c->tiles_y;
+		size_t want = (size_t)h.max_list + (size_t)h.max_list / 4 + 64;
+		if (want < 2 * (size_t)c->bin_cap) want = 2 * (size_t)c->bin_cap;
+		if (want * ntiles * 4 > c->opt_bin_limit)
+		{
+			if (P.ntri < 2) { set_err(c, "draw dropped: one primitive list exceeds the bin memory limit", cudaSuccess); return -1; }
+			/* split by triangles: first half (keeps the fused clear), then second half */
+			DrawParams A = P, B = P;
+			A.ntri = P.ntri / 2; A.count = 3u * A.ntri;
+			B.ntri = P.ntri - A.ntri; B.count = P.count - A.count; B.first = P.first + (int32_t)A.count;
+			B.clear.flags = 0;
+			if (!P.ibo) { A.n_shade = 3u * A.ntri; B.n_shade = 3u * B.ntri; A.clip_vid_base = A.n_shade; B.clip_vid_base = B.n_shade; }
+			if (issue_sync(c, A, depth + 1)) return -1;
+			return issue_sync(c, B, depth + 1);
+		}
+		if (grow(c, &c->pairs, &c->cap_pairs, want * ntiles)) return -1;
+		c->bin_cap = (uint32_t)(c->cap_pairs / ntiles);
 	}
-	return 0;
+	return issue_sync(c, P, depth);
 }
 
 static int flush_clear(swgldev_ctx* c)
@@ -1006,7 +1063,7 @@ static const swgl_ir_op* upload_code(swgldev_ctx* c, uint64_t id, const swgl_ir_
 static int launch_draw(swgldev_ctx* c, DrawParams& P)
 {
 	P.cap_bands = (uint32_t)(c->cap_bands > 0xffffffffull ? 0xffffffffull : c->cap_bands);
-	P.cap_pairs = (uint32_t)(c->cap_pairs > 0xffffffffull ? 0xffffffffull : c->cap_pairs);
+	P.bin_cap = c->bin_cap;
 	P.bands = c->bands; P.pairs = c->pairs;
 	c->last_draw = P; c->last_draw_valid = 1;
 
@@ -1019,25 +1076,26 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	STAGE(1);
 	k_setup_bin<<<(P.ntri + 127u) / 128u, 128, 0, c->stream>>>(P);
+	k_bin_tall<<<148, 256, 0, c->stream>>>(P);
 	STAGE(2);
-	k_scan_tiles<<<1, 1024, 0, c->stream>>>(P);
-	STAGE(3);
-	CK(cudaMemcpyAsync(c->h_ctr, c->ctr, 16, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaEventRecord(c->ctr_event, c->stream));
+	/* overflow flags are final once set-up is done: snapshot them on the side stream so the next
+	 * draw can be queued while this one is still rasterising */
+	CK(cudaEventRecord(c->setup_event, c->stream));
+	CK(cudaStreamWaitEvent(c->side, c->setup_event, 0));
+	CK(cudaMemcpyAsync(c->h_ctr, c->ctr, 16, cudaMemcpyDeviceToHost, c->side));
+	CK(cudaEventRecord(c->ctr_event, c->side));
 	c->ctr_pending = 1;
-	k_fill_bins<<<148 * 8, 256, 0, c->stream>>>(P);
-	STAGE(4);
 	if (P.fs_kind == SWFS_VARYING) launch_raster<SWFS_VARYING>(c, P);
 	else if (P.fs_kind == SWFS_TEXTURE) launch_raster<SWFS_TEXTURE>(c, P);
 	else launch_raster<SWFS_GENERIC>(c, P);
-	STAGE(5);
+	STAGE(3);
 #undef STAGE
-	c->n_launches += 5;
+	c->n_launches += 4;
 	CK(cudaGetLastError());
 	if (timing)
 	{
-		CK(cudaEventSynchronize(c->stage_ev[5]));
-		for (int i = 0; i < 5; i++)
+		CK(cudaEventSynchronize(c->stage_ev[3]));
+		for (int i = 0; i < 3; i++)
 		{
 			float ms = 0.0f;
 			if (cudaEventElapsedTime(&ms, c->stage_ev[i], c->stage_ev[i + 1]) == cudaSuccess) c->stage_us[i] += 1000.0 * ms;
@@ -1105,6 +1163,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (d->vs_image) memcpy(P.vs_image, d->vs_image, 4u * d->vs_words);
 	if (d->fs_image) memcpy(P.fs_image, d->fs_image, 4u * d->fs_words);
 	P.count_fragments = (uint32_t)c->opt_count_fragments;
+	P.diag = (uint32_t)c->opt_diag;
 
 	if (P.vs_kind == SWVS_GENERIC)
 	{
@@ -1122,11 +1181,15 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (grow(c, &c->clip, &c->cap_clip, (size_t)P.n_shade)) return -1;
 	if (grow(c, &c->vary, &c->cap_vary, ((size_t)P.n_shade + n_prims) * (P.nvf ? P.nvf : 1) + 4)) return -1;
 	if (grow(c, &c->prims, &c->cap_prims, n_prims)) return -1;
-	if (grow(c, &c->prim_band, &c->cap_prim_band, n_prims)) return -1;
-	if (grow(c, &c->bands, &c->cap_bands, n_prims * 2 + (1u << 20))) return -1;
-	if (grow(c, &c->pairs, &c->cap_pairs, n_prims * 3 + (1u << 21))) return -1;
-	P.clip = c->clip; P.vary = c->vary; P.prims = c->prims; P.prim_band = c->prim_band;
-	P.tile_count = c->tile_count; P.tile_off = c->tile_off; P.ctr = c->ctr;
+	if (grow(c, &c->bands, &c->cap_bands, (size_t)1 << 16)) return -1;
+	{
+		/* per-tile lists: K entries each, K grows (never shrinks) when a draw overflows it */
+		const size_t ntiles = (size_t)c->tiles_x * c->tiles_y;
+		if (c->bin_cap == 0) c->bin_cap = 512;
+		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
+	}
+	P.clip = c->clip; P.vary = c->vary; P.prims = c->prims;
+	P.tile_count = c->tile_count; P.ctr = c->ctr;
 
 	/* fused clear: the raster kernel starts the covered pixels from the clear value */
 	P.clear = c->pending_clear;
@@ -1214,6 +1277,13 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	if (!strcmp(name, "fuse_clear")) c->opt_fuse_clear = (int)value;
 	else if (!strcmp(name, "count_fragments")) c->opt_count_fragments = (int)value;
 	else if (!strcmp(name, "raster_path")) c->opt_raster_path = (int)value;
+	else if (!strcmp(name, "diag")) c->opt_diag = (int)value;
+	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
+	else if (!strcmp(name, "bin_cap") && value > 0)
+	{
+		/* test hook: force a (small) list capacity for the next draws */
+		c->bin_cap = (uint32_t)value;
+	}
 	else if (!strcmp(name, "stage_timing"))
 	{
 		c->opt_stage_timing = (int)value;
@@ -1231,7 +1301,8 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "tile_size")) return SWGL_TILE;
 	if (!strcmp(name, "kernel_launches")) return (int64_t)c->n_launches;
 	if (!strcmp(name, "stage_draws")) return (int64_t)c->stage_draws;
-	if (!strncmp(name, "stage_ns_", 9)) { int i = atoi(name + 9); return (i >= 0 && i < 5) ? (int64_t)(c->stage_us[i] * 1000.0) : -1; }
+	if (!strncmp(name, "stage_ns_", 9)) { int i = atoi(name + 9); return (i >= 0 && i < 3) ? (int64_t)(c->stage_us[i] * 1000.0) : -1; }
+	if (!strcmp(name, "bin_cap")) return c->bin_cap;
 	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "sizeof_draw_params")) return (int64_t)sizeof(DrawParams);
 	return -1;

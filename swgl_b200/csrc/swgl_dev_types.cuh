@@ -7,12 +7,12 @@
  *   vary[V + 2T][NVF]  float    packed varyings; the last 2T records are the vertices the near
  *                               clipper creates (at most two per input triangle)
  *   prims[2T]          64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
- *                               record ids; slot 2t+k keeps submission order
- *   prim_band[2T]      uint2    first band-entry index, topmost tile row  (x = 0xffffffff: dead)
- *   bands[...]         16 B     per (primitive, tile row): span-walk state (x0, x1) on entering the
- *                               row band + the tile-column range the walk touches there
- *   tile_count/off[Nt] u32      bin sizes / exclusive scan
- *   pairs[...]         u32      per-tile primitive lists (unordered; sorted in the raster CTA)
+ *                               record ids + first band entry; slot 2t+k keeps submission order
+ *   bands[...]         16 B     TALL primitives only (> SWGL_SHORT_ROWS rows), per tile row: span-walk
+ *                               state (x0, x1) on entering the row band + tile columns touched there
+ *   tile_count[Nt]     u32      per-tile list length (atomic cursor; the raster CTA re-zeroes it)
+ *   pairs[Nt][K]       u32      per-tile primitive lists, fixed capacity K (unordered; sorted by
+ *                               primitive id inside the raster CTA)
  *   color/depth[H][W]  u32/f32  the framebuffer, row 0 = top (swgl.c:3156-3166)
  */
 #ifndef SWGL_DEV_TYPES_CUH
@@ -30,28 +30,31 @@
 #define SWGL_BATCH       256      /* primitives staged per raster batch */
 #define SWGL_SORT_CAP    2048     /* tile lists up to this length are sorted in shared memory */
 #define SWGL_CTR_SLOTS   64
+#define SWGL_SHORT_ROWS  64       /* primitives up to this many rows are re-walked from their top row */
 
 struct Prim
 {
 	float4   v[3];      /* (float)X, (float)Y, clip z, clip w -- submission order (swgl.c:3688-3691) */
 	uint32_t vid[3];    /* varying record of each vertex */
-	uint32_t pad;
+	uint32_t band;      /* tall primitives: first band entry; 0xffffffff: short, no entries */
 };
 
-struct BandEntry
+struct BandEntry                /* tall primitives only, one per tile row they cross */
 {
 	float    x0, x1;    /* walk state before the first row of the band (swgl.c:3351-3356) */
 	uint32_t prim;
 	uint32_t cols;      /* first tile column (11 bits) | last tile column << 11 | tile row << 22;
-	                       0xffffffff = touches nothing */
+	                       0xffffffff = touches nothing (or a tile row of another rank) */
 };
 
 struct Counters
 {
 	uint32_t band_cursor;       /* band entries requested */
-	uint32_t pair_total;        /* bin entries requested */
-	uint32_t overflow;          /* 1: scratch too small, draw dropped (re-issued by the host) */
+	uint32_t max_list;          /* longest tile list requested (only maintained when a list overflows) */
+	uint32_t overflow;          /* bit0: a tile list exceeded K, bit1: band scratch too small; the draw
+	                               is dropped and re-issued by the host */
 	uint32_t prims_out;
+	unsigned long long pair_total;   /* bin entries consumed by the raster CTAs */
 	unsigned long long tested[SWGL_CTR_SLOTS];
 	unsigned long long shaded[SWGL_CTR_SLOTS];
 };
@@ -88,8 +91,8 @@ struct DrawParams
 	int32_t first; uint32_t count, ntri, n_shade;
 	/* scratch */
 	float4* clip; float* vary; uint32_t nvf; uint32_t clip_vid_base;
-	Prim* prims; uint2* prim_band; BandEntry* bands; uint32_t cap_bands;
-	uint32_t* tile_count; uint32_t* tile_off; uint32_t* pairs; uint32_t cap_pairs;
+	Prim* prims; BandEntry* bands; uint32_t cap_bands;
+	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
 	Counters* ctr;
 	/* shaders */
 	int32_t vs_kind, fs_kind;
@@ -105,6 +108,7 @@ struct DrawParams
 	/* fused clear */
 	ClearParams clear;
 	uint32_t count_fragments;
+	uint32_t diag;              /* development only: skip parts of kernels to attribute time */
 	/* initial variable files (uniform values) for the generic evaluator */
 	uint32_t vs_image[SWGL_MAX_VAR_WORDS];
 	uint32_t fs_image[SWGL_MAX_VAR_WORDS];

@@ -109,16 +109,16 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	FragShared& S = *reinterpret_cast<FragShared*>(smem_raw);
 
-	if (P.ctr->overflow) return;
 	const uint32_t tx = blockIdx.x, ty = blockIdx.y;
 	if (!owns_tile_row(P, ty)) return;
 	const uint32_t tile = ty * P.tiles_x + tx;
-	const uint32_t list_off = P.tile_off[tile];
-	const uint32_t n_list = P.tile_off[tile + 1] - list_off;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t n_list = take_tile_list(P, tile);
+	if (P.ctr->overflow || P.diag) return;
+	const size_t list_off = (size_t)tile * P.bin_cap;
 	const ClearParams cp = P.clear;
 	if (n_list == 0 && !cp.flags) return;
 
-	const uint32_t tid = threadIdx.x;
 	const int tile_x0 = (int)(tx << SWGL_TILE_SHIFT), tile_r0 = (int)(ty << SWGL_TILE_SHIFT);
 
 	/* ---- stage the tile: 4x1 strip per thread, 4 passes of 8 rows ---- */
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 			{
 				const uint32_t pid = S.ids[tid];
 				pr.v[0] = P.prims[pid].v[0]; pr.v[1] = P.prims[pid].v[1]; pr.v[2] = P.prims[pid].v[2];
+				pr.band = P.prims[pid].band;
 				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
 				y_in = max(w.ys, band_first_y);
 				y_out = min(w.ye - 1, band_last_y);
@@ -257,16 +258,9 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 			uint32_t my_frags = 0;
 			if (tid < nb)
 			{
-				float x0, x1;
-				if (y_in == w.ys) { x0 = w.c0x; x1 = w.c0x; }        /* starts in this band */
-				else
-				{
-					const uint2 pb = P.prim_band[S.ids[tid]];
-					const BandEntry be = P.bands[pb.x + (pb.y - ty)];
-					x0 = be.x0; x1 = be.x1;
-				}
-				bool switched = (y_in > w.ys) && ((float)y_in >= w.c1y);
-				float s1 = switched ? w.s2 : w.s1;
+				float x0, x1, s1;
+				bool switched;
+				walk_to_row(P, w, pr.band, ty, y_in, x0, x1, s1, switched);
 				S.row0[tid] = (uint32_t)(band_last_y - y_out);       /* smallest tile row index */
 				for (int y = y_in; y <= y_out; y++)
 				{

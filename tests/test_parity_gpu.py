@@ -108,3 +108,33 @@ def test_depth_zero_reopens_pixels(gpu_api, restatement):
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["shaded"] == rstats["shaded"]
+
+
+def test_bin_overflow_grows_and_splits(gpu_api, restatement):
+    """Per-tile lists have a fixed capacity K.  A draw that overflows it is dropped by the device,
+    then re-issued with a larger K -- or, when the lists may not grow any further, split into
+    consecutive sub-draws (which keep the submission order).  Result must not change."""
+    scene = S.random_triangles(1200, 256, 192, seed=5, extent=0.6, alpha=0.5)
+    rc, rd, rstats = restatement.render(scene)
+    for path in (1, 2):
+        # K = 4: grows until the longest list fits
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path, "bin_cap": 4})
+        assert err == ""
+        assert_bit_exact(O.compare(col, dep, rc, rd), "grow " + PATHS[path])
+        assert gpu_api.swglGetOption(b"bin_cap") > 4
+        # K = 8 and lists limited to 16 entries per tile: the draw has to be split recursively
+        ntiles = ((scene.width + 31) // 32) * ((scene.height + 31) // 32)
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path, "bin_cap": 8,
+                                                                   "bin_limit_bytes": ntiles * 16 * 4})
+        assert err == ""
+        assert_bit_exact(O.compare(col, dep, rc, rd), "split " + PATHS[path])
+
+
+def test_tall_triangles_use_band_entries(gpu_api, restatement):
+    """Triangles taller than SWGL_SHORT_ROWS keep per-band walk states; shorter ones are re-walked."""
+    scene = S.random_triangles(300, 512, 768, seed=8, extent=0.95, alpha=0.7, centre_range=0.8)
+    rc, rd, rstats = restatement.render(scene)
+    for path in (1, 2):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+        assert err == "" and stats["bands"] > 0
+        assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])

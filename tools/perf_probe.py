@@ -10,7 +10,7 @@ import swgl_b200 as sw
 from swgl_b200 import gl as G, scenes as S
 
 api = sw.load()
-STAGES = ["vertex", "setup_bin", "scan", "fill", "raster"]
+STAGES = ["vertex", "setup_bin", "raster"]
 
 
 def probe(cfg, reps=10, options=None):
