@@ -114,6 +114,9 @@ int          swgldev_sync(swgldev_ctx* c);
 swgldev_ptr  swgldev_alloc(swgldev_ctx* c, uint64_t bytes);
 int          swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes);
 void         swgldev_free(swgldev_ctx* c, swgldev_ptr p);
+/* largest u32 in an uploaded element buffer (device reduction; the extension glDrawElements
+ * shades vertices [0, max] once each) */
+uint32_t     swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
 
 /* glClear (swgl.c:3183-3214): rectangle is viewport ∩ framebuffer, already resolved. */
 int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,

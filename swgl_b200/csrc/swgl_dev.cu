@@ -133,6 +133,15 @@ __global__ void k_fill_fb(uint32_t* __restrict__ color, float* __restrict__ dept
 	for (; i < n; i += stride) { color[i] = word; depth[i] = d; }
 }
 
+/* ---- largest index of an element buffer (decides how many vertices an indexed draw shades) ---- */
+__global__ void __launch_bounds__(256) k_max_index(const uint32_t* __restrict__ idx, size_t n, uint32_t* out)
+{
+	uint32_t m = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = max(m, __ldg(idx + i));
+	for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
+}
+
 /* ---- vertex stage (swgl.c:3618-3666) ---- */
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawParams P)
@@ -927,6 +936,21 @@ int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t by
 	CK(cudaMemcpyAsync((void*)(uintptr_t)dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return 0;
+}
+
+uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
+{
+	cudaSetDevice(c->device);
+	const size_t n = bytes / 4u;
+	if (!n) return 0;
+	uint32_t* d_out = &c->ctr->max_list;    /* scratch word; no draw is in flight when buffers are specified */
+	if (swgldev_sync(c)) return 0;
+	cudaMemsetAsync(d_out, 0, 4, c->stream);
+	k_max_index<<<148 * 4, 256, 0, c->stream>>>((const uint32_t*)(uintptr_t)indices, n, d_out);
+	uint32_t h = 0;
+	cudaMemcpyAsync(&h, d_out, 4, cudaMemcpyDeviceToHost, c->stream);
+	cudaStreamSynchronize(c->stream);
+	return h;
 }
 
 /* ---- deferred overflow check: wait for the counter snapshot of the previous draw and, when

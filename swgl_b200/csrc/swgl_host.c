@@ -391,10 +391,8 @@ void glBindBuffer(GLenum type, GLuint buffer)
 
 static void scan_indices(gl_buffer* b, const void* data, uint32_t size)
 {
-	const uint32_t* idx = (const uint32_t*)data;
-	uint32_t mx = 0;
-	for (uint32_t i = 0; i < size / 4; i++) if (idx[i] > mx) mx = idx[i];
-	b->max_index = mx;
+	(void)data;
+	b->max_index = swgldev_max_index(G.dev, b->data, size);   /* reduction on the device copy */
 }
 
 void glBufferData(GLenum target, GLsizei size, const void* data, GLenum usage)
