@@ -46,6 +46,7 @@ struct swgldev_ctx
 
 	/* grow-only scratch */
 	float4* clip; size_t cap_clip;
+	float2* clip_xy; size_t cap_clip_xy;
 	float* vary; size_t cap_vary;        /* floats */
 	Prim* prims; size_t cap_prims;
 	BandEntry* bands; size_t cap_bands;
@@ -142,6 +143,14 @@ __global__ void __launch_bounds__(256) k_max_index(const uint32_t* __restrict__ 
 	if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
 }
 
+__device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P)
+{
+	/* swgl.c:3685-3691: int <- x / w * (VW/2) + (VW/2) + VX, stored back as float */
+	int X = cvt_x86((fdiv(p.x, p.w) * P.hw + P.hw) + P.fvx);
+	int Y = cvt_x86((fdiv(p.y, p.w) * P.hh + P.hh) + P.fvy);
+	return make_float4((float)X, (float)Y, p.z, p.w);
+}
+
 /* ---- vertex stage (swgl.c:3618-3666) ---- */
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawParams P)
@@ -198,7 +207,10 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 			for (uint32_t j = 0; j < P.varying[k].n_floats; j++) vout[P.varying[k].slot + j] = t[j];
 		}
 	}
-	P.clip[v] = pos;
+	/* divide + viewport snap here, once per vertex (swgl.c:3685-3691 does it per triangle corner);
+	 * the clip-space x, y are kept for triangles that cross the near plane */
+	P.clip[v] = to_screen(pos, P);
+	P.clip_xy[v] = make_float2(pos.x, pos.y);
 }
 
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
@@ -228,13 +240,6 @@ __device__ __forceinline__ void lerp_vary(const DrawParams& P, uint32_t dst, uin
 	for (uint32_t k = 0; k < P.nvf; k++) { float x = pa[k], y = pb[k]; pd[k] = x + t * (y - x); }
 }
 
-__device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P)
-{
-	/* swgl.c:3685-3691: int <- x / w * (VW/2) + (VW/2) + VX, stored back as float */
-	int X = cvt_x86((fdiv(p.x, p.w) * P.hw + P.hw) + P.fvx);
-	int Y = cvt_x86((fdiv(p.y, p.w) * P.hh + P.hh) + P.fvy);
-	return make_float4((float)X, (float)Y, p.z, p.w);
-}
 
 /* list slot for primitive `pid` in `tile`, from the tile's atomic cursor */
 __device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, uint32_t pid)
@@ -256,7 +261,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
                                                    uint32_t va, uint32_t vb, uint32_t vc,
                                                    uint32_t& tr_top, uint32_t& pk0, uint32_t& pk1, uint32_t& pk2)
 {
-	a = to_screen(a, P); b = to_screen(b, P); c = to_screen(c, P);
+	/* a, b, c are already ((float)X, (float)Y, z_clip, w_clip) */
 	TriWalk w;
 	if (!tri_setup(a, b, c, P, w)) return 0u;
 	/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
@@ -343,7 +348,7 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 		const float4 q2 = near_intersect(p[a], p[out_idx[1]], t1);
 		lerp_vary(P, new0, sid[a], sid[out_idx[0]], t0);
 		lerp_vary(P, new1, sid[a], sid[out_idx[1]], t1);
-		return setup_one_prim<true>(P, 2u * t, p[a], q1, q2, sid[a], new0, new1, d0, d1, d2, d3);
+		return setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(q1, P), to_screen(q2, P), sid[a], new0, new1, d0, d1, d2, d3);
 	}
 	if (n_in == 2)
 	{
@@ -352,8 +357,9 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 		const float4 q1 = near_intersect(p[b], p[o], t1);
 		lerp_vary(P, new0, sid[a], sid[o], t0);
 		lerp_vary(P, new1, sid[b], sid[o], t1);
-		uint32_t live = setup_one_prim<true>(P, 2u * t, p[a], p[b], q0, sid[a], sid[b], new0, d0, d1, d2, d3);
-		live += setup_one_prim<true>(P, 2u * t + 1u, p[b], q0, q1, sid[b], new0, new1, d0, d1, d2, d3);
+		const float4 sq0 = to_screen(q0, P);
+		uint32_t live = setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(p[b], P), sq0, sid[a], sid[b], new0, d0, d1, d2, d3);
+		live += setup_one_prim<true>(P, 2u * t + 1u, to_screen(p[b], P), sq0, to_screen(q1, P), sid[b], new0, new1, d0, d1, d2, d3);
 		return live;
 	}
 	return 0u;
@@ -376,15 +382,19 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 			s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
 		}
 		const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		const float4 p0 = (s0 < P.n_shade) ? P.clip[s0] : zero;
-		const float4 p1 = (s1 < P.n_shade) ? P.clip[s1] : zero;
-		const float4 p2 = (s2 < P.n_shade) ? P.clip[s2] : zero;
+		/* an index past the shaded range reads as a zero clip-space vertex */
+		const float4 p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
+		const float4 p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
+		const float4 p2 = (s2 < P.n_shade) ? P.clip[s2] : to_screen(zero, P);
 		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
 		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
 		if (in_mask == 7u) live = setup_one_prim<false>(P, 2u * t, p0, p1, p2, s0, s1, s2, tr_top, pk[0], pk[1], pk[2]);
 		else if (in_mask != 0u)
 		{
-			const float4 p[3] = { p0, p1, p2 };
+			/* back to clip space for the intersection arithmetic */
+			const float2 zz = make_float2(0.0f, 0.0f);
+			const float2 c0 = (s0 < P.n_shade) ? P.clip_xy[s0] : zz, c1 = (s1 < P.n_shade) ? P.clip_xy[s1] : zz, c2 = (s2 < P.n_shade) ? P.clip_xy[s2] : zz;
+			const float4 p[3] = { make_float4(c0.x, c0.y, p0.z, p0.w), make_float4(c1.x, c1.y, p1.z, p1.w), make_float4(c2.x, c2.y, p2.z, p2.w) };
 			const uint32_t sid[3] = { s0, s1, s2 };
 			live = setup_clipped(P, t, p, sid, in_mask);
 		}
@@ -822,7 +832,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tiles_y = (height + SWGL_TILE - 1) / SWGL_TILE;
 	c->stream = nullptr; c->color = nullptr; c->depth = nullptr; c->h_color = nullptr; c->h_depth = nullptr;
 	c->peer_color = nullptr; c->rank = 0; c->n_ranks = 1; c->band_rows = 1;
-	c->clip = nullptr; c->cap_clip = 0; c->vary = nullptr; c->cap_vary = 0;
+	c->clip = nullptr; c->cap_clip = 0; c->clip_xy = nullptr; c->cap_clip_xy = 0; c->vary = nullptr; c->cap_vary = 0;
 	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
 	c->tile_count = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
@@ -884,6 +894,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->setup_event) cudaEventDestroy(c->setup_event);
 	if (c->clip) cudaFree(c->clip);
+	if (c->clip_xy) cudaFree(c->clip_xy);
 	if (c->vary) cudaFree(c->vary);
 	if (c->prims) cudaFree(c->prims);
 	if (c->bands) cudaFree(c->bands);
@@ -1203,6 +1214,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	/* scratch */
 	const size_t n_prims = 2ull * ntri;
 	if (grow(c, &c->clip, &c->cap_clip, (size_t)P.n_shade)) return -1;
+	if (grow(c, &c->clip_xy, &c->cap_clip_xy, (size_t)P.n_shade)) return -1;
 	if (grow(c, &c->vary, &c->cap_vary, ((size_t)P.n_shade + n_prims) * (P.nvf ? P.nvf : 1) + 4)) return -1;
 	if (grow(c, &c->prims, &c->cap_prims, n_prims)) return -1;
 	if (grow(c, &c->bands, &c->cap_bands, (size_t)1 << 16)) return -1;
@@ -1212,7 +1224,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		if (c->bin_cap == 0) c->bin_cap = 512;
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
 	}
-	P.clip = c->clip; P.vary = c->vary; P.prims = c->prims;
+	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims;
 	P.tile_count = c->tile_count; P.ctr = c->ctr;
 
 	/* fused clear: the raster kernel starts the covered pixels from the clear value */

@@ -3,7 +3,9 @@
  *
  * HBM layout of one draw (all scratch is grow-only and reused across draws):
  *
- *   clip[V]            float4   clip-space gl_Position of every shaded vertex
+ *   clip[V]            float4   per shaded vertex: ((float)X, (float)Y, z_clip, w_clip) -- divide + viewport snap
+ *                               done once per vertex instead of once per triangle corner
+ *   clip_xy[V]         float2   clip-space x, y (only read when a triangle crosses the near plane)
  *   vary[V + 2T][NVF]  float    packed varyings; the last 2T records are the vertices the near
  *                               clipper creates (at most two per input triangle)
  *   prims[2T]          64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
@@ -90,7 +92,7 @@ struct DrawParams
 	const uint32_t* ibo; unsigned long long ibo_count;
 	int32_t first; uint32_t count, ntri, n_shade;
 	/* scratch */
-	float4* clip; float* vary; uint32_t nvf; uint32_t clip_vid_base;
+	float4* clip; float2* clip_xy; float* vary; uint32_t nvf; uint32_t clip_vid_base;
 	Prim* prims; BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
 	Counters* ctr;

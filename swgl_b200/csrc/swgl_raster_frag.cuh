@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 				{
 					int xa, xb;
 					row_span(x0, x1, P, xa, xb);
-					xa = max(xa, tile_x0) - tile_x0;
+					xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;   /* both ends inside [0, 32]: they share a 16-bit word */
 					xb = min(xb, tile_x0 + SWGL_TILE) - tile_x0;
 					if (xb < xa) xb = xa;
 					/* spans are stored by ascending tile row = descending y */
