@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 				{
 					int xa, xb;
 					row_span(x0, x1, P, xa, xb);
-					xa = max(xa, tile_x0) - tile_x0;
-					xb = min(xb, tile_x0 + SWGL_TILE) - tile_x0;
+					xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
+					xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;   /* xb may be INT_MIN: clamp before subtracting */
 					if (xa < xb)
 					{
 						const int rr = band_last_y - y;

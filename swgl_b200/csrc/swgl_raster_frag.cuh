@@ -83,12 +83,19 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_t
 }
 
 /* blend with the destination unpacked through the byte/255.0f table */
+__device__ __forceinline__ float4 clamp_color(float4 o)
+{
+	/* swgl.c:3428-3431, ternary MIN/MAX: NaN -> 0 */
+	o.x = RMIN(RMAX(o.x, 0.0f), 1.0f);
+	o.y = RMIN(RMAX(o.y, 0.0f), 1.0f);
+	o.z = RMIN(RMAX(o.z, 0.0f), 1.0f);
+	o.w = RMIN(RMAX(o.w, 0.0f), 1.0f);
+	return o;
+}
+
+/* r, g, b, a already clamped */
 __device__ __forceinline__ uint32_t blend_pack_lut(float r, float g, float b, float a, uint32_t cur, const float* lut)
 {
-	r = RMIN(RMAX(r, 0.0f), 1.0f);
-	g = RMIN(RMAX(g, 0.0f), 1.0f);
-	b = RMIN(RMAX(b, 0.0f), 1.0f);
-	a = RMIN(RMAX(a, 0.0f), 1.0f);
 	const float cr = lut[(cur >> 24) & 0xFF], cg = lut[(cur >> 16) & 0xFF];
 	const float cb = lut[(cur >> 8) & 0xFF], ca = lut[cur & 0xFF];
 	r = cr + a * (r - cr);
@@ -175,30 +182,36 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 			/* every warp sorts 32 ids with a shuffle network, then each id finds its final place as
 			 * (its position in its own run) + (ids below it in the other runs, by binary search) */
 			const uint32_t lane = tid & 31u, wid = tid >> 5;
+			const uint32_t n_runs = (n_list + 31u) >> 5;
 			uint32_t x = tid < n_list ? gl_ids[tid] : 0xffffffffu;
+			if (wid < n_runs)
+			{
 #pragma unroll
-			for (uint32_t k = 2; k <= 32; k <<= 1)
+				for (uint32_t k = 2; k <= 32; k <<= 1)
 #pragma unroll
-				for (uint32_t j = k >> 1; j > 0; j >>= 1)
-				{
-					const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-					const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
-					x = keep_min ? min(x, y) : max(x, y);
-				}
-			S.u.sort_buf[tid] = x;
+					for (uint32_t j = k >> 1; j > 0; j >>= 1)
+					{
+						const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+						const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+						x = keep_min ? min(x, y) : max(x, y);
+					}
+				S.u.sort_buf[tid] = x;
+			}
 			__syncthreads();
 			if (x != 0xffffffffu)
 			{
+				/* lower bounds in all other runs at once (6 independent shared loads per step) */
+				uint32_t cnt[FRAG_BATCH / 32];
+#pragma unroll
+				for (uint32_t r = 0; r < FRAG_BATCH / 32; r++) cnt[r] = 0;
+#pragma unroll
+				for (uint32_t st = 32; st > 0; st >>= 1)
+#pragma unroll
+					for (uint32_t r = 0; r < FRAG_BATCH / 32; r++)
+						if (r < n_runs && r != wid && cnt[r] + st <= 32u && S.u.sort_buf[(r << 5) + cnt[r] + st - 1u] < x) cnt[r] += st;
 				uint32_t rank = lane;
-				const uint32_t n_runs = (n_list + 31u) >> 5;
-				for (uint32_t r = 0; r < n_runs; r++)
-				{
-					if (r == wid) continue;
-					const uint32_t* run = &S.u.sort_buf[r << 5];
-					uint32_t lo = 0, hi = 32;    /* first position whose id is >= x */
-					while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (run[mid] < x) lo = mid + 1; else hi = mid; }
-					rank += lo;
-				}
+#pragma unroll
+				for (uint32_t r = 0; r < FRAG_BATCH / 32; r++) rank += cnt[r];
 				S.ids[rank] = x;
 				gl_ids[rank] = x;        /* a batch cut short by a pool limit reloads from here */
 			}
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 					int xa, xb;
 					row_span(x0, x1, P, xa, xb);
 					xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;   /* both ends inside [0, 32]: they share a 16-bit word */
-					xb = min(xb, tile_x0 + SWGL_TILE) - tile_x0;
+					xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;   /* xb may be INT_MIN: clamp before subtracting */
 					if (xb < xa) xb = xa;
 					/* spans are stored by ascending tile row = descending y */
 					const uint32_t slot = my_span_base + (uint32_t)(y_out - y);
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 						fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 						fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 						fi.stride = 1;
-						o = run_fragment<FS>(P, fi);
+						o = clamp_color(run_fragment<FS>(P, fi));
 						shaded_early = true;
 					}
 				}
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 								fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 								fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 								fi.stride = 1;
-								o = run_fragment<FS>(P, fi);
+								o = clamp_color(run_fragment<FS>(P, fi));
 							}
 							S.color[pix] = blend_pack_lut(o.x, o.y, o.z, o.w, S.color[pix], S.lut);
 							tile_dirty = true;

@@ -58,11 +58,11 @@ for (fl, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{100*v[0]/tot:5.1f}% inst {100*v[2]/tots:5.1f}% smp  thr/inst {v[1]/max(v[0],1):5.1f}  {fl}:{ln}  {text}")
 
 # ---- region summary for swgl_raster_frag.cuh (line ranges of the kernel's phases) ----
-regions = [("stage tile", "swgl_raster_frag.cuh", 100, 160), ("sort", "swgl_raster_frag.cuh", 161, 196),
-           ("phase A", "swgl_raster_frag.cuh", 197, 281), ("B search", "swgl_raster_frag.cuh", 282, 305),
-           ("B commit", "swgl_raster_frag.cuh", 309, 340), ("write-back", "swgl_raster_frag.cuh", 341, 376),
-           ("stats", "swgl_raster_frag.cuh", 377, 400), ("blend", "swgl_raster_frag.cuh", 78, 99),
-           ("scan util", "swgl_raster_frag.cuh", 58, 77)]
+regions = [("kernel prologue/list", "swgl_raster_frag.cuh", 106, 123), ("stage tile", "swgl_raster_frag.cuh", 124, 168), ("sort", "swgl_raster_frag.cuh", 169, 216),
+           ("phase A1", "swgl_raster_frag.cuh", 217, 256), ("phase A2 walk", "swgl_raster_frag.cuh", 257, 280), ("A scan+map", "swgl_raster_frag.cuh", 281, 321),
+           ("B locate", "swgl_raster_frag.cuh", 322, 352), ("B early shade", "swgl_raster_frag.cuh", 353, 371), ("B commit", "swgl_raster_frag.cuh", 372, 412),
+           ("write-back", "swgl_raster_frag.cuh", 413, 446), ("stats", "swgl_raster_frag.cuh", 447, 470), ("blend", "swgl_raster_frag.cuh", 85, 105),
+           ("scan util", "swgl_raster_frag.cuh", 64, 84)]
 summ = collections.defaultdict(lambda: [0, 0])
 for (fl, ln), v in agg.items():
     name = None
