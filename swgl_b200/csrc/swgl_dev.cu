@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
 __device__ __forceinline__ bool owns_tile_row(const DrawParams& P, uint32_t tr)
 {
-	return P.n_ranks <= 1 || ((tr / P.band_rows) % P.n_ranks) == P.rank;
+	/* ownership is decided per band of 32 framebuffer rows whatever the tile height */
+	return P.n_ranks <= 1 || (((((tr << P.th_shift) >> 5) / P.band_rows) % P.n_ranks) == P.rank);
 }
 
 __device__ __forceinline__ float4 near_intersect(const float4& a, const float4& b, float& t)
@@ -251,9 +252,9 @@ __device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, u
 
 /* One primitive: divide + viewport snap, set-up, span walk.  Returns 1 if the primitive is live
  * (reaches the rasteriser on this rank).
- *   tall (> SWGL_SHORT_ROWS rows): one BandEntry per tile row (walk state + tile columns);
+ *   tall (more than two tile heights): one BandEntry per tile row (walk state + tile columns);
  *        k_bin_tall turns the entries into list insertions, one thread per entry;
- *   short (<= 3 tile rows): the tile columns of each band come back in pk[0..2]
+ *   short (at most 3 tile rows): the tile columns of each band come back in pk[0..2]
  *        (c0 | c1 << 16, 0xffffffff = none) for the warp-aggregated insertion of the caller,
  *        or are inserted right here when INLINE_INSERT. */
 template <bool INLINE_INSERT>
@@ -265,8 +266,8 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 	TriWalk w;
 	if (!tri_setup(a, b, c, P, w)) return 0u;
 	/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
-	const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> SWGL_TILE_SHIFT;
-	const uint32_t tr_lo = (uint32_t)(P.ytop - (w.ye - 1)) >> SWGL_TILE_SHIFT;
+	const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> P.th_shift;
+	const uint32_t tr_lo = (uint32_t)(P.ytop - (w.ye - 1)) >> P.th_shift;
 	if (P.n_ranks > 1)
 	{
 		/* sort-first: a primitive none of whose tile rows belong to this rank is dropped here */
@@ -275,7 +276,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		if (!mine) return 0u;
 	}
 	uint32_t band = 0xffffffffu;
-	if (w.ye - w.ys > SWGL_SHORT_ROWS)
+	if (w.ye - w.ys > (2 << P.th_shift))     /* short = at most two tile heights = at most 3 tile rows */
 	{
 		const uint32_t nb = tr_hi - tr_lo + 1u;
 		band = atomicAdd(&P.ctr->band_cursor, nb);
@@ -293,7 +294,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
 	bool switched = false;
 	uint32_t tr = tr_hi;
-	int band_last_y = P.ytop - (int)(tr << SWGL_TILE_SHIFT);   /* last raster row of this band */
+	int band_last_y = P.ytop - (int)(tr << P.th_shift);   /* last raster row of this band */
 	float ex0 = x0, ex1 = x1;
 	int cmin = 0x7fffffff, cmax = -1;
 	for (int y = w.ys; y < w.ye; y++)
@@ -325,7 +326,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 					if (bi == 0) pk0 = pk; else if (bi == 1) pk1 = pk; else pk2 = pk;
 				}
 			}
-			tr--; band_last_y += SWGL_TILE;
+			tr--; band_last_y += 1 << P.th_shift;
 			ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
 		}
 	}
@@ -518,14 +519,14 @@ __device__ __forceinline__ uint32_t take_tile_list(const DrawParams& P, uint32_t
 
 /* Walk state (x0, x1, s1, switched) of a primitive on entering row y_in of tile row `ty`
  * (swgl.c:3350-3356, 3466-3471): from the band entry for tall primitives, by replaying the
- * additions from the first row for short ones. */
+ * additions from the first row for short ones (at most two tile heights of float additions). */
 __device__ __forceinline__ void walk_to_row(const DrawParams& P, const TriWalk& w, uint32_t band, uint32_t ty, int y_in,
                                             float& x0, float& x1, float& s1, bool& switched)
 {
 	if (y_in == w.ys) { x0 = w.c0x; x1 = w.c0x; s1 = w.s1; switched = false; return; }
 	if (band != 0xffffffffu)
 	{
-		const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> SWGL_TILE_SHIFT;
+		const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> P.th_shift;
 		const BandEntry be = P.bands[band + (tr_hi - ty)];
 		x0 = be.x0; x1 = be.x1;
 		switched = (float)y_in >= w.c1y;
@@ -579,24 +580,28 @@ __device__ __forceinline__ void sort_ids_shared(uint32_t* ids, uint32_t n, uint3
 
 __device__ __forceinline__ void sort_ids_global(uint32_t* ids, uint32_t n)
 {
-	/* fallback for very long lists: in-place bitonic network over global memory (L2-resident),
-	 * virtual padding with 0xffffffff beyond n */
+	/* fallback for very long lists: in-place bitonic network over global memory (L2-resident) in its
+	 * "flip + half-cleaner" form -- every exchange moves the smaller key down, so the virtual
+	 * 0xffffffff padding beyond n never moves and n need not be a power of two */
 	uint32_t n_pow2 = 1; while (n_pow2 < n) n_pow2 <<= 1;
 	for (uint32_t k = 2; k <= n_pow2; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+	{
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
 		{
-			for (uint32_t i = threadIdx.x; i < n_pow2; i += blockDim.x)
+			const uint32_t l = i ^ (k - 1u);
+			if (l > i && l < n) { const uint32_t a = ids[i], b = ids[l]; if (a > b) { ids[i] = b; ids[l] = a; } }
+		}
+		__syncthreads();
+		for (uint32_t j = k >> 2; j > 0; j >>= 1)
+		{
+			for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
 			{
-				uint32_t ixj = i ^ j;
-				if (ixj > i && i < n)
-				{
-					uint32_t a = ids[i], b = ixj < n ? ids[ixj] : 0xffffffffu;
-					bool up = (i & k) == 0;
-					if ((a > b) == up && ixj < n) { ids[i] = b; ids[ixj] = a; }
-				}
+				const uint32_t l = i ^ j;
+				if (l > i && l < n) { const uint32_t a = ids[i], b = ids[l]; if (a > b) { ids[i] = b; ids[l] = a; } }
 			}
 			__syncthreads();
 		}
+	}
 }
 
 template <int FS>
@@ -803,16 +808,22 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
  * host side of the C ABI
  * ====================================================================================== */
 #include "swgl_raster_frag.cuh"
+#include "swgl_raster_warp.cuh"
 
-/* raster_path: 1 = pixel-owner (k_raster), 2 = fragment-parallel (k_raster_frag), 0 = default */
+/* raster_path: 1 = pixel-owner CTA per 32x32 tile (k_raster), 2 = fragment-parallel CTA per 32x32
+ * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp); 0 = default (3) */
+static int raster_path_of(const swgldev_ctx* c) { return (c->opt_raster_path >= 1 && c->opt_raster_path <= 3) ? c->opt_raster_path : 3; }
+static uint32_t th_shift_of(int path) { return path == 3 ? WT_H_SHIFT : SWGL_TILE_SHIFT; }
+
 template <int FS>
 static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 {
-	dim3 grid(c->tiles_x, c->tiles_y);
-	const int path = c->opt_raster_path == 1 ? 1 : 2;
+	const int path = raster_path_of(c);
 	c->last_raster_path = path;
+	dim3 grid(P.tiles_x, P.tiles_y);
 	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
-	else k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
+	else if (path == 2) k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
+	else k_raster_warp<FS><<<(P.tiles_x * P.tiles_y + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, 0, c->stream>>>(P);
 }
 
 extern "C" {
@@ -845,7 +856,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->n_draws = 0; c->error[0] = 0;
 
 	const size_t npx = (size_t)width * height;
-	const size_t ntiles = (size_t)c->tiles_x * c->tiles_y;
+	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
 	bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaMalloc((void**)&c->color, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->depth, (npx ? npx : 1) * 4) == cudaSuccess
@@ -1010,7 +1021,7 @@ static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 		if (grow(c, &c->bands, &c->cap_bands, (size_t)h.band_cursor + (size_t)h.band_cursor / 4 + 1024)) return -1;
 	if (h.overflow & 1u)
 	{
-		const size_t ntiles = (size_t)c->tiles_x * c->tiles_y;
+		const size_t ntiles = (size_t)c->tiles_x * ((c->H + WT_H - 1) / WT_H);   /* finest tiling */
 		size_t want = (size_t)h.max_list + (size_t)h.max_list / 4 + 64;
 		if (want < 2 * (size_t)c->bin_cap) want = 2 * (size_t)c->bin_cap;
 		if (want * ntiles * 4 > c->opt_bin_limit)
@@ -1150,7 +1161,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
 	 * several raster rows onto row Height-1, swgl.c:3386). */
 	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
-	    || c->tiles_x > 2047u || c->tiles_y > 1023u)
+	    || c->tiles_x > 2047u || (c->H + WT_H - 1) / WT_H > 1023u)
 	{
 		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
 		return flush_clear(c);
@@ -1172,7 +1183,8 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.xlimit = (float)(uint32_t)((uint32_t)d->vx + d->vw);
 	P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
 	P.ytop = (int32_t)d->vh - 1 + 2 * d->vy;
-	P.tiles_x = c->tiles_x; P.tiles_y = c->tiles_y;
+	P.th_shift = th_shift_of(raster_path_of(c));
+	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.rank = c->rank; P.n_ranks = c->n_ranks; P.band_rows = c->band_rows ? c->band_rows : 1;
 	P.vbo = (const uint8_t*)(uintptr_t)d->vbo; P.vbo_bytes = d->vbo_bytes;
 	P.ibo = (const uint32_t*)(uintptr_t)d->ibo; P.ibo_count = d->ibo_bytes / 4u;
@@ -1220,8 +1232,8 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (grow(c, &c->bands, &c->cap_bands, (size_t)1 << 16)) return -1;
 	{
 		/* per-tile lists: K entries each, K grows (never shrinks) when a draw overflows it */
-		const size_t ntiles = (size_t)c->tiles_x * c->tiles_y;
-		if (c->bin_cap == 0) c->bin_cap = 512;
+		const size_t ntiles = (size_t)c->tiles_x * ((c->H + WT_H - 1) / WT_H);   /* finest tiling */
+		if (c->bin_cap == 0) c->bin_cap = 256;
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
 	}
 	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims;

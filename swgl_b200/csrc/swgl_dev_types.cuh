@@ -10,7 +10,7 @@
  *                               clipper creates (at most two per input triangle)
  *   prims[2T]          64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
  *                               record ids + first band entry; slot 2t+k keeps submission order
- *   bands[...]         16 B     TALL primitives only (> SWGL_SHORT_ROWS rows), per tile row: span-walk
+ *   bands[...]         16 B     TALL primitives only (more than two tile heights), per tile row: span-walk
  *                               state (x0, x1) on entering the row band + tile columns touched there
  *   tile_count[Nt]     u32      per-tile list length (atomic cursor; the raster CTA re-zeroes it)
  *   pairs[Nt][K]       u32      per-tile primitive lists, fixed capacity K (unordered; sorted by
@@ -32,7 +32,6 @@
 #define SWGL_BATCH       256      /* primitives staged per raster batch */
 #define SWGL_SORT_CAP    2048     /* tile lists up to this length are sorted in shared memory */
 #define SWGL_CTR_SLOTS   64
-#define SWGL_SHORT_ROWS  64       /* primitives up to this many rows are re-walked from their top row */
 
 struct Prim
 {
@@ -85,8 +84,9 @@ struct DrawParams
 	float fvx, fvy;             /* (float)VX, (float)VY */
 	float xlimit, ylimit;       /* (float)(uint32)(VX+VW), (float)(uint32)(VY+VH) */
 	int32_t ytop;               /* VH-1+2*VY: storage row = ytop - y           swgl.c:3386 */
-	uint32_t tiles_x, tiles_y;
-	uint32_t rank, n_ranks, band_rows;
+	uint32_t tiles_x, tiles_y;  /* tiles are 32 wide and (1 << th_shift) tall: 32 (CTA kernels) or 8 (warp kernel) */
+	uint32_t th_shift;
+	uint32_t rank, n_ranks, band_rows;   /* sort-first bands, in units of 32 framebuffer rows */
 	/* geometry */
 	const uint8_t* vbo; unsigned long long vbo_bytes;
 	const uint32_t* ibo; unsigned long long ibo_count;

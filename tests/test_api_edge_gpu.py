@@ -240,7 +240,7 @@ def test_two_textures_on_other_units(gpu_api, reference):
     _assert_same(a, b, 100)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["pixel_owner", "fragment_parallel"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["pixel_owner", "fragment_parallel", "warp_tile"])
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
 def test_extreme_coordinates_and_w(gpu_api, reference, seed, path):
     """Huge / tiny / negative w, vertices far off screen, zero-area triangles: NaN and INT_MIN paths

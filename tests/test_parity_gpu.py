@@ -32,7 +32,7 @@ def _small_scenes():
     return out
 
 
-PATHS = {1: "pixel_owner", 2: "fragment_parallel"}
+PATHS = {1: "pixel_owner", 2: "fragment_parallel", 3: "warp_tile"}
 
 
 @pytest.mark.parametrize("path", sorted(PATHS), ids=lambda p: PATHS[p])
@@ -88,7 +88,7 @@ def test_long_tile_lists_and_span_pool_cuts(gpu_api, restatement):
     the per-batch pool, and lists beyond the shared-memory sort capacity (2048)."""
     scene = S.random_triangles(6000, 256, 192, seed=77, extent=0.9, alpha=0.5)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2):
+    for path in (1, 2, 3):
         col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
@@ -103,7 +103,7 @@ def test_depth_zero_reopens_pixels(gpu_api, restatement):
     v[::3, :, 2] = 0.0          # every third triangle lies exactly on z = 0
     v[1::7, :, 2] = -0.25       # some negative depths too
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2):
+    for path in (1, 2, 3):
         col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
@@ -116,7 +116,7 @@ def test_bin_overflow_grows_and_splits(gpu_api, restatement):
     consecutive sub-draws (which keep the submission order).  Result must not change."""
     scene = S.random_triangles(1200, 256, 192, seed=5, extent=0.6, alpha=0.5)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2):
+    for path in (1, 2, 3):
         # K = 4: grows until the longest list fits
         col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path, "bin_cap": 4})
         assert err == ""
@@ -134,7 +134,7 @@ def test_tall_triangles_use_band_entries(gpu_api, restatement):
     """Triangles taller than SWGL_SHORT_ROWS keep per-band walk states; shorter ones are re-walked."""
     scene = S.random_triangles(300, 512, 768, seed=8, extent=0.95, alpha=0.7, centre_range=0.8)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2):
+    for path in (1, 2, 3):
         col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
         assert err == "" and stats["bands"] > 0
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])

@@ -61,7 +61,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["pixel_owner", "fragment_parallel"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["pixel_owner", "fragment_parallel", "warp_tile"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_generic_shader_matches_compiled_reference(gpu_api, reference, name, path):
     vs, fs, uniforms = CASES[name]
