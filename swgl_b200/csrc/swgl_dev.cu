@@ -811,14 +811,21 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 #include "swgl_raster_warp.cuh"
 
 /* raster_path: 1 = pixel-owner CTA per 32x32 tile (k_raster), 2 = fragment-parallel CTA per 32x32
- * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp); 0 = default (3) */
-static int raster_path_of(const swgldev_ctx* c) { return (c->opt_raster_path >= 1 && c->opt_raster_path <= 3) ? c->opt_raster_path : 3; }
+ * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = choose per draw: meshes of
+ * small triangles (few framebuffer pixels per submitted triangle) go to the warp kernel, everything
+ * else to the fragment-parallel CTA kernel.  All three produce identical bits. */
+static int raster_path_for(const swgldev_ctx* c, uint32_t ntri)
+{
+	if (c->opt_raster_path >= 1 && c->opt_raster_path <= 3) return c->opt_raster_path;
+	const double px_per_tri = (double)c->W * (double)c->H / (double)(ntri ? ntri : 1u);
+	return px_per_tri <= 64.0 ? 3 : 2;
+}
 static uint32_t th_shift_of(int path) { return path == 3 ? WT_H_SHIFT : SWGL_TILE_SHIFT; }
 
 template <int FS>
 static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 {
-	const int path = raster_path_of(c);
+	const int path = P.th_shift == WT_H_SHIFT ? 3 : (c->opt_raster_path == 1 ? 1 : 2);
 	c->last_raster_path = path;
 	dim3 grid(P.tiles_x, P.tiles_y);
 	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
@@ -1183,7 +1190,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.xlimit = (float)(uint32_t)((uint32_t)d->vx + d->vw);
 	P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
 	P.ytop = (int32_t)d->vh - 1 + 2 * d->vy;
-	P.th_shift = th_shift_of(raster_path_of(c));
+	P.th_shift = th_shift_of(raster_path_for(c, ntri));
 	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.rank = c->rank; P.n_ranks = c->n_ranks; P.band_rows = c->band_rows ? c->band_rows : 1;
 	P.vbo = (const uint8_t*)(uintptr_t)d->vbo; P.vbo_bytes = d->vbo_bytes;

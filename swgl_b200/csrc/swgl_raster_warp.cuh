@@ -174,6 +174,48 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 		uint32_t first_batch_id = 0xffffffffu;
 		if (n_list <= 32)
 			first_batch_id = warp_sort32(lane < n_list ? gl_ids[lane] : 0xffffffffu, lane);
+		else if (n_list <= 128)
+		{
+			/* up to four runs of 32, each sorted with the shuffle network; an id's final place is its
+			 * position in its own run plus the ids below it in the other runs (branch-free lower
+			 * bounds, all runs in flight); ranks stay in registers until every lane has finished
+			 * reading the runs, then the ids are scattered to their final places */
+			const uint32_t n_runs = (n_list + 31u) >> 5;
+			uint32_t x[4], rank[4];
+#pragma unroll
+			for (uint32_t c = 0; c < 4; c++)
+			{
+				x[c] = 0xffffffffu;
+				if (c < n_runs)
+				{
+					const uint32_t i = (c << 5) + lane;
+					x[c] = warp_sort32(i < n_list ? gl_ids[i] : 0xffffffffu, lane);
+					T.ids[i] = x[c];
+				}
+			}
+			__syncwarp();
+#pragma unroll
+			for (uint32_t c = 0; c < 4; c++)
+			{
+				rank[c] = lane;
+				if (c < n_runs && x[c] != 0xffffffffu)
+				{
+					uint32_t cnt[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+					for (uint32_t st = 32; st > 0; st >>= 1)
+#pragma unroll
+						for (uint32_t r = 0; r < 4; r++)
+							if (r != c && r < n_runs && cnt[r] + st <= 32u && T.ids[(r << 5) + cnt[r] + st - 1u] < x[c]) cnt[r] += st;
+					rank[c] += cnt[0] + cnt[1] + cnt[2] + cnt[3];
+				}
+			}
+			__syncwarp();
+#pragma unroll
+			for (uint32_t c = 0; c < 4; c++)
+				if (c < n_runs && x[c] != 0xffffffffu) T.ids[rank[c]] = x[c];
+			__syncwarp();
+			sorted = T.ids;
+		}
 		else if (n_list <= WT_SORT_CAP)
 		{
 			for (uint32_t i = lane; i < n_list; i += 32) T.ids[i] = gl_ids[i];

@@ -63,6 +63,12 @@ regions = [("kernel prologue/list", "swgl_raster_frag.cuh", 106, 123), ("stage t
            ("B locate", "swgl_raster_frag.cuh", 322, 352), ("B early shade", "swgl_raster_frag.cuh", 353, 371), ("B commit", "swgl_raster_frag.cuh", 372, 412),
            ("write-back", "swgl_raster_frag.cuh", 413, 446), ("stats", "swgl_raster_frag.cuh", 447, 470), ("blend", "swgl_raster_frag.cuh", 85, 105),
            ("scan util", "swgl_raster_frag.cuh", 64, 84)]
+if "warp" in kern:
+    regions = [("prologue+list", "swgl_raster_warp.cuh", 120, 153), ("stage tile", "swgl_raster_warp.cuh", 154, 169), ("stage tile", "swgl_raster_warp.cuh", 83, 119),
+               ("sort", "swgl_raster_warp.cuh", 170, 185), ("sort", "swgl_raster_warp.cuh", 42, 82), ("phase A", "swgl_raster_warp.cuh", 186, 222),
+               ("scan", "swgl_raster_warp.cuh", 223, 231), ("B locate", "swgl_raster_warp.cuh", 232, 268), ("B weights+shade", "swgl_raster_warp.cuh", 269, 288),
+               ("B commit", "swgl_raster_warp.cuh", 289, 327), ("write-back", "swgl_raster_warp.cuh", 328, 362), ("stats", "swgl_raster_warp.cuh", 363, 380),
+               ("blend", "swgl_raster_frag.cuh", 85, 115)]
 summ = collections.defaultdict(lambda: [0, 0])
 for (fl, ln), v in agg.items():
     name = None
