@@ -42,7 +42,7 @@ for r in rows[2:]:
     scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
     rdb = rd * scale.get(units[ix["dram__bytes_read.sum"]], 1.0)
     wrb = wr * scale.get(units[ix["dram__bytes_write.sum"]], 1.0)
-    traffic[name if name != "k_raster_frag" else "k_raster"] = int(rdb + wrb)
+    traffic["k_raster" if name.startswith("k_raster") else name] = int(rdb + wrb)
 with open(out_md, "w") as f:
     f.write(f"# ncu --set full summary of `{os.path.basename(rep)}`\n\n")
     f.write("One frame of the workload (glClear fused + glDrawElements); per-launch values, cold-cache and\n"
