@@ -143,7 +143,7 @@ def run_own(args):
     peer = None
     if world > 1:
         tiles_y = (scene.height + 31) // 32
-        band_rows = max(1, tiles_y // (world * 8))   # >= 8 interleaved bands per rank
+        band_rows = max(1, tiles_y // (world * 16))  # >= 16 interleaved bands of 32 rows per rank
         api.swglSetStripe(rank, world, band_rows)
         peer = multigpu.PeerColorTarget(api, dist, rank, world)
 

@@ -125,6 +125,10 @@ int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,
 /* glDrawArrays(GL_TRIANGLES) / glDrawElements (swgl.c:3609-3710 + DrawTriangle 3314-3473). */
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d);
 
+/* glDrawArrays(GL_POINTS) (swgl.c:3496-3608): one pixel per vertex, x scaled by VH/2 (sic), no
+ * near clip, no depth test, no blend, no Y flip; the last point submitted to a pixel wins. */
+int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d);
+
 /* glGetFramePtr (swgl.c:3738): refreshes and returns the pinned host mirror. */
 uint32_t* swgldev_map_color(swgldev_ctx* c);
 float*    swgldev_map_depth(swgldev_ctx* c);

@@ -53,6 +53,7 @@ struct swgldev_ctx
 	uint32_t* pairs; size_t cap_pairs;   /* tiles * bin_cap entries */
 	uint32_t bin_cap;                    /* K */
 	uint32_t* tile_count;
+	uint32_t* winner;                    /* GL_POINTS arbitration, W*H words, kept zeroed between draws */
 	Counters* ctr; Counters* h_ctr;      /* device counters, pinned snapshot */
 	cudaStream_t side;                   /* counter snapshots travel here, off the critical path */
 	cudaEvent_t setup_event;             /* set-up kernel of the last draw finished */
@@ -807,6 +808,80 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 /* ========================================================================================
  * host side of the C ABI
  * ====================================================================================== */
+/* ---- GL_POINTS (swgl.c:3496-3608) ----
+ * One pixel per vertex: X = (int)(x/w * (VH/2) + (VW/2) + VX) -- the x scale really is VH/2
+ * (swgl.c:3531) -- Y = (int)(y/w * (VH/2) + (VH/2) + VY), no near clip, no Y flip, depth and
+ * colour are overwritten unconditionally.  Points are submitted in order, so the last point that
+ * lands on a pixel wins: pass 1 takes the maximum point index per pixel, pass 2 lets the winner
+ * run the fragment shader and store. */
+__device__ __forceinline__ bool point_pixel(const DrawParams& P, uint32_t i, uint32_t& vid, uint32_t& pix, float& z)
+{
+	vid = i;
+	if (P.ibo)
+	{
+		const unsigned long long at = (unsigned long long)(long long)P.first + i;
+		vid = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
+	}
+	float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	float2 xy = make_float2(0.0f, 0.0f);
+	if (vid < P.n_shade) { c = P.clip[vid]; xy = P.clip_xy[vid]; }
+	const int X = cvt_x86((fdiv(xy.x, c.w) * P.hh + P.hw) + P.fvx);
+	const int Y = cvt_x86((fdiv(xy.y, c.w) * P.hh + P.hh) + P.fvy);
+	if (X < 0 || X >= (int)P.W || Y < 0 || Y >= (int)P.H) return false;
+	if (P.n_ranks > 1 && ((((uint32_t)Y >> 5) / P.band_rows) % P.n_ranks) != P.rank) return false;
+	pix = (uint32_t)X + (uint32_t)Y * P.W;
+	z = c.z;
+	return true;
+}
+
+__global__ void __launch_bounds__(256) k_points_claim(const __grid_constant__ DrawParams P)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.count) return;
+	uint32_t vid, pix; float z;
+	if (point_pixel(P, i, vid, pix, z)) atomicMax(&P.winner[pix], i + 1u);
+}
+
+template <int FS>
+__global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ DrawParams P)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P.count) return;
+	uint32_t vid, pix; float z;
+	if (!point_pixel(P, i, vid, pix, z)) return;
+	if (P.winner[pix] != i + 1u) return;
+	P.winner[pix] = 0u;                      /* re-armed for the next draw */
+	/* varyings are copied, not interpolated (swgl.c:3537-3553) */
+	const float* vv = P.vary + (size_t)vid * P.nvf;
+	float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+	if (FS == SWFS_VARYING) { for (int k = 0; k < 4; k++) o[k] = vv[P.fs_slot + k]; }
+	else if (FS == SWFS_TEXTURE)
+	{
+		const float4 t = sample_nearest(P.tex[P.fs_tex_unit], vv[P.fs_slot + P.fs_swz_u], vv[P.fs_slot + P.fs_swz_v]);
+		o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+	}
+	else
+	{
+		uint32_t V[SWGL_MAX_VAR_WORDS];
+		for (uint32_t k = 0; k < P.fs_words; k++) V[k] = P.fs_image[k];
+		for (uint32_t k = 0; k < P.n_varying; k++)
+			for (uint32_t j = 0; j < P.varying[k].n_floats; j++)
+				V[P.varying[k].fs_word + j] = __float_as_uint(vv[P.varying[k].slot + j]);
+		ir_execute(P.fs_ops, P.fs_nops, V, P);
+		for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
+	}
+	const float r = RMIN(RMAX(o[0], 0.0f), 1.0f), g = RMIN(RMAX(o[1], 0.0f), 1.0f);
+	const float b = RMIN(RMAX(o[2], 0.0f), 1.0f), a = RMIN(RMAX(o[3], 0.0f), 1.0f);
+	uint32_t word = 0;                       /* swgl.c:3599-3603: no blend */
+	word |= (uint32_t)__float2int_rz(r * 255.0f) << 24;
+	word |= (uint32_t)__float2int_rz(g * 255.0f) << 16;
+	word |= (uint32_t)__float2int_rz(b * 255.0f) << 8;
+	word |= (uint32_t)__float2int_rz(a * 255.0f);
+	P.depth[pix] = z;                        /* swgl.c:3582-3583: written as is, no test */
+	P.color[pix] = word;
+	if (P.peer_color) P.peer_color[pix] = word;
+}
+
 #include "swgl_raster_frag.cuh"
 #include "swgl_raster_warp.cuh"
 
@@ -853,7 +928,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->clip = nullptr; c->cap_clip = 0; c->clip_xy = nullptr; c->cap_clip_xy = 0; c->vary = nullptr; c->cap_vary = 0;
 	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
-	c->tile_count = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
+	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
 	c->n_launches = 0; c->stage_draws = 0;
@@ -909,6 +984,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	for (auto& kv : c->code_cache) cudaFree(kv.second);
 	cudaFree(c->color); cudaFree(c->depth); cudaFreeHost(c->h_color); cudaFreeHost(c->h_depth);
 	cudaFree(c->tile_count); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
+	if (c->winner) cudaFree(c->winner);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->setup_event) cudaEventDestroy(c->setup_event);
 	if (c->clip) cudaFree(c->clip);
@@ -1158,30 +1234,15 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	return 0;
 }
 
-int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
+/* Everything of DrawParams that does not depend on the primitive type.  Returns 1 when the draw
+ * has to be skipped (error string set), 0 otherwise. */
+static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams& P)
 {
-	cudaSetDevice(c->device);
-	if (settle_last_draw(c)) return -1;
-	c->last_draw_valid = 0;
-
-	/* The tile mapping needs storage row = VH-1+2*VY-y to be a bijection on the viewport rows,
-	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
-	 * several raster rows onto row Height-1, swgl.c:3386). */
-	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
-	    || c->tiles_x > 2047u || (c->H + WT_H - 1) / WT_H > 1023u)
-	{
-		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
-		return flush_clear(c);
-	}
-	const uint32_t ntri = (d->count + 2u) / 3u;
-	if (ntri == 0 || d->vh == 0) return flush_clear(c);
 	if (d->varying_floats > SWGL_MAX_VARYING_FLOATS || d->vs_words > SWGL_MAX_VAR_WORDS || d->fs_words > SWGL_MAX_VAR_WORDS)
 	{
 		set_err(c, "draw skipped: shader interface too large", cudaSuccess);
-		return flush_clear(c);
+		return 1;
 	}
-
-	DrawParams P;
 	memset(&P, 0, sizeof(P));
 	P.color = c->color; P.depth = c->depth; P.peer_color = c->peer_color; P.W = c->W; P.H = c->H;
 	P.vx = d->vx; P.vy = d->vy; P.vw = d->vw; P.vh = d->vh;
@@ -1190,15 +1251,11 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.xlimit = (float)(uint32_t)((uint32_t)d->vx + d->vw);
 	P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
 	P.ytop = (int32_t)d->vh - 1 + 2 * d->vy;
-	P.th_shift = th_shift_of(raster_path_for(c, ntri));
-	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.rank = c->rank; P.n_ranks = c->n_ranks; P.band_rows = c->band_rows ? c->band_rows : 1;
 	P.vbo = (const uint8_t*)(uintptr_t)d->vbo; P.vbo_bytes = d->vbo_bytes;
 	P.ibo = (const uint32_t*)(uintptr_t)d->ibo; P.ibo_count = d->ibo_bytes / 4u;
-	P.first = d->first; P.count = d->count; P.ntri = ntri;
-	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
+	P.first = d->first; P.count = d->count;
 	P.nvf = d->varying_floats;
-	P.clip_vid_base = P.n_shade;
 	P.vs_kind = d->vs_kind; P.fs_kind = d->fs_kind;
 	P.vs_words = d->vs_words; P.fs_words = d->fs_words;
 	P.pos_word = d->pos_word; P.out_word = d->out_word; P.out_floats = d->out_floats;
@@ -1218,17 +1275,45 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (d->fs_image) memcpy(P.fs_image, d->fs_image, 4u * d->fs_words);
 	P.count_fragments = (uint32_t)c->opt_count_fragments;
 	P.diag = (uint32_t)c->opt_diag;
-
 	if (P.vs_kind == SWVS_GENERIC)
 	{
 		P.vs_ops = upload_code(c, d->vs_code_id, d->vs_code); P.vs_nops = d->vs_code->n_ops;
-		if (!P.vs_ops) { set_err(c, "vertex shader upload failed", cudaGetLastError()); return -1; }
+		if (!P.vs_ops) { set_err(c, "vertex shader upload failed", cudaGetLastError()); return 1; }
 	}
 	if (P.fs_kind == SWFS_GENERIC)
 	{
 		P.fs_ops = upload_code(c, d->fs_code_id, d->fs_code); P.fs_nops = d->fs_code->n_ops;
-		if (!P.fs_ops) { set_err(c, "fragment shader upload failed", cudaGetLastError()); return -1; }
+		if (!P.fs_ops) { set_err(c, "fragment shader upload failed", cudaGetLastError()); return 1; }
 	}
+	P.tile_count = c->tile_count; P.ctr = c->ctr;
+	return 0;
+}
+
+int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
+{
+	cudaSetDevice(c->device);
+	if (settle_last_draw(c)) return -1;
+	c->last_draw_valid = 0;
+
+	/* The tile mapping needs storage row = VH-1+2*VY-y to be a bijection on the viewport rows,
+	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
+	 * several raster rows onto row Height-1, swgl.c:3386). */
+	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
+	    || c->tiles_x > 2047u || (c->H + WT_H - 1) / WT_H > 1023u)
+	{
+		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
+		return flush_clear(c);
+	}
+	const uint32_t ntri = (d->count + 2u) / 3u;
+	if (ntri == 0 || d->vh == 0) return flush_clear(c);
+
+	DrawParams P;
+	if (fill_common_params(c, d, P)) return flush_clear(c);
+	P.ntri = ntri;
+	P.th_shift = th_shift_of(raster_path_for(c, ntri));
+	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
+	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
+	P.clip_vid_base = P.n_shade;
 
 	/* scratch */
 	const size_t n_prims = 2ull * ntri;
@@ -1244,7 +1329,6 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
 	}
 	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims;
-	P.tile_count = c->tile_count; P.ctr = c->ctr;
 
 	/* fused clear: the raster kernel starts the covered pixels from the clear value */
 	P.clear = c->pending_clear;
@@ -1254,6 +1338,45 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	c->stats.draws = c->n_draws;
 	c->stats.triangles_in = ntri;
 	return launch_draw(c, P);
+}
+
+int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
+{
+	cudaSetDevice(c->device);
+	if (settle_last_draw(c)) return -1;
+	c->last_draw_valid = 0;
+	if (flush_clear(c)) return -1;           /* points overwrite pixels: the clear must land first */
+	if (d->count == 0) return 0;
+
+	DrawParams P;
+	if (fill_common_params(c, d, P)) return 0;
+	P.n_shade = d->ibo ? d->n_vertices : d->count;
+	P.clip_vid_base = P.n_shade;
+	P.th_shift = SWGL_TILE_SHIFT; P.tiles_x = c->tiles_x; P.tiles_y = c->tiles_y;
+	if (grow(c, &c->clip, &c->cap_clip, (size_t)P.n_shade)) return -1;
+	if (grow(c, &c->clip_xy, &c->cap_clip_xy, (size_t)P.n_shade)) return -1;
+	if (grow(c, &c->vary, &c->cap_vary, (size_t)P.n_shade * (P.nvf ? P.nvf : 1) + 4)) return -1;
+	if (!c->winner)
+	{
+		const size_t bytes = (size_t)c->W * c->H * 4;
+		CK(cudaMalloc((void**)&c->winner, bytes ? bytes : 4));
+		CK(cudaMemsetAsync(c->winner, 0, bytes, c->stream));
+	}
+	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.winner = c->winner;
+
+	const uint32_t vb = (P.n_shade + 255u) / 256u, pb = (P.count + 255u) / 256u;
+	if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	k_points_claim<<<pb, 256, 0, c->stream>>>(P);
+	if (P.fs_kind == SWFS_VARYING) k_points_write<SWFS_VARYING><<<pb, 256, 0, c->stream>>>(P);
+	else if (P.fs_kind == SWFS_TEXTURE) k_points_write<SWFS_TEXTURE><<<pb, 256, 0, c->stream>>>(P);
+	else k_points_write<SWFS_GENERIC><<<pb, 256, 0, c->stream>>>(P);
+	c->n_launches += 3;
+	c->n_draws++;
+	c->stats.draws = c->n_draws;
+	CK(cudaGetLastError());
+	return 0;
 }
 
 uint32_t* swgldev_map_color(swgldev_ctx* c)

@@ -96,6 +96,7 @@ struct DrawParams
 	Prim* prims; BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
 	Counters* ctr;
+	uint32_t* winner;           /* GL_POINTS: per-pixel index+1 of the last point submitted to it (0 = none) */
 	/* shaders */
 	int32_t vs_kind, fs_kind;
 	const swgl_ir_op* vs_ops; uint32_t vs_nops; uint32_t vs_words;

@@ -482,9 +482,15 @@ void glTexImage2D(GLenum target, GLint level, GLint internalformat, GLsizei widt
 void glGenerateMipmap(GLenum target)
 {
 	if (target != GL_TEXTURE_2D || !G.active_texture || !G.active_texture->data) return;
-	/* Mip-mapped sampling depends on undefined behaviour in the reference (rsqrt through an
-	 * 8-byte pun, swgl.c:3238-3254) and is a "next" row: not generated. */
-	set_error("glGenerateMipmap: mip-mapped sampling is not implemented (reference LOD is undefined behaviour); texture stays non-mipmapped");
+	/* The reference builds a 2x2-box chain here (swgl.c:2129-2171) that is only ever read when
+	 * MipMapLevel > 0 (swgl.c:2527).  MipMapLevel is 40 / DistBetweenPointAndLine(...) and that
+	 * distance is multiplied by rsqrt(), whose 8-byte pun of a 4-byte float (swgl.c:3246) folds
+	 * the low bit of the adjacent stack word -- rsqrt's own return address -- into the sign:
+	 * in the compiled reference (gcc -O2, oracle/_ref) that bit is 1, rsqrt is negative for every
+	 * input, MipMapLevel is never positive and the base level is always sampled.  Bug-compatible
+	 * behaviour is therefore: accept the call, keep sampling level 0
+	 * (tests/test_next_rows_gpu.py compares against the compiled reference). */
+	G.active_texture->n_mipmaps = 1;
 }
 
 /* ---------------------------------------------------------------------------------------- */
@@ -602,9 +608,9 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 	if (!G.active_vao) return;     /* swgl.c:3477-3478 */
 	if (!G.active_program) return;
 	if (!G.dev) return;
-	if (mode != GL_TRIANGLES)
+	if (mode != GL_TRIANGLES && mode != GL_POINTS)
 	{
-		set_error("glDraw*: only GL_TRIANGLES is on the accelerated path (GL_POINTS is out of scope, GL_LINES is unimplemented in the reference)");
+		/* GL_LINES has an enumerator but no implementation in the reference either (swgl.h:65) */
 		return;
 	}
 	gl_program* p = G.active_program;
@@ -734,7 +740,8 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 		d.tex[u].wrap_s_repeat = t->wrap_s == GL_REPEAT; d.tex[u].wrap_t_repeat = t->wrap_t == GL_REPEAT;
 	}
 
-	swgldev_draw_triangles(G.dev, &d);
+	if (mode == GL_POINTS) swgldev_draw_points(G.dev, &d);
+	else swgldev_draw_triangles(G.dev, &d);
 }
 
 void glDrawArrays(GLenum mode, GLint first, GLsizei count)
