@@ -71,7 +71,7 @@ int      swglIpcExportColor(void* handle64);
 uint64_t swglIpcOpen(const void* handle64);
 void     swglIpcClose(uint64_t device_ptr);
 
-/* Tuning / test hooks: "raster_path" (0 auto, 1 pixel-owner, 2 fragment-parallel),
+/* Tuning / test hooks: "raster_path" (0 per-draw choice, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
  * "fuse_clear" (0/1), "count_fragments" (0/1), "stage_timing" (0/1: per-kernel CUDA-event timing, synchronous);
  * "bin_cap" (per-tile list capacity, test hook), "bin_limit_bytes";
  * read-only: "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
