@@ -72,9 +72,11 @@ uint64_t swglIpcOpen(const void* handle64);
 void     swglIpcClose(uint64_t device_ptr);
 
 /* Tuning / test hooks: "raster_path" (0 per-draw choice, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
+ * "host_mirror" (1 adaptive: when glGetFramePtr follows every draw or two, the raster kernels also store finished
+ * tiles into the pinned frame mirror and glGetFramePtr only waits; 0 always copy; 2 whenever the mirror is in sync),
  * "fuse_clear" (0/1), "count_fragments" (0/1), "stage_timing" (0/1: per-kernel CUDA-event timing, synchronous);
  * "bin_cap" (per-tile list capacity, test hook), "bin_limit_bytes";
- * read-only: "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
+ * read-only: "wt_draws", "mirror_synced", "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
  * "stage_draws", "tile_size", "device". */
 void swglSetOption(const char* name, int64_t value);
 int64_t swglGetOption(const char* name);

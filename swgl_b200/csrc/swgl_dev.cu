@@ -41,6 +41,13 @@ struct swgldev_ctx
 	uint32_t W, H, tiles_x, tiles_y;
 	uint32_t* color; float* depth;
 	uint32_t* h_color; float* h_depth;   /* pinned host mirrors (glGetFramePtr) */
+	/* Write-through host mirror: when the application reads every frame back, the raster kernels
+	 * store finished tiles into h_color as well (posted PCIe writes under the kernel) and
+	 * glGetFramePtr only has to wait.  mirror_synced: h_color equals the device colour once the
+	 * stream has drained. */
+	int mirror_synced, wt_predict, color_exposed;
+	uint64_t wt_draws;
+	uint32_t draws_since_map;
 	uint32_t* peer_color;
 	uint32_t rank, n_ranks, band_rows;
 
@@ -69,7 +76,7 @@ struct swgldev_ctx
 	int last_raster_path;
 
 	/* options */
-	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag;
+	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror;
 	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
 	cudaEvent_t stage_ev[8];
@@ -932,6 +939,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
 	c->n_launches = 0; c->stage_draws = 0;
+	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
@@ -1133,6 +1141,7 @@ static int flush_clear(swgldev_ctx* c)
 	if (cp.x1 <= cp.x0 || cp.y1 <= cp.y0) return 0;
 	dim3 block(128), grid(((uint32_t)(cp.x1 - cp.x0) + 511u) / 512u, (uint32_t)(cp.y1 - cp.y0));
 	k_clear<<<grid, block, 0, c->stream>>>(c->color, c->depth, c->W, cp);
+	c->mirror_synced = 0;
 	c->n_launches++;
 	CK(cudaGetLastError());
 	return 0;
@@ -1175,6 +1184,7 @@ void swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth)
 	c->pending_clear.flags = 0;
 	size_t n = (size_t)c->W * c->H;
 	k_fill_fb<<<1184, 256, 0, c->stream>>>(c->color, c->depth, n, color_word, depth);
+	c->mirror_synced = 0;
 }
 
 static const swgl_ir_op* upload_code(swgldev_ctx* c, uint64_t id, const swgl_ir_code* code)
@@ -1334,6 +1344,17 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.clear = c->pending_clear;
 	c->pending_clear.flags = 0;
 
+	/* write-through host mirror (single GPU, no peer target): see swgldev_ctx */
+	c->draws_since_map++;
+	if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && c->mirror_synced && !c->color_exposed
+	    && (c->opt_host_mirror == 2 || (c->wt_predict && c->draws_since_map <= 2)))
+	{
+		P.peer_color = c->h_color;
+		c->wt_draws++;
+	}
+	else
+		c->mirror_synced = 0;
+
 	c->n_draws++;
 	c->stats.draws = c->n_draws;
 	c->stats.triangles_in = ntri;
@@ -1374,6 +1395,8 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 	else k_points_write<SWFS_GENERIC><<<pb, 256, 0, c->stream>>>(P);
 	c->n_launches += 3;
 	c->n_draws++;
+	c->draws_since_map++;
+	c->mirror_synced = 0;
 	c->stats.draws = c->n_draws;
 	CK(cudaGetLastError());
 	return 0;
@@ -1381,9 +1404,16 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 
 uint32_t* swgldev_map_color(swgldev_ctx* c)
 {
-	if (swgldev_sync(c)) return c->h_color;
-	cudaMemcpyAsync(c->h_color, c->color, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream);
-	cudaStreamSynchronize(c->stream);
+	if (swgldev_sync(c)) { c->mirror_synced = 0; return c->h_color; }
+	if (!c->mirror_synced)
+	{
+		cudaMemcpyAsync(c->h_color, c->color, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream);
+		cudaStreamSynchronize(c->stream);
+	}
+	/* an application that reads back after every draw or two gets the write-through mirror next time */
+	c->wt_predict = c->draws_since_map <= 2;
+	c->draws_since_map = 0;
+	c->mirror_synced = (c->n_ranks == 1 && !c->peer_color && !c->color_exposed) ? 1 : 0;
 	return c->h_color;
 }
 
@@ -1395,7 +1425,12 @@ float* swgldev_map_depth(swgldev_ctx* c)
 	return c->h_depth;
 }
 
-swgldev_ptr swgldev_color_devptr(swgldev_ctx* c) { return (swgldev_ptr)(uintptr_t)c->color; }
+swgldev_ptr swgldev_color_devptr(swgldev_ctx* c)
+{
+	/* the caller may now write the attachment behind the library's back: no write-through mirror */
+	c->color_exposed = 1; c->mirror_synced = 0;
+	return (swgldev_ptr)(uintptr_t)c->color;
+}
 swgldev_ptr swgldev_depth_devptr(swgldev_ctx* c) { return (swgldev_ptr)(uintptr_t)c->depth; }
 
 void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out)
@@ -1456,6 +1491,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "count_fragments")) c->opt_count_fragments = (int)value;
 	else if (!strcmp(name, "raster_path")) c->opt_raster_path = (int)value;
 	else if (!strcmp(name, "diag")) c->opt_diag = (int)value;
+	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
 	{
@@ -1475,6 +1511,9 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "fuse_clear")) return c->opt_fuse_clear;
 	if (!strcmp(name, "count_fragments")) return c->opt_count_fragments;
 	if (!strcmp(name, "raster_path")) return c->opt_raster_path;
+	if (!strcmp(name, "host_mirror")) return c->opt_host_mirror;
+	if (!strcmp(name, "mirror_synced")) return c->mirror_synced;
+	if (!strcmp(name, "wt_draws")) return (int64_t)c->wt_draws;
 	if (!strcmp(name, "last_raster_path")) return c->last_raster_path;
 	if (!strcmp(name, "tile_size")) return SWGL_TILE;
 	if (!strcmp(name, "kernel_launches")) return (int64_t)c->n_launches;

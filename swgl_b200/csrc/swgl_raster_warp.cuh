@@ -369,29 +369,32 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 		}
 	}
 
-	/* ---- write-back: 128-bit stores of the finished tile ---- */
+	/* ---- write-back: each store instruction covers four whole 128-byte row segments (the mirror
+	 * target may be a peer GPU or pinned host memory, where partial lines cost full transactions) ---- */
 	if (__any_sync(0xffffffffu, dirty))
 	{
-		const int r = (int)(lane >> 2), row = tile_r0 + r, px0 = tile_x0 + (int)((lane & 3u) << 3);
-		if (row < (int)P.H)
+		const int px0 = tile_x0 + (int)((lane & 7u) << 2);
+#pragma unroll
+		for (int i = 0; i < WT_H / 4; i++)
 		{
+			const int r = (int)(lane >> 3) + 4 * i, row = tile_r0 + r;
+			if (row >= (int)P.H) continue;
 			const size_t pixg = (size_t)row * P.W + (size_t)px0;
-			const uint32_t s = (uint32_t)r * SWGL_TILE + ((lane & 3u) << 3);
-			uint4 c0 = *(const uint4*)&T.color[s], c1 = *(const uint4*)&T.color[s + 4];
-			float4 d0 = *(const float4*)&T.depth[s], d1 = *(const float4*)&T.depth[s + 4];
-			d0.x = canon_nan(d0.x); d0.y = canon_nan(d0.y); d0.z = canon_nan(d0.z); d0.w = canon_nan(d0.w);
-			d1.x = canon_nan(d1.x); d1.y = canon_nan(d1.y); d1.z = canon_nan(d1.z); d1.w = canon_nan(d1.w);
-			if (px0 + 7 < (int)P.W && ((pixg & 3u) == 0))
+			const uint32_t s = (uint32_t)r * SWGL_TILE + ((lane & 7u) << 2);
+			const uint4 c4 = *(const uint4*)&T.color[s];
+			float4 d4 = *(const float4*)&T.depth[s];
+			d4.x = canon_nan(d4.x); d4.y = canon_nan(d4.y); d4.z = canon_nan(d4.z); d4.w = canon_nan(d4.w);
+			if (px0 + 3 < (int)P.W && ((pixg & 3u) == 0))
 			{
-				*(uint4*)(P.color + pixg) = c0; *(uint4*)(P.color + pixg + 4) = c1;
-				*(float4*)(P.depth + pixg) = d0; *(float4*)(P.depth + pixg + 4) = d1;
-				if (P.peer_color) { *(uint4*)(P.peer_color + pixg) = c0; *(uint4*)(P.peer_color + pixg + 4) = c1; }
+				*(uint4*)(P.color + pixg) = c4;
+				*(float4*)(P.depth + pixg) = d4;
+				if (P.peer_color) *(uint4*)(P.peer_color + pixg) = c4;
 			}
 			else
 			{
-				const uint32_t cc[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
-				const float dd[8] = { d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w };
-				for (int k = 0; k < 8; k++)
+				const uint32_t cc[4] = { c4.x, c4.y, c4.z, c4.w };
+				const float dd[4] = { d4.x, d4.y, d4.z, d4.w };
+				for (int k = 0; k < 4; k++)
 					if (px0 + k < (int)P.W)
 					{
 						P.color[pixg + k] = cc[k]; P.depth[pixg + k] = dd[k];

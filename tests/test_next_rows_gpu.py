@@ -94,3 +94,48 @@ def test_generate_mipmap_keeps_sampling_the_base_level(gpu_api, reference):
         _assert_same(a, b, 1000)
         outs[mip] = a
     assert np.array_equal(outs[False][0], outs[True][0])
+
+
+def test_write_through_host_mirror_matches_copy_mode(gpu_api, reference):
+    """n4: an application that reads every frame back gets the frame stored into the pinned mirror by
+    the raster kernels themselves; what glGetFramePtr returns must not depend on the mode."""
+    scene = S.random_triangles(400, W, H, seed=77, alpha=None, extent=0.4)
+    pts = _points(5, 600)
+
+    def frames(api, is_gpu):
+        out = []
+        p, _, _ = _program(api, S.VS_PASSTHROUGH, S.FS_COLOR)
+        api.glUseProgram(p)
+        _vao(api, np.concatenate([scene.vertices, pts]), [(0, 4, 0), (1, 4, 16)])
+        n = len(scene.vertices)
+        for f in range(6):
+            if f != 3:
+                api.glClear(3)                     # frame 3 draws over frame 2 without a clear
+            api.glDrawArrays(G.GL_TRIANGLES, (f * 30) % 300, n - 300)
+            if f == 4:
+                api.glDrawArrays(G.GL_POINTS, n, len(pts))     # a kernel that does not write through
+            if f == 5:
+                api.glDrawArrays(G.GL_TRIANGLES, 0, 90)        # second draw of the frame
+            out.append(G.frame_color(api, W, H).copy())
+        return out
+
+    got = {}
+    for mode in (1, 0):
+        gpu_api.glInit(W, H)
+        gpu_api.swglSetOption(b"host_mirror", mode)
+        gpu_api.glViewport(0, 0, W, H)
+        gpu_api.glClearColor(0.0, 0.0, 0.0, 1.0)
+        w0 = gpu_api.swglGetOption(b"wt_draws")
+        got[mode] = frames(gpu_api, True)
+        used = gpu_api.swglGetOption(b"wt_draws") - w0
+        assert (used > 0) == (mode == 1), used
+        assert gpu_api.swglGetLastError().decode() == ""
+    gpu_api.swglSetOption(b"host_mirror", 1)
+    api = reference.api
+    api.glInit(W, H)
+    api.glViewport(0, 0, W, H)
+    api.glClearColor(0.0, 0.0, 0.0, 1.0)
+    want = frames(api, False)
+    for f in range(6):
+        assert np.array_equal(got[1][f], got[0][f]), f
+        assert np.array_equal(got[1][f], want[f]), f
