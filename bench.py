@@ -255,6 +255,40 @@ def run_own(args):
            "h2d_bytes_per_step": int(verts.numel() * 4 + idx.numel() * 4) * world,
            "d2h_bytes_per_step": scene.width * scene.height * 4}
 
+    # ---- the same step pipelined: two geometry sets and two frame mirrors; step N's
+    # upload overlaps frame N-1 on the device, its frame is collected during step N+1 ----
+    e2e_pipe = None
+    if world == 1:
+        sets = [G.add_geometry(api, scene, indexed=True, named=True)[:3] for _ in range(2)]
+
+        def pipe_step(i, prev):
+            vao, vbo, ebo = sets[i & 1]
+            api.glBindVertexArray(vao)
+            api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo)
+            api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, ebo)
+            api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.numel() * 4, C.c_void_p(verts.data_ptr()))
+            api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.numel() * 4, C.c_void_p(idx.data_ptr()))
+            frame()
+            t = api.swglFrameSubmit()
+            if prev:
+                api.swglFrameWait(prev)
+            return t
+
+        prev = 0
+        for i in range(3):
+            prev = pipe_step(i, prev)
+        api.swglFrameWait(prev)
+        barrier()
+        t0 = time.perf_counter()
+        prev = 0
+        for i in range(args.steps):
+            prev = pipe_step(i, prev)
+        api.swglFrameWait(prev)
+        pipe_s = (time.perf_counter() - t0) / args.steps
+        barrier()
+        e2e_pipe = {"value": n_tris / pipe_s, "unit": METRIC, "ms_per_step": pipe_s * 1e3,
+                    "note": "swglFrameSubmit/swglFrameWait, two geometry sets: same bytes per step as e2e, each frame is read one step later"}
+
     clocks = sampler.stop() if rank == 0 else {}   # sampled across the value, roofline and e2e legs
 
     # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
@@ -295,6 +329,8 @@ def run_own(args):
             "frame_ms": ms_per_step, "shaded_fragments": shaded, "tested_fragments": tested,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
         }
+        if e2e_pipe is not None:
+            line["e2e_pipelined"] = e2e_pipe
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if mg_check is not None:

@@ -71,6 +71,18 @@ int      swglIpcExportColor(void* handle64);
 uint64_t swglIpcOpen(const void* handle64);
 void     swglIpcClose(uint64_t device_ptr);
 
+/* The step after the path (glGetFramePtr consumers, swgl.c:3738): frame pipelining.  swglFrameSubmit stamps
+ * the frame drawn so far and returns a ticket (> 0) at once; swglFrameWait blocks until that frame lies in
+ * one of two pinned mirrors and returns it (row 0 = top, the reference's R<<24|G<<16|B<<8|A words).  The
+ * pointer stays valid until the next-but-one swglFrameSubmit.  With swglBufferRespecify on a second set of
+ * buffers, frame N+1's upload crosses PCIe while frame N is rasterised and written to its mirror. */
+uint64_t swglFrameSubmit(void);
+const uint32_t* swglFrameWait(uint64_t ticket);
+/* The colour attachment as bytes R, G, B, A (swizzled on the device) into W*H*4 bytes of host memory. */
+int swglReadPixelsRGBA8(void* dst);
+/* The current frame as a binary PPM (P6); 0 on success. */
+int swglWritePPM(const char* path);
+
 /* Tuning / test hooks: "raster_path" (0 per-draw choice, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
  * "host_mirror" (1 adaptive: when glGetFramePtr follows every draw or two, the raster kernels also store finished
  * tiles into the pinned frame mirror and glGetFramePtr only waits; 0 always copy; 2 whenever the mirror is in sync),

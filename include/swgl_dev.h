@@ -113,6 +113,9 @@ int          swgldev_sync(swgldev_ctx* c);
 /* memory: glBufferData / glTexImage2D copies (swgl.c:3142-3144, 2107-2118) ---------------- */
 swgldev_ptr  swgldev_alloc(swgldev_ctx* c, uint64_t bytes);
 int          swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes);
+/* same contract, but the copy waits only for the draws that read `dst` (an allocation base): the
+ * next frame's buffers cross PCIe while the current frame is still being rasterised */
+int          swgldev_upload_overlapped(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes);
 void         swgldev_free(swgldev_ctx* c, swgldev_ptr p);
 /* largest u32 in an uploaded element buffer (device reduction; the extension glDrawElements
  * shades vertices [0, max] once each) */
@@ -132,6 +135,13 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d);
 /* glGetFramePtr (swgl.c:3738): refreshes and returns the pinned host mirror. */
 uint32_t* swgldev_map_color(swgldev_ctx* c);
 float*    swgldev_map_depth(swgldev_ctx* c);
+/* the step after the path: frame pipelining over two pinned mirrors.  submit stamps the
+ * frame rendered so far (ticket > 0) and returns at once; wait blocks until that frame is in its mirror
+ * and returns it (valid until the next-but-one submit). */
+uint64_t        swgldev_frame_submit(swgldev_ctx* c);
+const uint32_t* swgldev_frame_wait(swgldev_ctx* c, uint64_t ticket);
+/* colour attachment as bytes R, G, B, A (swizzled on the device) into `dst` (W*H*4 bytes of host memory) */
+int       swgldev_read_rgba8(swgldev_ctx* c, void* dst);
 swgldev_ptr swgldev_color_devptr(swgldev_ctx* c);
 swgldev_ptr swgldev_depth_devptr(swgldev_ctx* c);
 void      swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth); /* whole framebuffer */

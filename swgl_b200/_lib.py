@@ -45,6 +45,10 @@ EXTENSION_EXPORTS = {
     "swglGetOption": (C.c_int64, [C.c_char_p]),
     "swglDebugShaderIR": (C.c_size_t, [C.c_uint32, C.c_char_p, C.c_size_t]),
     "swglGetShaderCompiled": (C.c_int, [C.c_uint32]),
+    "swglFrameSubmit": (C.c_uint64, []),
+    "swglFrameWait": (C.POINTER(C.c_uint32), [C.c_uint64]),
+    "swglReadPixelsRGBA8": (C.c_int, [C.c_void_p]),
+    "swglWritePPM": (C.c_int, [C.c_char_p]),
 }
 
 _api = None

@@ -47,6 +47,22 @@ struct swgldev_ctx
 	 * stream has drained. */
 	int mirror_synced, wt_predict, color_exposed;
 	uint64_t wt_draws;
+	/* frame pipelining: two mirrors, h_color is the active one; swgldev_frame_submit
+	 * stamps the frame and flips, swgldev_frame_wait hands the finished mirror out */
+	uint32_t* h_mirror[2];
+	cudaEvent_t frame_ev[2];
+	cudaStream_t copy;                   /* frame copies of swgldev_frame_submit (DMA, overlaps the next upload) */
+	cudaEvent_t frame_done;
+	int copy_inflight;                   /* the copy stream may still read the colour attachment (slot + 1) */
+	uint64_t frame_serial;
+	uint32_t* rgba_staging;
+	/* uploads run on their own stream and wait only for the draws that read the destination, so the
+	 * next frame's buffers can cross PCIe while this frame is rasterised (every draw gets a serial and
+	 * an event in a small ring) */
+	cudaStream_t upload;
+	cudaEvent_t draw_ev[8];
+	uint64_t draw_serial;
+	uint32_t* d_maxidx;
 	uint32_t draws_since_map;
 	uint32_t* peer_color;
 	uint32_t rank, n_ranks, band_rows;
@@ -69,6 +85,7 @@ struct swgldev_ctx
 
 	std::map<uint64_t, swgl_ir_op*> code_cache;
 	std::vector<void*> allocations;
+	std::map<uintptr_t, uint64_t> last_use;   /* allocation base -> serial of the last draw reading it */
 
 	ClearParams pending_clear;
 	DrawParams last_draw;                /* for re-issue after a scratch overflow */
@@ -143,6 +160,13 @@ __global__ void k_fill_fb(uint32_t* __restrict__ color, float* __restrict__ dept
 }
 
 /* ---- largest index of an element buffer (decides how many vertices an indexed draw shades) ---- */
+/* R<<24|G<<16|B<<8|A words (swgl.c:3455-3460) -> bytes R, G, B, A in memory */
+__global__ void __launch_bounds__(256) k_pack_rgba8(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		out[i] = __byte_perm(in[i], 0u, 0x0123);
+}
+
 __global__ void __launch_bounds__(256) k_max_index(const uint32_t* __restrict__ idx, size_t n, uint32_t* out)
 {
 	uint32_t m = 0;
@@ -896,6 +920,26 @@ __global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ Dr
  * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = choose per draw: meshes of
  * small triangles (few framebuffer pixels per submitted triangle) go to the warp kernel, everything
  * else to the fragment-parallel CTA kernel.  All three produce identical bits. */
+/* every draw gets a serial and an event; the allocations it reads remember the serial */
+static int stamp_draw(swgldev_ctx* c, const swgldev_draw* d)
+{
+	c->draw_serial++;
+	CK(cudaEventRecord(c->draw_ev[c->draw_serial & 7u], c->stream));
+	const swgldev_ptr used[2] = { d->vbo, d->ibo };
+	for (int i = 0; i < 2; i++)
+	{
+		auto it = c->last_use.find((uintptr_t)used[i]);
+		if (it != c->last_use.end()) it->second = c->draw_serial;
+	}
+	for (int u = 0; u < SWGL_MAX_TEX_UNITS; u++)
+		if (d->tex[u].data)
+		{
+			auto it = c->last_use.find((uintptr_t)d->tex[u].data);
+			if (it != c->last_use.end()) it->second = c->draw_serial;
+		}
+	return 0;
+}
+
 static int raster_path_for(const swgldev_ctx* c, uint32_t ntri)
 {
 	if (c->opt_raster_path >= 1 && c->opt_raster_path <= 3) return c->opt_raster_path;
@@ -940,6 +984,9 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
 	c->n_launches = 0; c->stage_draws = 0;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
+	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
+	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr;
+	for (int i = 0; i < 8; i++) c->draw_ev[i] = nullptr;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
@@ -947,10 +994,19 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 
 	const size_t npx = (size_t)width * height;
 	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
+	/* the upload stream's small reduction kernel must not queue behind a whole raster grid */
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
 	bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaMalloc((void**)&c->color, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->depth, (npx ? npx : 1) * 4) == cudaSuccess
-	       && cudaMallocHost((void**)&c->h_color, (npx ? npx : 1) * 4) == cudaSuccess
+	       && cudaMallocHost((void**)&c->h_mirror[0], (npx ? npx : 1) * 4) == cudaSuccess
+	       && cudaStreamCreateWithPriority(&c->upload, cudaStreamNonBlocking, prio_hi) == cudaSuccess
+	       && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming) == cudaSuccess
+	       && cudaMalloc((void**)&c->d_maxidx, 4) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->frame_ev[0], cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->frame_ev[1], cudaEventDisableTiming) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_depth, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->tile_count, (ntiles + 1) * 4) == cudaSuccess
 	       && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess
@@ -970,6 +1026,9 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 		return nullptr;
 	}
 	memset(c->h_ctr, 0, sizeof(Counters));
+	c->h_color = c->h_mirror[0];
+	for (int i = 0; i < 8; i++)
+		if (cudaEventCreateWithFlags(&c->draw_ev[i], cudaEventDisableTiming) != cudaSuccess) { swgldev_destroy(c); return nullptr; }
 
 	/* the raster kernels need more than the default 48 KB of dynamic shared memory */
 	const int smem = (int)sizeof(RasterShared);
@@ -990,7 +1049,15 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	for (void* p : c->allocations) cudaFree(p);
 	for (auto& kv : c->code_cache) cudaFree(kv.second);
-	cudaFree(c->color); cudaFree(c->depth); cudaFreeHost(c->h_color); cudaFreeHost(c->h_depth);
+	if (c->upload) { cudaStreamSynchronize(c->upload); cudaStreamDestroy(c->upload); }
+	if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+	if (c->frame_done) cudaEventDestroy(c->frame_done);
+	cudaFree(c->color); cudaFree(c->depth); cudaFreeHost(c->h_mirror[0]); cudaFreeHost(c->h_depth);
+	if (c->h_mirror[1]) cudaFreeHost(c->h_mirror[1]);
+	if (c->rgba_staging) cudaFree(c->rgba_staging);
+	if (c->d_maxidx) cudaFree(c->d_maxidx);
+	for (int i = 0; i < 2; i++) if (c->frame_ev[i]) cudaEventDestroy(c->frame_ev[i]);
+	for (int i = 0; i < 8; i++) if (c->draw_ev[i]) cudaEventDestroy(c->draw_ev[i]);
 	cudaFree(c->tile_count); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
 	if (c->winner) cudaFree(c->winner);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
@@ -1025,6 +1092,7 @@ swgldev_ptr swgldev_alloc(swgldev_ctx* c, uint64_t bytes)
 	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
 	if (e != cudaSuccess) { set_err(c, "cudaMalloc (buffer/texture upload)", e); return 0; }
 	c->allocations.push_back(p);
+	c->last_use[(uintptr_t)p] = 0;
 	return (swgldev_ptr)(uintptr_t)p;
 }
 
@@ -1036,11 +1104,14 @@ void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 		{
 			c->allocations[i] = c->allocations.back();
 			c->allocations.pop_back();
+			c->last_use.erase((uintptr_t)q);
 			cudaStreamSynchronize(c->stream); /* queued draws may still read it */
 			cudaFree(q);
 			return;
 		}
 }
+
+static int settle_last_draw(swgldev_ctx* c);
 
 int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes)
 {
@@ -1051,18 +1122,37 @@ int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t by
 	return 0;
 }
 
+/* Same contract as swgldev_upload, but the copy only waits for the draws that read the destination
+ * allocation: it overlaps whatever else is queued (the frame being rasterised, for instance). */
+int swgldev_upload_overlapped(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes)
+{
+	cudaSetDevice(c->device);
+	/* an overflowed draw is re-issued from its buffers: resolve it before they may change */
+	if (settle_last_draw(c)) return -1;
+	auto it = c->last_use.find((uintptr_t)dst);
+	if (it == c->last_use.end()) return swgldev_upload(c, dst, src, bytes);   /* not an allocation base: plain ordering */
+	const uint64_t last_use = it->second;
+	if (last_use)
+	{
+		const uint64_t s = (c->draw_serial - last_use < 8u) ? last_use : c->draw_serial;   /* older than the ring: newest */
+		CK(cudaStreamWaitEvent(c->upload, c->draw_ev[s & 7u], 0));
+	}
+	CK(cudaMemcpyAsync((void*)(uintptr_t)dst, src, bytes, cudaMemcpyHostToDevice, c->upload));
+	CK(cudaStreamSynchronize(c->upload));
+	return 0;
+}
+
 uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 {
 	cudaSetDevice(c->device);
 	const size_t n = bytes / 4u;
 	if (!n) return 0;
-	uint32_t* d_out = &c->ctr->max_list;    /* scratch word; no draw is in flight when buffers are specified */
-	if (swgldev_sync(c)) return 0;
-	cudaMemsetAsync(d_out, 0, 4, c->stream);
-	k_max_index<<<148 * 4, 256, 0, c->stream>>>((const uint32_t*)(uintptr_t)indices, n, d_out);
+	/* on the upload stream: the buffer was just written there and nothing later has been queued */
+	cudaMemsetAsync(c->d_maxidx, 0, 4, c->upload);
+	k_max_index<<<148 * 4, 256, 0, c->upload>>>((const uint32_t*)(uintptr_t)indices, n, c->d_maxidx);
 	uint32_t h = 0;
-	cudaMemcpyAsync(&h, d_out, 4, cudaMemcpyDeviceToHost, c->stream);
-	cudaStreamSynchronize(c->stream);
+	cudaMemcpyAsync(&h, c->d_maxidx, 4, cudaMemcpyDeviceToHost, c->upload);
+	cudaStreamSynchronize(c->upload);
 	return h;
 }
 
@@ -1133,6 +1223,16 @@ static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 	return issue_sync(c, P, depth);
 }
 
+/* a frame copy of swgldev_frame_submit may still be reading the colour attachment: kernels that
+ * write it queue behind that copy (everything before them -- uploads, vertex stage, set-up -- does not) */
+static int guard_color_write(swgldev_ctx* c)
+{
+	if (!c->copy_inflight) return 0;
+	CK(cudaStreamWaitEvent(c->stream, c->frame_ev[c->copy_inflight - 1], 0));
+	c->copy_inflight = 0;
+	return 0;
+}
+
 static int flush_clear(swgldev_ctx* c)
 {
 	ClearParams cp = c->pending_clear;
@@ -1140,6 +1240,7 @@ static int flush_clear(swgldev_ctx* c)
 	c->pending_clear.flags = 0;
 	if (cp.x1 <= cp.x0 || cp.y1 <= cp.y0) return 0;
 	dim3 block(128), grid(((uint32_t)(cp.x1 - cp.x0) + 511u) / 512u, (uint32_t)(cp.y1 - cp.y0));
+	if (guard_color_write(c)) return -1;
 	k_clear<<<grid, block, 0, c->stream>>>(c->color, c->depth, c->W, cp);
 	c->mirror_synced = 0;
 	c->n_launches++;
@@ -1153,6 +1254,7 @@ int swgldev_sync(swgldev_ctx* c)
 	if (settle_last_draw(c)) return -1;
 	if (flush_clear(c)) return -1;
 	CK(cudaStreamSynchronize(c->stream));
+	if (c->copy_inflight) CK(cudaStreamSynchronize(c->copy));
 	return 0;
 }
 
@@ -1183,6 +1285,7 @@ void swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth)
 	settle_last_draw(c);
 	c->pending_clear.flags = 0;
 	size_t n = (size_t)c->W * c->H;
+	guard_color_write(c);
 	k_fill_fb<<<1184, 256, 0, c->stream>>>(c->color, c->depth, n, color_word, depth);
 	c->mirror_synced = 0;
 }
@@ -1224,6 +1327,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	CK(cudaMemcpyAsync(c->h_ctr, c->ctr, 16, cudaMemcpyDeviceToHost, c->side));
 	CK(cudaEventRecord(c->ctr_event, c->side));
 	c->ctr_pending = 1;
+	if (guard_color_write(c)) return -1;
 	if (P.fs_kind == SWFS_VARYING) launch_raster<SWFS_VARYING>(c, P);
 	else if (P.fs_kind == SWFS_TEXTURE) launch_raster<SWFS_TEXTURE>(c, P);
 	else launch_raster<SWFS_GENERIC>(c, P);
@@ -1346,9 +1450,13 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 
 	/* write-through host mirror (single GPU, no peer target): see swgldev_ctx */
 	c->draws_since_map++;
-	if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && c->mirror_synced && !c->color_exposed
+	/* a fused clear of the whole framebuffer makes every tile dirty: the mirror is complete afterwards */
+	const bool full_clear = (P.clear.flags & 1u) && P.clear.x0 <= 0 && P.clear.y0 <= 0
+	                        && P.clear.x1 >= (int32_t)c->W && P.clear.y1 >= (int32_t)c->H;
+	if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && !c->color_exposed && (c->mirror_synced || full_clear)
 	    && (c->opt_host_mirror == 2 || (c->wt_predict && c->draws_since_map <= 2)))
 	{
+		c->mirror_synced = 1;
 		P.peer_color = c->h_color;
 		c->wt_draws++;
 	}
@@ -1358,7 +1466,8 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	c->n_draws++;
 	c->stats.draws = c->n_draws;
 	c->stats.triangles_in = ntri;
-	return launch_draw(c, P);
+	if (launch_draw(c, P)) return -1;
+	return stamp_draw(c, d);
 }
 
 int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
@@ -1389,6 +1498,7 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 	if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	if (guard_color_write(c)) return -1;
 	k_points_claim<<<pb, 256, 0, c->stream>>>(P);
 	if (P.fs_kind == SWFS_VARYING) k_points_write<SWFS_VARYING><<<pb, 256, 0, c->stream>>>(P);
 	else if (P.fs_kind == SWFS_TEXTURE) k_points_write<SWFS_TEXTURE><<<pb, 256, 0, c->stream>>>(P);
@@ -1399,7 +1509,7 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 	c->mirror_synced = 0;
 	c->stats.draws = c->n_draws;
 	CK(cudaGetLastError());
-	return 0;
+	return stamp_draw(c, d);
 }
 
 uint32_t* swgldev_map_color(swgldev_ctx* c)
@@ -1415,6 +1525,68 @@ uint32_t* swgldev_map_color(swgldev_ctx* c)
 	c->draws_since_map = 0;
 	c->mirror_synced = (c->n_ranks == 1 && !c->peer_color && !c->color_exposed) ? 1 : 0;
 	return c->h_color;
+}
+
+/* ---- frame pipelining ---- */
+uint64_t swgldev_frame_submit(swgldev_ctx* c)
+{
+	cudaSetDevice(c->device);
+	if (settle_last_draw(c) || flush_clear(c)) return 0;
+	const size_t bytes = (size_t)c->W * c->H * 4;
+	if (!c->h_mirror[1])
+	{
+		if (cudaMallocHost((void**)&c->h_mirror[1], bytes ? bytes : 4) != cudaSuccess) { set_err(c, "cudaMallocHost (second frame mirror)", cudaGetLastError()); return 0; }
+	}
+	const uint32_t slot = (uint32_t)(c->frame_serial & 1u);
+	cudaError_t e = cudaSuccess;
+	if (c->mirror_synced)
+		e = cudaEventRecord(c->frame_ev[slot], c->stream);          /* already written through */
+	else
+	{
+		/* copy engine on its own stream: the next frame's uploads, vertex stage and set-up overlap it */
+		if (c->copy_inflight) e = cudaStreamWaitEvent(c->stream, c->frame_ev[c->copy_inflight - 1], 0);
+		if (e == cudaSuccess) e = cudaEventRecord(c->frame_done, c->stream);
+		if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy, c->frame_done, 0);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_mirror[slot], c->color, bytes, cudaMemcpyDeviceToHost, c->copy);
+		if (e == cudaSuccess) e = cudaEventRecord(c->frame_ev[slot], c->copy);
+		c->copy_inflight = (int)slot + 1;
+	}
+	if (e != cudaSuccess) { set_err(c, "swglFrameSubmit", e); return 0; }
+	c->frame_serial++;
+	/* the next frame goes to the other mirror.  No write-through while frames are pipelined: SM
+	 * stores to host memory starve the next frame's upload of PCIe read requests (measured). */
+	c->h_color = c->h_mirror[c->frame_serial & 1u];
+	c->mirror_synced = 0;
+	c->wt_predict = 0;
+	c->draws_since_map = 0;
+	return c->frame_serial;     /* ticket */
+}
+
+const uint32_t* swgldev_frame_wait(swgldev_ctx* c, uint64_t ticket)
+{
+	cudaSetDevice(c->device);
+	if (ticket == 0 || ticket > c->frame_serial || c->frame_serial - ticket >= 2u)
+	{
+		set_err(c, "swglFrameWait: ticket is not one of the last two submitted frames", cudaSuccess);
+		return nullptr;
+	}
+	const uint32_t slot = (uint32_t)((ticket - 1u) & 1u);
+	if (cudaEventSynchronize(c->frame_ev[slot]) != cudaSuccess) { set_err(c, "cudaEventSynchronize (frame)", cudaGetLastError()); return nullptr; }
+	return c->h_mirror[slot];
+}
+
+/* glGetFramePtr consumers that want bytes in R, G, B, A order: swizzled on the device, then copied */
+int swgldev_read_rgba8(swgldev_ctx* c, void* dst)
+{
+	if (swgldev_sync(c)) return -1;
+	const size_t n = (size_t)c->W * c->H;
+	if (!n) return 0;
+	if (!c->rgba_staging) CK(cudaMalloc((void**)&c->rgba_staging, n * 4));
+	k_pack_rgba8<<<1184, 256, 0, c->stream>>>(c->color, c->rgba_staging, n);
+	c->n_launches++;
+	CK(cudaMemcpyAsync(dst, c->rgba_staging, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
 }
 
 float* swgldev_map_depth(swgldev_ctx* c)

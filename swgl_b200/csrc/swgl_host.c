@@ -28,6 +28,7 @@ typedef struct
 	uint32_t size;          /* bytes; 0 = never specified (swgl.c:3140) */
 	uint32_t capacity;
 	uint32_t max_index;     /* element data only: largest u32 in the buffer */
+	void* origin;           /* a VAO's own struct: the named buffer it is a snapshot of */
 } gl_buffer;
 
 typedef struct
@@ -184,6 +185,35 @@ float* swglGetDepthPtr(void)
 }
 
 void swglFinish(void) { if (G.dev) swgldev_sync(G.dev); }
+
+/* the step after the path */
+uint64_t swglFrameSubmit(void) { return G.dev ? swgldev_frame_submit(G.dev) : 0; }
+const uint32_t* swglFrameWait(uint64_t ticket) { return G.dev ? swgldev_frame_wait(G.dev, ticket) : NULL; }
+int swglReadPixelsRGBA8(void* dst) { return (G.dev && dst) ? swgldev_read_rgba8(G.dev, dst) : -1; }
+
+int swglWritePPM(const char* path)
+{
+	const uint32_t* px = glGetFramePtr();
+	if (!px || !path) return -1;
+	FILE* f = fopen(path, "wb");
+	if (!f) { set_error("swglWritePPM: cannot open the file"); return -1; }
+	fprintf(f, "P6\n%u %u\n255\n", (unsigned)G.width, (unsigned)G.height);
+	uint8_t* row = (uint8_t*)malloc((size_t)G.width * 3u + 3u);
+	int rc = row ? 0 : -1;
+	for (uint32_t y = 0; row && y < (uint32_t)G.height; y++)
+	{
+		const uint32_t* src = px + (size_t)y * (size_t)G.width;
+		for (uint32_t x = 0; x < (uint32_t)G.width; x++)
+		{
+			row[3u * x] = (uint8_t)(src[x] >> 24); row[3u * x + 1u] = (uint8_t)(src[x] >> 16); row[3u * x + 2u] = (uint8_t)(src[x] >> 8);
+		}
+		if (fwrite(row, 3u, (size_t)G.width, f) != (size_t)G.width) { rc = -1; break; }
+	}
+	free(row);
+	if (fclose(f) != 0) rc = -1;
+	if (rc) set_error("swglWritePPM: write failed");
+	return rc;
+}
 
 const char* swglGetLastError(void)
 {
@@ -384,6 +414,7 @@ void glBindBuffer(GLenum type, GLuint buffer)
 		/* with a vertex array bound the VAO's own Buffer struct becomes the bound buffer and
 		 * takes a snapshot of the named buffer's fields (swgl.c:3116-3122) */
 		*vao_own = *target;
+		vao_own->origin = target;
 		*slot = vao_own;
 	}
 	else *slot = target;
@@ -423,8 +454,15 @@ void swglBufferRespecify(GLenum target, GLsizei size, const void* data)
 		b->capacity = size;
 	}
 	b->size = size;
-	swgldev_upload(G.dev, b->data, data, size);
+	swgldev_upload_overlapped(G.dev, b->data, data, size);
 	if (target == GL_ELEMENT_ARRAY_BUFFER) scan_indices(b, data, size);
+	if (b->origin && ((gl_buffer*)b->origin)->size != 0)
+	{
+		/* the named buffer owns this storage too (specified before it was bound into the vertex
+		 * array): keep it current, so that binding the name again does not resurrect stale fields */
+		gl_buffer* o = (gl_buffer*)b->origin;
+		o->data = b->data; o->size = b->size; o->capacity = b->capacity; o->max_index = b->max_index;
+	}
 }
 
 /* ---------------------------------------------------------------------------------------- */

@@ -124,6 +124,49 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(_vp)
 
 
+def add_geometry(gl: GLApi, scene, *, indexed: bool, named: bool = False):
+    """A vertex array with its own vertex (and element) buffer holding ``scene``'s geometry; it stays
+    bound.  Returns (vao, vbo, ebo or 0, number of vertices / indices to draw).
+
+    With a vertex array bound, glBindBuffer makes the array's OWN Buffer struct the bound buffer and
+    overwrites it with a snapshot of the named one (swgl.c:3116-3122), so data specified through it
+    never reaches the named buffer and binding the name again wipes it.  ``named=True`` specifies the
+    data with no vertex array bound (the named buffers own it); such a set can be re-bound by name
+    later, which is what a client that alternates between geometry sets has to do."""
+    verts = scene.vertices if indexed else scene.deindexed()
+    verts = np.ascontiguousarray(verts, np.float32)
+    idx = np.ascontiguousarray(scene.indices, np.uint32) if (indexed and scene.indices is not None) else None
+    vao, vbo, ebo = _u32(0), _u32(0), _u32(0)
+    if named:
+        gl.glBindVertexArray(0)
+        gl.glGenBuffers(1, C.byref(vbo))
+        gl.glBindBuffer(GL_ARRAY_BUFFER, vbo.value)
+        gl.glBufferData(GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), GL_STATIC_DRAW)
+        if idx is not None:
+            gl.glGenBuffers(1, C.byref(ebo))
+            gl.glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, ebo.value)
+            gl.glBufferData(GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), GL_STATIC_DRAW)
+    gl.glGenVertexArrays(1, C.byref(vao))
+    gl.glBindVertexArray(vao.value)
+    if not named:
+        gl.glGenBuffers(1, C.byref(vbo))
+    gl.glBindBuffer(GL_ARRAY_BUFFER, vbo.value)
+    if not named:
+        gl.glBufferData(GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), GL_STATIC_DRAW)
+    for loc, n, off in scene.attribs:
+        gl.glVertexAttribPointer(loc, n, GL_FLOAT, GL_FALSE, scene.stride, _vp(off))
+        gl.glEnableVertexAttribArray(loc)
+    n_draw = len(verts)
+    if idx is not None:
+        if not named:
+            gl.glGenBuffers(1, C.byref(ebo))
+        gl.glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, ebo.value)
+        if not named:
+            gl.glBufferData(GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), GL_STATIC_DRAW)
+        n_draw = len(idx)
+    return vao.value, vbo.value, ebo.value, n_draw
+
+
 def setup_scene(gl: GLApi, scene, *, indexed: bool, init: bool = True):
     """Issue every cold-path call for ``scene``; returns a dict with the program id etc.
 
@@ -144,26 +187,7 @@ def setup_scene(gl: GLApi, scene, *, indexed: bool, init: bool = True):
     gl.glLinkProgram(prog)
     gl.glUseProgram(prog)
 
-    vao = _u32(0)
-    gl.glGenVertexArrays(1, C.byref(vao))
-    gl.glBindVertexArray(vao.value)
-    vbo = _u32(0)
-    gl.glGenBuffers(1, C.byref(vbo))
-    gl.glBindBuffer(GL_ARRAY_BUFFER, vbo.value)
-    verts = scene.vertices if indexed else scene.deindexed()
-    verts = np.ascontiguousarray(verts, np.float32)
-    gl.glBufferData(GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), GL_STATIC_DRAW)
-    for loc, n, off in scene.attribs:
-        gl.glVertexAttribPointer(loc, n, GL_FLOAT, GL_FALSE, scene.stride, _vp(off))
-        gl.glEnableVertexAttribArray(loc)
-    n_draw = len(verts)
-    if indexed and scene.indices is not None:
-        ebo = _u32(0)
-        gl.glGenBuffers(1, C.byref(ebo))
-        gl.glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, ebo.value)
-        idx = np.ascontiguousarray(scene.indices, np.uint32)
-        gl.glBufferData(GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), GL_STATIC_DRAW)
-        n_draw = len(idx)
+    vao, vbo, ebo, n_draw = add_geometry(gl, scene, indexed=indexed)
 
     if scene.texture is not None:
         tex = _u32(0)
@@ -199,7 +223,8 @@ def setup_scene(gl: GLApi, scene, *, indexed: bool, init: bool = True):
     vp = scene.viewport or (0, 0, scene.width, scene.height)
     gl.glViewport(*vp)
     gl.glClearColor(*scene.clear_color)
-    return {"program": prog, "n_draw": n_draw, "indexed": indexed and scene.indices is not None}
+    return {"program": prog, "n_draw": n_draw, "indexed": indexed and scene.indices is not None,
+            "vao": vao, "vbo": vbo, "ebo": ebo}
 
 
 def frame_color(gl: GLApi, width: int, height: int) -> np.ndarray:

@@ -139,3 +139,143 @@ def test_write_through_host_mirror_matches_copy_mode(gpu_api, reference):
     for f in range(6):
         assert np.array_equal(got[1][f], got[0][f]), f
         assert np.array_equal(got[1][f], want[f]), f
+
+
+def _two_buffer_sets(api, n_bytes_v, attribs):
+    """Two VAOs with their own vertex buffers (the double-buffered geometry of a streaming client)."""
+    sets = []
+    for _ in range(2):
+        # data specified with no vertex array bound, so that the NAMED buffer owns it and the set can
+        # be bound again by name (with an array bound, glBindBuffer snapshots the name, swgl.c:3116-3122)
+        api.glBindVertexArray(0)
+        vbo = C.c_uint32(0)
+        api.glGenBuffers(1, C.byref(vbo))
+        api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+        zero = np.zeros(n_bytes_v // 4, np.float32)
+        api.glBufferData(G.GL_ARRAY_BUFFER, n_bytes_v, _ptr(zero), G.GL_STATIC_DRAW)
+        vao = C.c_uint32(0)
+        api.glGenVertexArrays(1, C.byref(vao))
+        api.glBindVertexArray(vao.value)
+        api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+        for loc, n, off in attribs:
+            api.glVertexAttribPointer(loc, n, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(off))
+            api.glEnableVertexAttribArray(loc)
+        sets.append((vao.value, vbo.value))
+    return sets
+
+
+@pytest.mark.parametrize("full_clear", [True, False])
+def test_frame_pipelining_submit_wait(gpu_api, reference, full_clear):
+    """n4: swglFrameSubmit / swglFrameWait over two mirrors, uploads overlapping the previous frame."""
+    frames_v = [np.ascontiguousarray(S.random_triangles(300, W, H, seed=900 + f, alpha=None, extent=0.5).vertices)
+                for f in range(7)]
+    nbytes = frames_v[0].nbytes
+    vp = (0, 0, W, H) if full_clear else (10, 6, 160, 120)
+
+    # reference: one frame at a time
+    api = reference.api
+    want = []
+    for f, v in enumerate(frames_v):
+        api.glInit(W, H)
+        reference.lib.swglref_fill(0, C.c_float(0.0))
+        p, _, _ = _program(api, S.VS_PASSTHROUGH, S.FS_COLOR)
+        api.glUseProgram(p)
+        _vao(api, v, [(0, 4, 0), (1, 4, 16)])
+        api.glClearColor(0.1, 0.2, 0.3, 1.0)
+        api.glViewport(*vp)
+        api.glClear(3)
+        api.glDrawArrays(G.GL_TRIANGLES, 0, len(v))
+        want.append(G.frame_color(api, W, H).copy())
+
+    api = gpu_api
+    api.glInit(W, H)
+    api.swglFillFramebuffer(0, C.c_float(0.0))
+    p, _, _ = _program(api, S.VS_PASSTHROUGH, S.FS_COLOR)
+    api.glUseProgram(p)
+    sets = _two_buffer_sets(api, nbytes, [(0, 4, 0), (1, 4, 16)])
+    api.glClearColor(0.1, 0.2, 0.3, 1.0)
+    api.glViewport(*vp)
+    w0 = api.swglGetOption(b"wt_draws")
+    got, prev = [], 0
+
+    def collect(ticket):
+        ptr = api.swglFrameWait(ticket)
+        assert ptr
+        got.append(np.ctypeslib.as_array(ptr, shape=(H, W)).copy())
+
+    for f, v in enumerate(frames_v):
+        vao, vbo = sets[f & 1]
+        api.glBindVertexArray(vao)
+        api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo)
+        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, nbytes, _ptr(v))
+        if not full_clear:
+            api.swglFillFramebuffer(0, C.c_float(0.0))     # what glInit leaves outside the viewport in the reference run
+        api.glClear(3)
+        api.glDrawArrays(G.GL_TRIANGLES, 0, len(v))
+        t = api.swglFrameSubmit()
+        assert t == f + 1
+        if prev:
+            collect(prev)
+        prev = t
+    collect(prev)
+    assert api.swglGetLastError().decode() == ""
+    assert api.swglGetOption(b"wt_draws") == w0      # pipelined frames travel by DMA, not write-through
+    for f in range(len(frames_v)):
+        assert np.array_equal(got[f], want[f]), f
+    # a ticket older than the two mirrors is refused
+    assert not api.swglFrameWait(1)
+    assert b"ticket" in api.swglGetLastError()
+
+
+def test_respecify_right_after_a_draw_keeps_the_queued_draw_intact(gpu_api, reference):
+    """The overlapped upload must wait for the draws that still read the buffer (single-buffered client)."""
+    a = np.ascontiguousarray(S.random_triangles(3000, W, H, seed=31, alpha=None, extent=0.6).vertices)
+    b = np.ascontiguousarray(S.random_triangles(3000, W, H, seed=32, alpha=None, extent=0.6).vertices)
+
+    def script(api, respec):
+        p, _, _ = _program(api, S.VS_PASSTHROUGH, S.FS_COLOR)
+        api.glUseProgram(p)
+        _vao(api, a, [(0, 4, 0), (1, 4, 16)])
+        api.glClear(3)
+        for _ in range(4):
+            api.glDrawArrays(G.GL_TRIANGLES, 0, len(a))
+        respec(api)
+        api.glDrawArrays(G.GL_TRIANGLES, 0, len(b))
+
+    def gpu_respec(api):
+        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, b.nbytes, _ptr(b))
+
+    def ref_respec(api):     # the reference ignores re-specification: a fresh buffer instead
+        _vao(api, b, [(0, 4, 0), (1, 4, 16)])
+
+    out = []
+    for api, is_ref in ((gpu_api, False), (reference.api, True)):
+        api.glInit(W, H)
+        (reference.lib.swglref_fill if is_ref else api.swglFillFramebuffer)(0, C.c_float(0.0))
+        api.glViewport(0, 0, W, H)
+        api.glClearColor(0.0, 0.0, 0.0, 1.0)
+        script(api, ref_respec if is_ref else gpu_respec)
+        out.append(G.frame_color(api, W, H).copy())
+    assert np.array_equal(out[0], out[1])
+
+
+def test_read_pixels_rgba8_and_ppm(gpu_api, reference, tmp_path):
+    scene = S.random_triangles(200, W, H, seed=5, alpha=None, extent=0.5)
+    def script(api):
+        st = G.setup_scene(api, scene, indexed=False, init=False)
+        api.glClear(3)
+        api.glDrawArrays(G.GL_TRIANGLES, 0, st["n_draw"])
+    a, b = _both(gpu_api, reference, script)
+    _assert_same(a, b, 100)
+    want_bytes = np.stack([(b[0] >> 24) & 255, (b[0] >> 16) & 255, (b[0] >> 8) & 255, b[0] & 255], axis=-1).astype(np.uint8)
+    rgba = np.zeros((H, W, 4), np.uint8)
+    assert gpu_api.swglReadPixelsRGBA8(rgba.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(rgba, want_bytes)
+    path = tmp_path / "frame.ppm"
+    assert gpu_api.swglWritePPM(str(path).encode()) == 0
+    raw = path.read_bytes()
+    header = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(header) and len(raw) == len(header) + W * H * 3
+    assert np.array_equal(np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3), want_bytes[:, :, :3])
+    assert gpu_api.swglWritePPM(b"/nonexistent-dir/x.ppm") != 0
+    assert b"swglWritePPM" in gpu_api.swglGetLastError()
