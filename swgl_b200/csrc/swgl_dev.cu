@@ -322,6 +322,29 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 	}
 	tr_top = tr_hi;
 
+	if (!INLINE_INSERT && band == 0xffffffffu)
+	{
+		/* Short and narrow (the bulk of a fine mesh): bin by the x extent of the three vertices instead of
+		 * walking the spans here -- the raster kernels walk them anyway and clamp to their tile.  The
+		 * walk's x0/x1 stay inside the hull of the vertex columns up to the rounding of at most two tile
+		 * heights of slope additions: with |x| <= 2^15 and an extent of at most 64 pixels that is below
+		 * 0.25 pixel, so [xmin - 1, xmax + 1] covers every pixel row_span() can produce. */
+		const float xmin = fminf(fminf(a.x, b.x), c.x), xmax = fmaxf(fmaxf(a.x, b.x), c.x);
+		if (xmin >= -32768.0f && xmax <= 32768.0f && xmax - xmin <= 64.0f)
+		{
+			const int lo = max((int)xmin - 1, max((int)P.fvx, 0));
+			const int hi = min((int)xmax + 1, min((int)ceilf(P.xlimit), (int)P.W) - 1);
+			if (lo <= hi && !(P.diag & 1u))
+			{
+				const uint32_t pk = ((uint32_t)lo >> SWGL_TILE_SHIFT) | (((uint32_t)hi >> SWGL_TILE_SHIFT) << 16);
+				if (owns_tile_row(P, tr_hi)) pk0 = pk;
+				if (tr_hi >= tr_lo + 1u && owns_tile_row(P, tr_hi - 1u)) pk1 = pk;
+				if (tr_hi >= tr_lo + 2u && owns_tile_row(P, tr_hi - 2u)) pk2 = pk;
+			}
+			return 1u;
+		}
+	}
+
 	/* the walk (swgl.c:3356-3361, 3466-3471) */
 	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
 	bool switched = false;

@@ -21,7 +21,7 @@ for l in sass[start:end]:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", l) or re.match(r"\s+[A-Z@!]", l):
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l) or re.match(r"\s+[A-Z@!]", l):
         if re.match(r"\s+\.", l):
             continue
         ins_lines.append((cur, l.strip()))
