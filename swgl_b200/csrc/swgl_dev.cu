@@ -63,6 +63,7 @@ struct swgldev_ctx
 	cudaEvent_t draw_ev[8];
 	uint64_t draw_serial;
 	uint32_t* d_maxidx;
+	float* lut255;
 	uint32_t draws_since_map;
 	uint32_t* peer_color;
 	uint32_t rank, n_ranks, band_rows;
@@ -96,6 +97,7 @@ struct swgldev_ctx
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror;
 	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
+	int64_t selftest_mismatches;
 	cudaEvent_t stage_ev[8];
 	double stage_us[8];                  /* accumulated per-stage device time (stage timing mode) */
 	uint64_t stage_draws;
@@ -152,6 +154,8 @@ __global__ void k_clear(uint32_t* __restrict__ color, float* __restrict__ depth,
 	}
 }
 
+__global__ void k_init_lut255(float* lut) { lut[threadIdx.x] = (float)threadIdx.x / 255.0f; }
+
 __global__ void k_fill_fb(uint32_t* __restrict__ color, float* __restrict__ depth, size_t n, uint32_t word, float d)
 {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,6 +177,62 @@ __global__ void __launch_bounds__(256) k_max_index(const uint32_t* __restrict__ 
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = max(m, __ldg(idx + i));
 	for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
 	if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
+}
+
+/* ---- self-test of the shared-reciprocal division (swgl_dev_math.cuh) against `/` on the three
+ * operand domains frag_weights_fast() relies on; counts results that differ in any bit ---- */
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& s)
+{
+	uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint32_t test_mantissa(uint64_t r)
+{
+	const uint32_t m = (uint32_t)(r >> 8) & 0x7fffffu;
+	switch ((uint32_t)r & 15u)
+	{
+	case 0: return 0u;
+	case 1: return 0x7fffffu;
+	case 2: return 0x7ffffeu;
+	case 3: return 1u;
+	case 4: return 0x400000u;
+	case 5: return 1u << (m % 23u);
+	case 6: return 0x7fffffu ^ (1u << (m % 23u));
+	default: return m;
+	}
+}
+
+__device__ __forceinline__ float test_float(uint32_t sign, int exp2, uint32_t mant, bool integer_valued)
+{
+	if (integer_valued && exp2 < 23) mant &= ~((1u << (23 - exp2)) - 1u);
+	return __uint_as_float((sign << 31) | ((uint32_t)(exp2 + 127) << 23) | mant);
+}
+
+__global__ void __launch_bounds__(256) k_selftest_division(uint64_t n, uint64_t seed, unsigned long long* mismatches)
+{
+	unsigned long long bad = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		uint64_t s = seed ^ (i * 0xD1342543DE82EF95ull);
+		const uint64_t r0 = splitmix64(s), r1 = splitmix64(s), r2 = splitmix64(s);
+		const uint32_t cls = (uint32_t)(i % 3u);
+		/* dividend exponent range, divisor exponent range per domain (see frag_weights_fast) */
+		const int xlo = cls == 0 ? 0 : cls == 1 ? -82 : -98, xhi = cls == 0 ? 61 : cls == 1 ? 62 : 78;
+		const int ylo = cls == 0 ? 0 : cls == 1 ? -16 : -30, yhi = cls == 0 ? 58 : cls == 1 ? 15 : 23;
+		const int ex = xlo + (int)((r2 >> 8) % (uint64_t)(xhi - xlo + 1));
+		const int ey = ylo + (int)((r2 >> 24) % (uint64_t)(yhi - ylo + 1));
+		float x = test_float((uint32_t)(r2 & 1u), ex, test_mantissa(r0), cls == 0);
+		const float y = test_float((uint32_t)((r2 >> 1) & 1u), ey, test_mantissa(r1), cls == 0);
+		if (((r2 >> 2) & 15u) == 0) x = __uint_as_float((uint32_t)(r2 & 1u) << 31);    /* +-0 */
+		const float fast = div_shared(x, y, rcp_refined(y));
+		const float ref = x / y;
+		if (__float_as_uint(fast) != __float_as_uint(ref)) bad++;
+	}
+	for (int o = 16; o > 0; o >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, o);
+	if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 __device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P)
@@ -1005,10 +1065,10 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
-	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr;
+	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->lut255 = nullptr;
 	for (int i = 0; i < 8; i++) c->draw_ev[i] = nullptr;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
@@ -1028,6 +1088,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming) == cudaSuccess
 	       && cudaMalloc((void**)&c->d_maxidx, 4) == cudaSuccess
+	       && cudaMalloc((void**)&c->lut255, 256 * sizeof(float)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[0], cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[1], cudaEventDisableTiming) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_depth, (npx ? npx : 1) * 4) == cudaSuccess
@@ -1049,6 +1110,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 		return nullptr;
 	}
 	memset(c->h_ctr, 0, sizeof(Counters));
+	k_init_lut255<<<1, 256, 0, c->stream>>>(c->lut255);
 	c->h_color = c->h_mirror[0];
 	for (int i = 0; i < 8; i++)
 		if (cudaEventCreateWithFlags(&c->draw_ev[i], cudaEventDisableTiming) != cudaSuccess) { swgldev_destroy(c); return nullptr; }
@@ -1079,6 +1141,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->h_mirror[1]) cudaFreeHost(c->h_mirror[1]);
 	if (c->rgba_staging) cudaFree(c->rgba_staging);
 	if (c->d_maxidx) cudaFree(c->d_maxidx);
+	if (c->lut255) cudaFree(c->lut255);
 	for (int i = 0; i < 2; i++) if (c->frame_ev[i]) cudaEventDestroy(c->frame_ev[i]);
 	for (int i = 0; i < 8; i++) if (c->draw_ev[i]) cudaEventDestroy(c->draw_ev[i]);
 	cudaFree(c->tile_count); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
@@ -1422,7 +1485,7 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 		P.fs_ops = upload_code(c, d->fs_code_id, d->fs_code); P.fs_nops = d->fs_code->n_ops;
 		if (!P.fs_ops) { set_err(c, "fragment shader upload failed", cudaGetLastError()); return 1; }
 	}
-	P.tile_count = c->tile_count; P.ctr = c->ctr;
+	P.tile_count = c->tile_count; P.ctr = c->ctr; P.lut255 = c->lut255;
 	return 0;
 }
 
@@ -1693,6 +1756,21 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 		/* test hook: force a (small) list capacity for the next draws */
 		c->bin_cap = (uint32_t)value;
 	}
+	else if (!strcmp(name, "selftest_division") && value > 0)
+	{
+		/* value = number of operand pairs; result in get_option("selftest_division_mismatches") */
+		unsigned long long* d = nullptr;
+		unsigned long long h = ~0ull;
+		if (cudaMalloc((void**)&d, 8) == cudaSuccess)
+		{
+			cudaMemsetAsync(d, 0, 8, c->stream);
+			k_selftest_division<<<148 * 8, 256, 0, c->stream>>>((uint64_t)value, 0x5357474cull + (uint64_t)value, d);
+			c->n_launches++;
+			if (cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) h = ~0ull;
+			cudaFree(d);
+		}
+		c->selftest_mismatches = (int64_t)h;
+	}
 	else if (!strcmp(name, "stage_timing"))
 	{
 		c->opt_stage_timing = (int)value;
@@ -1715,6 +1793,7 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "stage_draws")) return (int64_t)c->stage_draws;
 	if (!strncmp(name, "stage_ns_", 9)) { int i = atoi(name + 9); return (i >= 0 && i < 3) ? (int64_t)(c->stage_us[i] * 1000.0) : -1; }
 	if (!strcmp(name, "bin_cap")) return c->bin_cap;
+	if (!strcmp(name, "selftest_division_mismatches")) return c->selftest_mismatches;
 	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "sizeof_draw_params")) return (int64_t)sizeof(DrawParams);
 	return -1;

@@ -96,6 +96,7 @@ struct DrawParams
 	Prim* prims; BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
 	Counters* ctr;
+	const float* lut255;        /* byte / 255.0f (swgl.c:2116, 3434-3437), computed once on the device */
 	uint32_t* winner;           /* GL_POINTS: per-pixel index+1 of the last point submitted to it (0 = none) */
 	/* shaders */
 	int32_t vs_kind, fs_kind;

@@ -5,12 +5,15 @@
  * anywhere after the prologue.  Per batch of 32 primitives (ascending primitive id):
  *
  *   A  lane = primitive: replay the span walk over the tile's 8 rows (swgl.c:3356-3361,
- *      3466-3471), spans to shared memory, fragment count in a register;
- *   S  warp shuffle scan of the counts;
- *   B  lane = fragment, dense steps of 32: shuffle binary search for the owning lane, row walk
- *      over at most 8 spans, Barycentric + perspective + z (swgl.c:3365-3382), fragment shader,
- *      then the ordered part: lanes that hit the same pixel are found with __match_any_sync and
- *      commit (depth test + blend, swgl.c:3387-3462) in lane order = submission order.
+ *      3466-3471); each row's span stays in a register, fragment and span counts too;
+ *   S  one warp shuffle scan of both counts, then every non-empty span is appended to the batch's
+ *      span list (first fragment, row, first column, primitive lane) and its first fragment is
+ *      marked in a bit map (one word per step of phase B);
+ *   B  lane = fragment, dense steps of 32: the step's word of the bit map and a population count
+ *      give the span of each lane (no search), Barycentric + perspective + z (swgl.c:3365-3382)
+ *      with shared reciprocals (frag_weights_fast), fragment shader, then the ordered part: lanes
+ *      that hit the same pixel are found with __match_any_sync and commit (depth test + blend,
+ *      swgl.c:3387-3462) in lane order = submission order.
  *
  * Compared with the CTA-per-32x32-tile kernel (k_raster_frag) this trades ~40 % more
  * (tile, primitive) pairs for: no __syncthreads in the hot loop, shuffle scans instead of block
@@ -24,13 +27,26 @@
 #define WT_PIX      (SWGL_TILE * WT_H)
 #define WT_WARPS    4        /* tiles per CTA */
 #define WT_SORT_CAP 256      /* list entries a warp sorts in shared memory */
+#define WT_MAX_SPANS (32 * WT_H)             /* (primitive, row) spans of one batch */
+#define WT_MAX_FRAGS (32 * WT_PIX)           /* fragments of one batch */
 
+/* span entry: first fragment (13 bits) | tile row << 13 | first column << 16 | primitive lane << 21
+ * | primitive passed prim_fast_ok() << 26 */
+#define WT_PC_WORDS (4 * PC_VEC4)             /* per-primitive constants of phase B, see prim_consts() */
 struct WarpTile
 {
 	uint32_t color[WT_PIX];
 	float    depth[WT_PIX];
-	uint32_t ids[WT_SORT_CAP];
-	uint16_t span[WT_H][32];       /* [row][lane]: xa | xb << 8 */
+	union
+	{
+		uint32_t ids[WT_SORT_CAP];               /* scratch of the list sort (before the first batch) */
+		struct
+		{
+			uint32_t span[WT_MAX_SPANS];         /* this batch's non-empty spans in fragment order */
+			uint32_t start_bits[WT_MAX_FRAGS / 32];  /* bit f: fragment f is the first of a span */
+		} b;
+	} u;
+	float4   pc[32 * WT_PC_WORDS / 4];       /* [primitive lane][6]: constants staged by phase A */
 };
 
 struct WarpShared
@@ -54,10 +70,31 @@ __device__ __forceinline__ uint32_t warp_sort32(uint32_t x, uint32_t lane)
 	return x;
 }
 
+/* a bitonic sequence of 32 (one value per lane) -> ascending */
+__device__ __forceinline__ uint32_t warp_bitonic_clean(uint32_t x, uint32_t lane)
+{
+#pragma unroll
+	for (uint32_t j = 16; j > 0; j >>= 1)
+	{
+		const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+		x = (lane & j) ? max(x, y) : min(x, y);
+	}
+	return x;
+}
+
+/* two ascending runs of 32 (a, b) -> one ascending run of 64 (a = lower half, b = upper half) */
+__device__ __forceinline__ void warp_merge64(uint32_t& a, uint32_t& b, uint32_t lane)
+{
+	const uint32_t rb = __shfl_sync(0xffffffffu, b, 31u - lane);
+	const uint32_t lo = min(a, rb), hi = max(a, rb);
+	a = warp_bitonic_clean(lo, lane);
+	b = warp_bitonic_clean(hi, lane);
+}
+
 /* In-place ascending sort of n ids by one warp (shared or global memory).  Bitonic network in its
  * "flip + half-cleaner" form: every compare-exchange moves the smaller key to the lower index, so
  * the virtual 0xffffffff padding beyond n never has to move and n need not be a power of two. */
-__device__ __forceinline__ void warp_sort_mem(uint32_t* ids, uint32_t n, uint32_t lane)
+__device__ __noinline__ void warp_sort_mem(uint32_t* ids, uint32_t n, uint32_t lane)
 {
 	uint32_t n_pow2 = 1; while (n_pow2 < n) n_pow2 <<= 1;
 	for (uint32_t k = 2; k <= n_pow2; k <<= 1)
@@ -117,12 +154,31 @@ __device__ __forceinline__ void wt_load8(const DrawParams& P, const ClearParams&
 		}
 }
 
+/* Shading of a fragment that failed the depth test before the ordered part and passes in it (an
+ * earlier fragment of the same step stored exactly 0.0 = "empty"): rare, kept out of the hot loop. */
 template <int FS>
-__global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_constant__ DrawParams P)
+__device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, float px, float py)
+{
+	const Prim* q = P.prims + pid;
+	BaryConst k;
+	bary_setup(q->v[0], q->v[1], q->v[2], k);
+	FragIn fi;
+	float z2;
+	frag_weights(k, px, py, fi.u, fi.v, fi.w, z2);
+	fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
+	fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
+	fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
+	fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
+	fi.stride = 1;
+	return clamp_color(run_fragment<FS>(P, fi));
+}
+
+template <int FS>
+__global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_constant__ DrawParams P)
 {
 	__shared__ WarpShared S;
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = (float)i / 255.0f;
+	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
 	__syncthreads();            /* the only block-level barrier */
 
 	const uint32_t n_tiles = P.tiles_x * P.tiles_y;
@@ -171,68 +227,53 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 		/* ---- ascending primitive id = submission order ---- */
 		uint32_t* gl_ids = P.pairs + (size_t)tile * P.bin_cap;
 		const uint32_t* sorted = gl_ids;
-		uint32_t first_batch_id = 0xffffffffu;
-		if (n_list <= 32)
-			first_batch_id = warp_sort32(lane < n_list ? gl_ids[lane] : 0xffffffffu, lane);
-		else if (n_list <= 128)
+		uint32_t xs0 = 0xffffffffu, xs1 = 0xffffffffu, xs2 = 0xffffffffu, xs3 = 0xffffffffu;
+		if (n_list <= 128)
 		{
-			/* up to four runs of 32, each sorted with the shuffle network; an id's final place is its
-			 * position in its own run plus the ids below it in the other runs (branch-free lower
-			 * bounds, all runs in flight); ranks stay in registers until every lane has finished
-			 * reading the runs, then the ids are scattered to their final places */
-			const uint32_t n_runs = (n_list + 31u) >> 5;
-			uint32_t x[4], rank[4];
-#pragma unroll
-			for (uint32_t c = 0; c < 4; c++)
+			/* up to four runs of 32 sorted with the shuffle network and merged with bitonic merges:
+			 * the whole list stays in registers (element 32 * c + lane in xs[c]) */
+			xs0 = warp_sort32(lane < n_list ? gl_ids[lane] : 0xffffffffu, lane);
+			if (n_list > 32)
 			{
-				x[c] = 0xffffffffu;
-				if (c < n_runs)
-				{
-					const uint32_t i = (c << 5) + lane;
-					x[c] = warp_sort32(i < n_list ? gl_ids[i] : 0xffffffffu, lane);
-					T.ids[i] = x[c];
-				}
+				xs1 = warp_sort32(32u + lane < n_list ? gl_ids[32u + lane] : 0xffffffffu, lane);
+				warp_merge64(xs0, xs1, lane);
 			}
-			__syncwarp();
-#pragma unroll
-			for (uint32_t c = 0; c < 4; c++)
+			if (n_list > 64)
 			{
-				rank[c] = lane;
-				if (c < n_runs && x[c] != 0xffffffffu)
+				xs2 = warp_sort32(64u + lane < n_list ? gl_ids[64u + lane] : 0xffffffffu, lane);
+				if (n_list > 96)
 				{
-					uint32_t cnt[4] = { 0u, 0u, 0u, 0u };
-#pragma unroll
-					for (uint32_t st = 32; st > 0; st >>= 1)
-#pragma unroll
-						for (uint32_t r = 0; r < 4; r++)
-							if (r != c && r < n_runs && cnt[r] + st <= 32u && T.ids[(r << 5) + cnt[r] + st - 1u] < x[c]) cnt[r] += st;
-					rank[c] += cnt[0] + cnt[1] + cnt[2] + cnt[3];
+					xs3 = warp_sort32(96u + lane < n_list ? gl_ids[96u + lane] : 0xffffffffu, lane);
+					warp_merge64(xs2, xs3, lane);
 				}
+				/* 64 + 64: reverse the upper run, compare-exchange, then clean both bitonic halves */
+				const uint32_t r2 = __shfl_sync(0xffffffffu, xs3, 31u - lane), r3 = __shfl_sync(0xffffffffu, xs2, 31u - lane);
+				const uint32_t l0 = min(xs0, r2), l1 = min(xs1, r3), h0 = max(xs0, r2), h1 = max(xs1, r3);
+				xs0 = warp_bitonic_clean(min(l0, l1), lane); xs1 = warp_bitonic_clean(max(l0, l1), lane);
+				xs2 = warp_bitonic_clean(min(h0, h1), lane); xs3 = warp_bitonic_clean(max(h0, h1), lane);
 			}
-			__syncwarp();
-#pragma unroll
-			for (uint32_t c = 0; c < 4; c++)
-				if (c < n_runs && x[c] != 0xffffffffu) T.ids[rank[c]] = x[c];
-			__syncwarp();
-			sorted = T.ids;
 		}
 		else if (n_list <= WT_SORT_CAP)
 		{
-			for (uint32_t i = lane; i < n_list; i += 32) T.ids[i] = gl_ids[i];
+			for (uint32_t i = lane; i < n_list; i += 32) T.u.ids[i] = gl_ids[i];
 			__syncwarp();
-			warp_sort_mem(T.ids, n_list, lane);
-			sorted = T.ids;
+			warp_sort_mem(T.u.ids, n_list, lane);
+			for (uint32_t i = lane; i < n_list; i += 32) gl_ids[i] = T.u.ids[i];   /* the scratch is reused by the batches */
+			__syncwarp();
 		}
 		else warp_sort_mem(gl_ids, n_list, lane);
 
 		for (uint32_t base = 0; base < n_list; base += 32)
 		{
 			const uint32_t nb = min(32u, n_list - base);
-			/* ---- phase A: lane = primitive ---- */
-			const uint32_t pid = (n_list <= 32) ? first_batch_id : (lane < nb ? sorted[base + lane] : 0xffffffffu);
-			uint32_t cnt = 0, rowinfo = 0;
+			/* ---- phase A: lane = primitive.  Replay the walk over the tile's rows; row r's span
+			 * (first column | length << 8) stays in a register ---- */
+			const uint32_t pid = (n_list <= 128) ? (base == 0 ? xs0 : base == 32 ? xs1 : base == 64 ? xs2 : xs3)
+			                                     : (lane < nb ? sorted[base + lane] : 0xffffffffu);
+			uint32_t cnt = 0, nsp = 0, fast = 0;
+			uint32_t sp[WT_H];
 #pragma unroll
-			for (int r = 0; r < WT_H; r++) T.span[r][lane] = 0;
+			for (int r = 0; r < WT_H; r++) sp[r] = 0u;
 			if (lane < nb)
 			{
 				const Prim* q = P.prims + pid;
@@ -243,51 +284,72 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 				const int y_in = max(w.ys, band_first_y), y_out = min(w.ye - 1, band_last_y);
 				if (y_out >= y_in)
 				{
+					fast = prim_fast_ok(a, b, c) ? 1u : 0u;
+					prim_consts(a, b, c, q->vid[0], q->vid[1], q->vid[2], pid, &T.pc[lane * PC_VEC4]);
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
-					for (int y = y_in; y <= y_out; y++)
+#pragma unroll
+					for (int r = WT_H - 1; r >= 0; r--)
 					{
-						int xa, xb;
-						row_span(x0, x1, P, xa, xb);
-						xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
-						xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
-						if (xb < xa) xb = xa;
-						T.span[band_last_y - y][lane] = (uint16_t)(xa | (xb << 8));
-						cnt += (uint32_t)(xb - xa);
-						if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-						x0 += w.s0; x1 += s1;
+						const int y = band_last_y - r;
+						if (y >= y_in && y <= y_out)
+						{
+							int xa, xb;
+							row_span(x0, x1, P, xa, xb);
+							xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
+							xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
+							if (xb > xa)
+							{
+								sp[r] = (uint32_t)xa | ((uint32_t)(xb - xa) << 8);
+								cnt += (uint32_t)(xb - xa);
+								nsp++;
+							}
+							if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+							x0 += w.s0; x1 += s1;
+						}
 					}
-					rowinfo = (uint32_t)(band_last_y - y_out) | ((uint32_t)(y_out - y_in + 1) << 8);
 				}
 			}
-			/* ---- S: exclusive scan of the fragment counts ---- */
-			uint32_t incl = cnt;
+			/* ---- S: one exclusive scan for fragment counts (low half) and span counts (high half) ---- */
+			const uint32_t both = cnt | (nsp << 16);
+			uint32_t incl = both;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += y; }
-			const uint32_t off = incl - cnt;
-			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t excl = incl - both;
+			const uint32_t last = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t total = last & 0xffffu;       /* at most 32 x 256 = 8192 fragments, 256 spans */
 			n_tested += (lane == 0) ? total : 0u;
+			if (total == 0) continue;
+			for (uint32_t j = lane; (j << 5) < total; j += 32) T.u.b.start_bits[j] = 0u;
+			__syncwarp();
+			{
+				uint32_t run = excl & 0xffffu, k = excl >> 16;
+#pragma unroll
+				for (int r = 0; r < WT_H; r++)
+				{
+					const uint32_t len = sp[r] >> 8;
+					if (len)
+					{
+						T.u.b.span[k++] = run | ((uint32_t)r << 13) | ((sp[r] & 31u) << 16) | (lane << 21) | (fast << 26);
+						atomicOr(&T.u.b.start_bits[run >> 5], 1u << (run & 31u));
+						run += len;
+					}
+				}
+			}
 			__syncwarp();
 
 			/* ---- phase B: lane = fragment, dense steps of 32 in submission order ---- */
+			uint32_t spans_before = 0;           /* spans that start before this step */
 			for (uint32_t t0 = 0; t0 < total; t0 += 32)
 			{
 				const uint32_t t = t0 + lane;
 				const bool active = t < total;
-				/* owner = last lane whose offset is <= t (empty lanes share the offset of their
-				 * successor, so the last one is the lane that really owns fragment t) */
-				uint32_t owner = 0;
-#pragma unroll
-				for (uint32_t st = 16; st > 0; st >>= 1)
-				{
-					const uint32_t probe = min(owner + st, 31u);
-					const uint32_t v = __shfl_sync(0xffffffffu, off, probe);
-					if (owner + st < 32u && v <= t) owner += st;
-				}
-				const uint32_t o_off = __shfl_sync(0xffffffffu, off, owner);
-				const uint32_t o_rows = __shfl_sync(0xffffffffu, rowinfo, owner);
-				const uint32_t o_pid = __shfl_sync(0xffffffffu, pid, owner);
+				/* the span of fragment t: the last one that starts at or before it */
+				const uint32_t starts = T.u.b.start_bits[t0 >> 5];
+				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & (0xffffffffu >> (31u - lane))) - 1u];
+				spans_before += (uint32_t)__popc(starts);
+				const float4* pc = &T.pc[((e >> 21) & 31u) * PC_VEC4];
 				bool pending = active;
 				uint32_t pix = 0;
 				float z = 0.0f;
@@ -295,30 +357,25 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 				bool shaded_early = false;
 				if (active)
 				{
-					uint32_t g = t - o_off, r = o_rows & 0xffu, sp = 0;
-					const uint32_t r_end = r + (o_rows >> 8);
-					for (; r < r_end; r++)
-					{
-						sp = T.span[r][owner];
-						const uint32_t len = (sp >> 8) - (sp & 0xffu);
-						if (g < len) break;
-						g -= len;
-					}
-					const uint32_t lx = (sp & 0xffu) + g;
+					const uint32_t r = (e >> 13) & 7u;
+					const uint32_t lx = ((e >> 16) & 31u) + (t - (e & 0x1fffu));
 					pix = r * SWGL_TILE + lx;
-					const Prim* q = P.prims + o_pid;
-					const float4 a = q->v[0], b = q->v[1], c = q->v[2];
-					BaryConst k;
-					bary_setup(a, b, c, k);
 					FragIn fi;
-					frag_weights(k, (float)(tile_x0 + (int)lx), (float)(band_last_y - (int)r), fi.u, fi.v, fi.w, z);
+					const float px = (float)(tile_x0 + (int)lx), py = (float)(band_last_y - (int)r);
+					if (!(frag_weights_fast(pc, px, py, fi.u, fi.v, fi.w, z) && ((e >> 26) & 1u)))
+					{
+						const Prim* q = P.prims + __float_as_uint(pc[5].w);
+						const float4 s4 = frag_weights_slow(q->v[0], q->v[1], q->v[2], px, py);
+						fi.u = s4.x; fi.v = s4.y; fi.w = s4.z; z = s4.w;
+					}
 					/* the fragment shader does not read the framebuffer: run it before the ordered
 					 * part unless the fragment already fails against the stored depth (then it can only
 					 * pass later if an earlier fragment stores exactly 0.0 = "empty": shaded late) */
 					const float cur = T.depth[pix];
 					if (cur == 0.0f || cur >= z)
 					{
-						fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
+						const float4 ids = pc[5];
+						fi.vid0 = __float_as_uint(ids.x); fi.vid1 = __float_as_uint(ids.y); fi.vid2 = __float_as_uint(ids.z);
 						fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
 						fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 						fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
@@ -329,10 +386,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 				}
 				/* ---- ordered commit: lanes on the same pixel go in lane order ---- */
 				const uint32_t peers = __match_any_sync(0xffffffffu, active ? pix : (0x80000000u | lane));
-				uint32_t my_turn = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-				uint32_t turns = my_turn;
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) turns = max(turns, __shfl_xor_sync(0xffffffffu, turns, o));
+				const uint32_t my_turn = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+				const uint32_t turns = __reduce_max_sync(0xffffffffu, my_turn);
 				for (uint32_t turn = 0; turn <= turns; turn++)
 				{
 					if (pending && my_turn == turn)
@@ -343,20 +398,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32) k_raster_warp(const __grid_cons
 							T.depth[pix] = z;
 							n_shaded++;
 							if (!shaded_early)
-							{
-								const Prim* q = P.prims + o_pid;
-								BaryConst k;
-								bary_setup(q->v[0], q->v[1], q->v[2], k);
-								FragIn fi;
-								float z2;
-								frag_weights(k, (float)(tile_x0 + (int)(pix & (SWGL_TILE - 1))), (float)(band_last_y - (int)(pix >> SWGL_TILE_SHIFT)), fi.u, fi.v, fi.w, z2);
-								fi.vid0 = q->vid[0]; fi.vid1 = q->vid[1]; fi.vid2 = q->vid[2];
-								fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
-								fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
-								fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
-								fi.stride = 1;
-								col = clamp_color(run_fragment<FS>(P, fi));
-							}
+								col = shade_late<FS>(P, __float_as_uint(pc[5].w), (float)(tile_x0 + (int)(pix & (SWGL_TILE - 1))), (float)(band_last_y - (int)(pix >> SWGL_TILE_SHIFT)));
 							T.color[pix] = blend_pack_lut(col.x, col.y, col.z, col.w, T.color[pix], S.lut);
 							dirty = true;
 						}
