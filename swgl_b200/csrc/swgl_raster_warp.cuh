@@ -28,7 +28,7 @@
 #define WT_WARPS    4        /* tiles per CTA */
 #define WT_SORT_CAP 256      /* list entries a warp sorts in shared memory */
 #define WT_MAX_SPANS (32 * WT_H)             /* (primitive, row) spans of one batch */
-#define WT_MAX_FRAGS (32 * WT_PIX)           /* fragments of one batch */
+#define WT_MAX_FRAGS 2048                     /* fragments of one batch: a batch that would produce more is cut short */
 
 /* span entry: first fragment (13 bits) | tile row << 13 | first column << 16 | primitive lane << 21
  * | primitive passed prim_fast_ok() << 26 */
@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	__syncwarp();
 
 	uint32_t n_tested = 0, n_shaded = 0;
+	/* packed vec4 varying records can be fetched with 128-bit loads */
+	const bool vary_vec4 = ((P.nvf | P.fs_slot) & 3u) == 0 && (((uintptr_t)P.vary) & 15u) == 0;
 	if (n_list > 0)
 	{
 		/* ---- ascending primitive id = submission order ---- */
@@ -263,13 +265,23 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 		}
 		else warp_sort_mem(gl_ids, n_list, lane);
 
-		for (uint32_t base = 0; base < n_list; base += 32)
+		uint32_t take = 32;                      /* primitives consumed by the batch */
+		for (uint32_t base = 0; base < n_list; base += take)
 		{
 			const uint32_t nb = min(32u, n_list - base);
+			take = 32;
 			/* ---- phase A: lane = primitive.  Replay the walk over the tile's rows; row r's span
 			 * (first column | length << 8) stays in a register ---- */
-			const uint32_t pid = (n_list <= 128) ? (base == 0 ? xs0 : base == 32 ? xs1 : base == 64 ? xs2 : xs3)
-			                                     : (lane < nb ? sorted[base + lane] : 0xffffffffu);
+			uint32_t pid;
+			if (n_list > 128) pid = lane < nb ? sorted[base + lane] : 0xffffffffu;
+			else if ((base & 31u) == 0) pid = base == 0 ? xs0 : base == 32 ? xs1 : base == 64 ? xs2 : xs3;
+			else
+			{   /* after a batch that was cut short: element base + lane of the register-resident list */
+				const uint32_t i = base + lane, sl = i & 31u, sr = i >> 5;
+				const uint32_t v0 = __shfl_sync(0xffffffffu, xs0, sl), v1 = __shfl_sync(0xffffffffu, xs1, sl);
+				const uint32_t v2 = __shfl_sync(0xffffffffu, xs2, sl), v3 = __shfl_sync(0xffffffffu, xs3, sl);
+				pid = sr == 0 ? v0 : sr == 1 ? v1 : sr == 2 ? v2 : sr == 3 ? v3 : 0xffffffffu;
+			}
 			uint32_t cnt = 0, nsp = 0, fast = 0;
 			uint32_t sp[WT_H];
 #pragma unroll
@@ -318,13 +330,26 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += y; }
 			const uint32_t excl = incl - both;
 			const uint32_t last = __shfl_sync(0xffffffffu, incl, 31);
-			const uint32_t total = last & 0xffffu;       /* at most 32 x 256 = 8192 fragments, 256 spans */
+			uint32_t total = last & 0xffffu;             /* at most 32 x 256 = 8192 fragments, 256 spans */
+			uint32_t excl_k = excl;
+			if (total > WT_MAX_FRAGS)
+			{
+				/* more fragments than the start-bit map holds: keep the leading primitives that fit (at
+				 * least 8, a primitive has at most 256 fragments here) and start the next batch behind them */
+				take = (uint32_t)__popc(__ballot_sync(0xffffffffu, (incl & 0xffffu) <= WT_MAX_FRAGS));
+				total = __shfl_sync(0xffffffffu, incl, take - 1u) & 0xffffu;
+				if (lane >= take)
+				{
+#pragma unroll
+					for (int r = 0; r < WT_H; r++) sp[r] = 0u;
+				}
+			}
 			n_tested += (lane == 0) ? total : 0u;
 			if (total == 0) continue;
 			for (uint32_t j = lane; (j << 5) < total; j += 32) T.u.b.start_bits[j] = 0u;
 			__syncwarp();
 			{
-				uint32_t run = excl & 0xffffu, k = excl >> 16;
+				uint32_t run = excl_k & 0xffffu, k = excl_k >> 16;
 #pragma unroll
 				for (int r = 0; r < WT_H; r++)
 				{
@@ -339,6 +364,19 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			}
 			__syncwarp();
 
+			/* the next batch's primitive records are requested now and arrive while this batch is shaded */
+			if (base + 32u < n_list && take == 32u && (base & 31u) == 0)
+			{
+				const uint32_t nxt = (n_list <= 128) ? (base == 0 ? xs1 : base == 32 ? xs2 : xs3)
+				                                     : (base + 32u + lane < n_list ? sorted[base + 32u + lane] : 0xffffffffu);
+				if (nxt != 0xffffffffu)
+				{
+					const Prim* q = P.prims + nxt;
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
+					asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)q + 32));
+				}
+			}
+
 			/* ---- phase B: lane = fragment, dense steps of 32 in submission order ---- */
 			uint32_t spans_before = 0;           /* spans that start before this step */
 			for (uint32_t t0 = 0; t0 < total; t0 += 32)
@@ -350,23 +388,50 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & (0xffffffffu >> (31u - lane))) - 1u];
 				spans_before += (uint32_t)__popc(starts);
 				const float4* pc = &T.pc[((e >> 21) & 31u) * PC_VEC4];
+				const uint32_t r = (e >> 13) & 7u;
+				const uint32_t lx = ((e >> 16) & 31u) + (t - (e & 0x1fffu));
+				const uint32_t pix = active ? r * SWGL_TILE + lx : (0x80000000u | lane);
+				/* lanes on the same pixel commit in lane order; the match is issued before the arithmetic
+				 * it does not depend on */
+				const uint32_t peers = __match_any_sync(0xffffffffu, pix);
+				/* the varyings of the fast shader shapes are requested before the weights are computed */
+				float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va, vc = va;
+				if (FS != SWFS_GENERIC && active)
+				{
+					const float4 ids = pc[5];
+					const float* pa = P.vary + (size_t)__float_as_uint(ids.x) * P.nvf + P.fs_slot;
+					const float* pb = P.vary + (size_t)__float_as_uint(ids.y) * P.nvf + P.fs_slot;
+					const float* pv = P.vary + (size_t)__float_as_uint(ids.z) * P.nvf + P.fs_slot;
+					if (FS == SWFS_VARYING)
+					{
+						if (vary_vec4) { va = __ldg((const float4*)pa); vb = __ldg((const float4*)pb); vc = __ldg((const float4*)pv); }
+						else
+						{
+							va = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
+							vb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+							vc = make_float4(__ldg(pv), __ldg(pv + 1), __ldg(pv + 2), __ldg(pv + 3));
+						}
+					}
+					else
+					{
+						va.x = __ldg(pa + P.fs_swz_u); va.y = __ldg(pa + P.fs_swz_v);
+						vb.x = __ldg(pb + P.fs_swz_u); vb.y = __ldg(pb + P.fs_swz_v);
+						vc.x = __ldg(pv + P.fs_swz_u); vc.y = __ldg(pv + P.fs_swz_v);
+					}
+				}
 				bool pending = active;
-				uint32_t pix = 0;
 				float z = 0.0f;
 				float4 col = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 				bool shaded_early = false;
 				if (active)
 				{
-					const uint32_t r = (e >> 13) & 7u;
-					const uint32_t lx = ((e >> 16) & 31u) + (t - (e & 0x1fffu));
-					pix = r * SWGL_TILE + lx;
-					FragIn fi;
+					float u, v, w;
 					const float px = (float)(tile_x0 + (int)lx), py = (float)(band_last_y - (int)r);
-					if (!(frag_weights_fast(pc, px, py, fi.u, fi.v, fi.w, z) && ((e >> 26) & 1u)))
+					if (!(frag_weights_fast(pc, px, py, u, v, w, z) && ((e >> 26) & 1u)))
 					{
 						const Prim* q = P.prims + __float_as_uint(pc[5].w);
 						const float4 s4 = frag_weights_slow(q->v[0], q->v[1], q->v[2], px, py);
-						fi.u = s4.x; fi.v = s4.y; fi.w = s4.z; z = s4.w;
+						u = s4.x; v = s4.y; w = s4.z; z = s4.w;
 					}
 					/* the fragment shader does not read the framebuffer: run it before the ordered
 					 * part unless the fragment already fails against the stored depth (then it can only
@@ -374,18 +439,28 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					const float cur = T.depth[pix];
 					if (cur == 0.0f || cur >= z)
 					{
-						const float4 ids = pc[5];
-						fi.vid0 = __float_as_uint(ids.x); fi.vid1 = __float_as_uint(ids.y); fi.vid2 = __float_as_uint(ids.z);
-						fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
-						fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
-						fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
-						fi.stride = 1;
-						col = clamp_color(run_fragment<FS>(P, fi));
+						if (FS == SWFS_VARYING)      /* InterpolateLinearEx (swgl.c:3270-3297) */
+							col = make_float4(va.x * u + vb.x * v + vc.x * w, va.y * u + vb.y * v + vc.y * w,
+							                  va.z * u + vb.z * v + vc.z * w, va.w * u + vb.w * v + vc.w * w);
+						else if (FS == SWFS_TEXTURE)
+							col = sample_nearest(P.tex[P.fs_tex_unit], va.x * u + vb.x * v + vc.x * w, va.y * u + vb.y * v + vc.y * w);
+						else
+						{
+							const float4 ids = pc[5];
+							FragIn fi;
+							fi.u = u; fi.v = v; fi.w = w;
+							fi.vid0 = __float_as_uint(ids.x); fi.vid1 = __float_as_uint(ids.y); fi.vid2 = __float_as_uint(ids.z);
+							fi.a = P.vary + (size_t)fi.vid0 * P.nvf + P.fs_slot;
+							fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
+							fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
+							fi.stride = 1;
+							col = run_fragment<FS>(P, fi);
+						}
+						col = clamp_color(col);
 						shaded_early = true;
 					}
 				}
-				/* ---- ordered commit: lanes on the same pixel go in lane order ---- */
-				const uint32_t peers = __match_any_sync(0xffffffffu, active ? pix : (0x80000000u | lane));
+				/* ---- ordered commit ---- */
 				const uint32_t my_turn = (uint32_t)__popc(peers & ((1u << lane) - 1u));
 				const uint32_t turns = __reduce_max_sync(0xffffffffu, my_turn);
 				for (uint32_t turn = 0; turn <= turns; turn++)

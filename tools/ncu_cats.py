@@ -4,18 +4,19 @@ rep = sys.argv[1]
 kern = sys.argv[2] if len(sys.argv) > 2 else "_Z13k_raster_warpILi1EEv10DrawParams"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(root, "swgl_b200/csrc/swgl_raster_warp.cuh")).read().splitlines()
+KSTART = next(i for i, l in enumerate(src) if "k_raster_warp(const __grid_constant__" in l)
 def find(marker):
-    return next(i + 1 for i, l in enumerate(src) if marker in l)
-marks = [("helpers", 1), ("prologue+stage", find("k_raster_warp(const __grid_constant__")), ("sort", find("ascending primitive id = submission order ----")),
+    return next(i + 1 for i, l in enumerate(src) if i >= KSTART and marker in l)
+marks = [("helpers(sort32,merge,stage)", 1), ("prologue+stage", find("k_raster_warp(const __grid_constant__")), ("sort", find("ascending primitive id = submission order ----")),
          ("phaseA", find("for (uint32_t base = 0; base < n_list; base += 32)")), ("scan+spans", find("---- S: one exclusive scan")),
-         ("locate", find("---- phase B: lane = fragment")), ("fetch+weights", find("const Prim* q = P.prims + o_pid;")),
+         ("locate", find("---- phase B: lane = fragment")), ("fetch+weights", find("FragIn fi;")),
          ("shade", find("the fragment shader does not read the framebuffer")), ("commit", find("---- ordered commit")),
          ("writeback", find("---- write-back"))]
 math = open(os.path.join(root, "swgl_b200/csrc/swgl_dev_math.cuh")).read().splitlines()
 def mfind(marker):
     return next(i + 1 for i, l in enumerate(math) if marker in l)
-mmarks = [("math misc", 1), ("fdiv", mfind("float fdiv(float x, float y)") - 5), ("phaseA(math)", mfind("float canon_nan") - 3), ("bary_setup", mfind("struct BaryConst") - 1),
-          ("weights slow", mfind("Barycentric + perspective correction + depth")), ("weights fast", mfind("the same eight divisions with shared")), ("blend etc", mfind("clamp, unpack destination, blend, pack"))]
+mmarks = [("math misc", 1), ("fdiv", mfind("float fdiv(float x, float y)") - 5), ("div_shared", mfind("Division with a shared, refined reciprocal")), ("phaseA(math)", mfind("float canon_nan") - 3), ("bary_setup", mfind("struct BaryConst") - 1),
+          ("weights slow", mfind("Barycentric + perspective correction + depth")), ("weights fast", mfind("the same eight divisions with shared")), ("prim_consts", mfind("Per-primitive constants of the fragment arithmetic")), ("weights fast", mfind("frag_weights() from staged constants")), ("blend etc", mfind("clamp, unpack destination, blend, pack"))]
 env = dict(os.environ, NCU_KERNEL="k_raster_warp")
 out = subprocess.run([sys.executable, os.path.join(root, "tools/ncu_lines.py"), rep, kern, "3000"], capture_output=True, text=True, env=env).stdout
 cats = {}
