@@ -305,6 +305,12 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 	P.clip_xy[v] = make_float2(pos.x, pos.y);
 }
 
+/* primitive 2t+k (k = 1: the second triangle the near clipper makes of input triangle t, rare) */
+__device__ __forceinline__ Prim* prim_at(const DrawParams& P, uint32_t pid)
+{
+	return ((pid & 1u) ? P.prims2 : P.prims) + (pid >> 1);
+}
+
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
 __device__ __forceinline__ bool owns_tile_row(const DrawParams& P, uint32_t tr)
 {
@@ -374,7 +380,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		band = atomicAdd(&P.ctr->band_cursor, nb);
 		if ((unsigned long long)band + nb > (unsigned long long)P.cap_bands) { atomicOr(&P.ctr->overflow, 2u); return 0u; }
 	}
-	Prim* out = P.prims + pid;
+	Prim* out = prim_at(P, pid);
 	if (!(P.diag & 2u))
 	{
 		out->v[0] = a; out->v[1] = b; out->v[2] = c;
@@ -517,26 +523,50 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 	}
 
 	/* warp-aggregated list insertion for the short, unclipped primitives: neighbouring triangles
-	 * mostly land in the same tile, so lanes that want the same tile share one atomicAdd */
+	 * mostly land in the same tile, so lanes that want the same tile share one atomicAdd.  The first
+	 * tile column of all three bands goes first, with the three atomics in flight together (the
+	 * round trip of an atomic that returns a value is what this kernel waits for); further columns
+	 * (primitives that straddle a tile boundary in x) follow one at a time. */
+	uint32_t base[3], peers[3], tile[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		const bool have = pk[k] != 0xffffffffu;
+		tile[k] = have ? (tr_top - (uint32_t)k) * P.tiles_x + (pk[k] & 0xffffu) : 0xffffffffu;
+		peers[k] = __match_any_sync(0xffffffffu, tile[k]);
+		base[k] = 0;
+		if (have && lane == (uint32_t)__ffs(peers[k]) - 1u) base[k] = atomicAdd(&P.tile_count[tile[k]], (uint32_t)__popc(peers[k]));
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		const uint32_t b0 = __shfl_sync(0xffffffffu, base[k], __ffs(peers[k]) - 1);
+		if (pk[k] != 0xffffffffu)
+		{
+			const uint32_t slot = b0 + (uint32_t)__popc(peers[k] & ((1u << lane) - 1u));
+			if (slot < P.bin_cap) P.pairs[(size_t)tile[k] * P.bin_cap + slot] = 2u * t;
+			else atomicOr(&P.ctr->overflow, 1u);
+		}
+	}
 #pragma unroll
 	for (int k = 0; k < 3; k++)
 	{
 		const uint32_t c1 = pk[k] >> 16;
-		uint32_t cx = pk[k] & 0xffffu;
+		uint32_t cx = (pk[k] & 0xffffu) + 1u;
 		const bool valid = pk[k] != 0xffffffffu;
 		while (__any_sync(0xffffffffu, valid && cx <= c1))
 		{
 			const bool have = valid && cx <= c1;
-			const uint32_t tile = have ? (tr_top - (uint32_t)k) * P.tiles_x + cx : 0xffffffffu;
-			const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-			const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-			uint32_t base = 0;
-			if (have && lane == leader) base = atomicAdd(&P.tile_count[tile], (uint32_t)__popc(peers));
-			base = __shfl_sync(0xffffffffu, base, leader);
+			const uint32_t tl = have ? (tr_top - (uint32_t)k) * P.tiles_x + cx : 0xffffffffu;
+			const uint32_t pr = __match_any_sync(0xffffffffu, tl);
+			const uint32_t leader = (uint32_t)__ffs(pr) - 1u;
+			uint32_t bs = 0;
+			if (have && lane == leader) bs = atomicAdd(&P.tile_count[tl], (uint32_t)__popc(pr));
+			bs = __shfl_sync(0xffffffffu, bs, leader);
 			if (have)
 			{
-				const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-				if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = 2u * t;
+				const uint32_t slot = bs + (uint32_t)__popc(pr & ((1u << lane) - 1u));
+				if (slot < P.bin_cap) P.pairs[(size_t)tl * P.bin_cap + slot] = 2u * t;
 				else atomicOr(&P.ctr->overflow, 1u);
 			}
 			cx++;
@@ -800,7 +830,7 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 			if (tid < nb)
 			{
 				const uint32_t pid = ids[base + tid];
-				const Prim pr = P.prims[pid];
+				const Prim pr = *prim_at(P, pid);
 				TriWalk w;
 				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
 				const int y_in = max(w.ys, band_first_y);
@@ -1528,7 +1558,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		if (c->bin_cap == 0) c->bin_cap = 256;
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
 	}
-	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims;
+	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims; P.prims2 = c->prims + ntri;
 
 	/* fused clear: the raster kernel starts the covered pixels from the clear value */
 	P.clear = c->pending_clear;

@@ -8,8 +8,9 @@
  *   clip_xy[V]         float2   clip-space x, y (only read when a triangle crosses the near plane)
  *   vary[V + 2T][NVF]  float    packed varyings; the last 2T records are the vertices the near
  *                               clipper creates (at most two per input triangle)
- *   prims[2T]          64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
- *                               record ids + first band entry; slot 2t+k keeps submission order
+ *   prims[T] prims2[T] 64 B     screen-space primitive: 3 x (X, Y, z_clip, w_clip) + varying
+ *                               record ids + first band entry; primitive id 2t+k keeps submission order
+ *                               (k = 1, the second triangle of a near-clipped input, lives in prims2)
  *   bands[...]         16 B     TALL primitives only (more than two tile heights), per tile row: span-walk
  *                               state (x0, x1) on entering the row band + tile columns touched there
  *   tile_count[Nt]     u32      per-tile list length (atomic cursor; the raster CTA re-zeroes it)
@@ -93,7 +94,8 @@ struct DrawParams
 	int32_t first; uint32_t count, ntri, n_shade;
 	/* scratch */
 	float4* clip; float2* clip_xy; float* vary; uint32_t nvf; uint32_t clip_vid_base;
-	Prim* prims; BandEntry* bands; uint32_t cap_bands;
+	Prim* prims; Prim* prims2;  /* primitive 2t at prims[t], 2t+1 (second triangle of a near-clipped input) at prims2[t] */
+	BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
 	Counters* ctr;
 	const float* lut255;        /* byte / 255.0f (swgl.c:2116, 3434-3437), computed once on the device */

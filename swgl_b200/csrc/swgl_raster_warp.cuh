@@ -159,7 +159,7 @@ __device__ __forceinline__ void wt_load8(const DrawParams& P, const ClearParams&
 template <int FS>
 __device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, float px, float py)
 {
-	const Prim* q = P.prims + pid;
+	const Prim* q = prim_at(P, pid);
 	BaryConst k;
 	bary_setup(q->v[0], q->v[1], q->v[2], k);
 	FragIn fi;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			for (int r = 0; r < WT_H; r++) sp[r] = 0u;
 			if (lane < nb)
 			{
-				const Prim* q = P.prims + pid;
+				const Prim* q = prim_at(P, pid);
 				const float4 a = q->v[0], b = q->v[1], c = q->v[2];
 				const uint32_t band = q->band;
 				TriWalk w;
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				if (y_out >= y_in)
 				{
 					fast = prim_fast_ok(a, b, c) ? 1u : 0u;
-					prim_consts(a, b, c, q->vid[0], q->vid[1], q->vid[2], pid, &T.pc[lane * PC_VEC4]);
+					const uint32_t vid0 = q->vid[0], vid1 = q->vid[1], vid2 = q->vid[2];
+					prim_consts(a, b, c, vid0, vid1, vid2, pid, &T.pc[lane * PC_VEC4]);
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				                                     : (base + 32u + lane < n_list ? sorted[base + 32u + lane] : 0xffffffffu);
 				if (nxt != 0xffffffffu)
 				{
-					const Prim* q = P.prims + nxt;
+					const Prim* q = prim_at(P, nxt);
 					asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
 					asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)q + 32));
 				}
@@ -394,31 +395,6 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				/* lanes on the same pixel commit in lane order; the match is issued before the arithmetic
 				 * it does not depend on */
 				const uint32_t peers = __match_any_sync(0xffffffffu, pix);
-				/* the varyings of the fast shader shapes are requested before the weights are computed */
-				float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va, vc = va;
-				if (FS != SWFS_GENERIC && active)
-				{
-					const float4 ids = pc[5];
-					const float* pa = P.vary + (size_t)__float_as_uint(ids.x) * P.nvf + P.fs_slot;
-					const float* pb = P.vary + (size_t)__float_as_uint(ids.y) * P.nvf + P.fs_slot;
-					const float* pv = P.vary + (size_t)__float_as_uint(ids.z) * P.nvf + P.fs_slot;
-					if (FS == SWFS_VARYING)
-					{
-						if (vary_vec4) { va = __ldg((const float4*)pa); vb = __ldg((const float4*)pb); vc = __ldg((const float4*)pv); }
-						else
-						{
-							va = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
-							vb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
-							vc = make_float4(__ldg(pv), __ldg(pv + 1), __ldg(pv + 2), __ldg(pv + 3));
-						}
-					}
-					else
-					{
-						va.x = __ldg(pa + P.fs_swz_u); va.y = __ldg(pa + P.fs_swz_v);
-						vb.x = __ldg(pb + P.fs_swz_u); vb.y = __ldg(pb + P.fs_swz_v);
-						vc.x = __ldg(pv + P.fs_swz_u); vc.y = __ldg(pv + P.fs_swz_v);
-					}
-				}
 				bool pending = active;
 				float z = 0.0f;
 				float4 col = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -429,7 +405,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					const float px = (float)(tile_x0 + (int)lx), py = (float)(band_last_y - (int)r);
 					if (!(frag_weights_fast(pc, px, py, u, v, w, z) && ((e >> 26) & 1u)))
 					{
-						const Prim* q = P.prims + __float_as_uint(pc[5].w);
+						const Prim* q = prim_at(P, __float_as_uint(pc[5].w));
 						const float4 s4 = frag_weights_slow(q->v[0], q->v[1], q->v[2], px, py);
 						u = s4.x; v = s4.y; w = s4.z; z = s4.w;
 					}
@@ -439,6 +415,30 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					const float cur = T.depth[pix];
 					if (cur == 0.0f || cur >= z)
 					{
+						float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va, vc = va;
+						if (FS != SWFS_GENERIC)
+						{
+							const float4 ids = pc[5];
+							const float* pa = P.vary + (size_t)__float_as_uint(ids.x) * P.nvf + P.fs_slot;
+							const float* pb = P.vary + (size_t)__float_as_uint(ids.y) * P.nvf + P.fs_slot;
+							const float* pv = P.vary + (size_t)__float_as_uint(ids.z) * P.nvf + P.fs_slot;
+							if (FS == SWFS_VARYING)
+							{
+								if (vary_vec4) { va = __ldg((const float4*)pa); vb = __ldg((const float4*)pb); vc = __ldg((const float4*)pv); }
+								else
+								{
+									va = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
+									vb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+									vc = make_float4(__ldg(pv), __ldg(pv + 1), __ldg(pv + 2), __ldg(pv + 3));
+								}
+							}
+							else
+							{
+								va.x = __ldg(pa + P.fs_swz_u); va.y = __ldg(pa + P.fs_swz_v);
+								vb.x = __ldg(pb + P.fs_swz_u); vb.y = __ldg(pb + P.fs_swz_v);
+								vc.x = __ldg(pv + P.fs_swz_u); vc.y = __ldg(pv + P.fs_swz_v);
+							}
+						}
 						if (FS == SWFS_VARYING)      /* InterpolateLinearEx (swgl.c:3270-3297) */
 							col = make_float4(va.x * u + vb.x * v + vc.x * w, va.y * u + vb.y * v + vc.y * w,
 							                  va.z * u + vb.z * v + vc.z * w, va.w * u + vb.w * v + vc.w * w);
