@@ -12,7 +12,8 @@ import os
 from . import gl as G
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswgl_b200.so")
+# SWGL_B200_LIB: development override (A/B of two builds on one GPU box, tools/ab_lib.py)
+LIB_PATH = os.environ.get("SWGL_B200_LIB") or os.path.join(HERE, "libswgl_b200.so")
 
 
 class swglStats(C.Structure):

@@ -94,7 +94,7 @@ struct swgldev_ctx
 	int last_raster_path;
 
 	/* options */
-	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror;
+	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
 	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
 	int64_t selftest_mismatches;
@@ -311,6 +311,66 @@ __device__ __forceinline__ Prim* prim_at(const DrawParams& P, uint32_t pid)
 	return ((pid & 1u) ? P.prims2 : P.prims) + (pid >> 1);
 }
 
+/* The three snapped vertices of input triangle t and their varying records: stream positions 3t,
+ * 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611), through the element buffer
+ * for glDrawElements; an index past the shaded range reads as a zero clip-space vertex. */
+__device__ __forceinline__ void tri_vertices(const DrawParams& P, uint32_t t, float4& p0, float4& p1, float4& p2,
+                                             uint32_t& s0, uint32_t& s1, uint32_t& s2)
+{
+	s0 = 3u * t; s1 = s0 + 1u; s2 = s0 + 2u;
+	if (P.ibo)
+	{
+		const unsigned long long at = (unsigned long long)(long long)P.first + s0;
+		s0 = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
+		s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
+		s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
+	}
+	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
+	p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
+	p2 = (s2 < P.n_shade) ? P.clip[s2] : to_screen(zero, P);
+}
+
+/* A tile-list entry is (primitive id << 1) | has_record.  Short, unclipped primitives of a draw that
+ * goes to the warp rasteriser have no record: the consumer gathers the three vertices through the
+ * element buffer again (the per-vertex data is shared by the neighbouring triangles and stays in
+ * cache) instead of the set-up kernel writing 64 bytes per triangle. */
+/* Same, as three vertex addresses: the vertex loads and everything behind them are shared by both
+ * kinds of entry.  A record-less entry always has its three indices inside the shaded range (the
+ * set-up kernel writes a record otherwise). */
+struct PrimRef { const float4* a; const float4* b; const float4* c; uint32_t vid0, vid1, vid2, band; };
+__device__ __forceinline__ PrimRef prim_ref(const DrawParams& P, uint32_t entry)
+{
+	PrimRef r;
+	if (entry & 1u)
+	{
+		const Prim* q = prim_at(P, entry >> 1);
+		const uint4 m = *(const uint4*)q->vid;
+		r.a = q->v; r.b = q->v + 1; r.c = q->v + 2;
+		r.vid0 = m.x; r.vid1 = m.y; r.vid2 = m.z; r.band = m.w;
+		return r;
+	}
+	const uint32_t s = 3u * (entry >> 2);
+	r.vid0 = s; r.vid1 = s + 1u; r.vid2 = s + 2u;
+	if (P.ibo)
+	{
+		const uint32_t* ix = P.ibo + ((unsigned long long)(long long)P.first + s);
+		r.vid0 = __ldg(ix); r.vid1 = __ldg(ix + 1); r.vid2 = __ldg(ix + 2);
+	}
+	r.a = P.clip + r.vid0; r.b = P.clip + r.vid1; r.c = P.clip + r.vid2;
+	r.band = 0xffffffffu;
+	return r;
+}
+
+__device__ __forceinline__ Prim load_prim(const DrawParams& P, uint32_t entry)
+{
+	if (entry & 1u) return *prim_at(P, entry >> 1);
+	Prim r;
+	tri_vertices(P, entry >> 2, r.v[0], r.v[1], r.v[2], r.vid[0], r.vid[1], r.vid[2]);
+	r.band = 0xffffffffu;
+	return r;
+}
+
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
 __device__ __forceinline__ bool owns_tile_row(const DrawParams& P, uint32_t tr)
 {
@@ -341,10 +401,10 @@ __device__ __forceinline__ void lerp_vary(const DrawParams& P, uint32_t dst, uin
 
 
 /* list slot for primitive `pid` in `tile`, from the tile's atomic cursor */
-__device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, uint32_t pid)
+__device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, uint32_t entry)
 {
 	const uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
-	if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = pid;
+	if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = entry;
 	else atomicOr(&P.ctr->overflow, 1u);
 }
 
@@ -358,7 +418,8 @@ __device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, u
 template <bool INLINE_INSERT>
 __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t pid, float4 a, float4 b, float4 c,
                                                    uint32_t va, uint32_t vb, uint32_t vc,
-                                                   uint32_t& tr_top, uint32_t& pk0, uint32_t& pk1, uint32_t& pk2)
+                                                   uint32_t& tr_top, uint32_t& pk0, uint32_t& pk1, uint32_t& pk2,
+                                                   uint32_t& rec_band, bool& rec_pending)
 {
 	/* a, b, c are already ((float)X, (float)Y, z_clip, w_clip) */
 	TriWalk w;
@@ -380,11 +441,18 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		band = atomicAdd(&P.ctr->band_cursor, nb);
 		if ((unsigned long long)band + nb > (unsigned long long)P.cap_bands) { atomicOr(&P.ctr->overflow, 2u); return 0u; }
 	}
-	Prim* out = prim_at(P, pid);
-	if (!(P.diag & 2u))
+	/* list entry; the record is written unless the consumer can gather the primitive itself */
+	const bool has_record = INLINE_INSERT || band != 0xffffffffu || !P.lean_prims || va >= P.n_shade || vb >= P.n_shade || vc >= P.n_shade;
+	const uint32_t entry = (pid << 1) | (has_record ? 1u : 0u);
+	if (has_record)
 	{
-		out->v[0] = a; out->v[1] = b; out->v[2] = c;
-		*(uint4*)out->vid = make_uint4(va, vb, vc, band);
+		if (INLINE_INSERT)
+		{
+			Prim* out = prim_at(P, pid);
+			out->v[0] = a; out->v[1] = b; out->v[2] = c;
+			*(uint4*)out->vid = make_uint4(va, vb, vc, band);
+		}
+		else { rec_band = band; rec_pending = true; }   /* the caller stores the warp's records together */
 	}
 	tr_top = tr_hi;
 
@@ -433,13 +501,13 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 			if (band != 0xffffffffu)
 			{
 				BandEntry e;
-				e.x0 = ex0; e.x1 = ex1; e.prim = pid;
+				e.x0 = ex0; e.x1 = ex1; e.prim = entry;
 				e.cols = hit ? (c0 | (c1 << 11) | (tr << 22)) : 0xffffffffu;
 				P.bands[band + (tr_hi - tr)] = e;
 			}
 			else if (hit)
 			{
-				if (INLINE_INSERT) { for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, pid); }
+				if (INLINE_INSERT) { for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry); }
 				else
 				{
 					const uint32_t pk = c0 | (c1 << 16);
@@ -462,7 +530,8 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 	for (int j = 0; j < 3; j++) { if ((in_mask >> j) & 1u) in_idx[n_in++] = j; else out_idx[n_out++] = j; }
 	const uint32_t new0 = P.clip_vid_base + 2u * t, new1 = new0 + 1u;
 	float t0, t1;
-	uint32_t d0, d1, d2, d3;
+	uint32_t d0, d1, d2, d3, d4;
+	bool d5;
 	if (n_in == 1)
 	{
 		const int a = in_idx[0];
@@ -470,7 +539,7 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 		const float4 q2 = near_intersect(p[a], p[out_idx[1]], t1);
 		lerp_vary(P, new0, sid[a], sid[out_idx[0]], t0);
 		lerp_vary(P, new1, sid[a], sid[out_idx[1]], t1);
-		return setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(q1, P), to_screen(q2, P), sid[a], new0, new1, d0, d1, d2, d3);
+		return setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(q1, P), to_screen(q2, P), sid[a], new0, new1, d0, d1, d2, d3, d4, d5);
 	}
 	if (n_in == 2)
 	{
@@ -480,37 +549,29 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 		lerp_vary(P, new0, sid[a], sid[o], t0);
 		lerp_vary(P, new1, sid[b], sid[o], t1);
 		const float4 sq0 = to_screen(q0, P);
-		uint32_t live = setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(p[b], P), sq0, sid[a], sid[b], new0, d0, d1, d2, d3);
-		live += setup_one_prim<true>(P, 2u * t + 1u, to_screen(p[b], P), sq0, to_screen(q1, P), sid[b], new0, new1, d0, d1, d2, d3);
+		uint32_t live = setup_one_prim<true>(P, 2u * t, to_screen(p[a], P), to_screen(p[b], P), sq0, sid[a], sid[b], new0, d0, d1, d2, d3, d4, d5);
+		live += setup_one_prim<true>(P, 2u * t + 1u, to_screen(p[b], P), sq0, to_screen(q1, P), sid[b], new0, new1, d0, d1, d2, d3, d4, d5);
 		return live;
 	}
 	return 0u;
 }
 
-__global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawParams P)
+__global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ DrawParams P)
 {
+	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	uint32_t live = 0, tr_top = 0, pk[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu };
+	uint32_t rec_band = 0xffffffffu;
+	bool rec_pending = false;
+	float4 p0, p1, p2;
+	uint32_t s0 = 0, s1 = 0, s2 = 0;
 	if (t < P.ntri)
 	{
-		/* stream positions 3t, 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611) */
-		uint32_t s0 = 3u * t, s1 = s0 + 1u, s2 = s0 + 2u;
-		if (P.ibo)
-		{
-			const unsigned long long at = (unsigned long long)(long long)P.first + s0;
-			s0 = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
-			s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
-			s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
-		}
-		const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		/* an index past the shaded range reads as a zero clip-space vertex */
-		const float4 p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
-		const float4 p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
-		const float4 p2 = (s2 < P.n_shade) ? P.clip[s2] : to_screen(zero, P);
+		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
 		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
 		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
-		if (in_mask == 7u) live = setup_one_prim<false>(P, 2u * t, p0, p1, p2, s0, s1, s2, tr_top, pk[0], pk[1], pk[2]);
+		if (in_mask == 7u) live = setup_one_prim<false>(P, 2u * t, p0, p1, p2, s0, s1, s2, tr_top, pk[0], pk[1], pk[2], rec_band, rec_pending);
 		else if (in_mask != 0u)
 		{
 			/* back to clip space for the intersection arithmetic */
@@ -522,11 +583,34 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 		}
 	}
 
+	/* The unclipped primitives' 64-byte records leave as whole 512-byte runs: a thread storing its own
+	 * record would touch 32 half-written sectors per store instruction. */
+	{
+		const uint32_t recs = __ballot_sync(0xffffffffu, rec_pending);
+		if (recs)
+		{
+			if (rec_pending)
+			{
+				stage[wid][lane][0] = p0; stage[wid][lane][1] = p1; stage[wid][lane][2] = p2;
+				stage[wid][lane][3] = make_float4(__uint_as_float(s0), __uint_as_float(s1), __uint_as_float(s2), __uint_as_float(rec_band));
+			}
+			__syncwarp();
+			float4* out = (float4*)(P.prims + (t - lane));
+#pragma unroll
+			for (uint32_t i = 0; i < 4; i++)
+			{
+				const uint32_t idx = i * 32u + lane, rec = idx >> 2;
+				if ((recs >> rec) & 1u) out[idx] = stage[wid][rec][idx & 3u];
+			}
+		}
+	}
+
 	/* warp-aggregated list insertion for the short, unclipped primitives: neighbouring triangles
 	 * mostly land in the same tile, so lanes that want the same tile share one atomicAdd.  The first
 	 * tile column of all three bands goes first, with the three atomics in flight together (the
 	 * round trip of an atomic that returns a value is what this kernel waits for); further columns
 	 * (primitives that straddle a tile boundary in x) follow one at a time. */
+	const uint32_t short_entry = (4u * t) | (rec_pending ? 1u : 0u);   /* primitive 2t; pk[] is only set for short unclipped ones */
 	uint32_t base[3], peers[3], tile[3];
 #pragma unroll
 	for (int k = 0; k < 3; k++)
@@ -544,7 +628,7 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 		if (pk[k] != 0xffffffffu)
 		{
 			const uint32_t slot = b0 + (uint32_t)__popc(peers[k] & ((1u << lane) - 1u));
-			if (slot < P.bin_cap) P.pairs[(size_t)tile[k] * P.bin_cap + slot] = 2u * t;
+			if (slot < P.bin_cap) P.pairs[(size_t)tile[k] * P.bin_cap + slot] = short_entry;
 			else atomicOr(&P.ctr->overflow, 1u);
 		}
 	}
@@ -566,7 +650,7 @@ __global__ void __launch_bounds__(128) k_setup_bin(const __grid_constant__ DrawP
 			if (have)
 			{
 				const uint32_t slot = bs + (uint32_t)__popc(pr & ((1u << lane) - 1u));
-				if (slot < P.bin_cap) P.pairs[(size_t)tl * P.bin_cap + slot] = 2u * t;
+				if (slot < P.bin_cap) P.pairs[(size_t)tl * P.bin_cap + slot] = short_entry;
 				else atomicOr(&P.ctr->overflow, 1u);
 			}
 			cx++;
@@ -830,7 +914,7 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 			if (tid < nb)
 			{
 				const uint32_t pid = ids[base + tid];
-				const Prim pr = *prim_at(P, pid);
+				const Prim pr = load_prim(P, pid);
 				TriWalk w;
 				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
 				const int y_in = max(w.ys, band_first_y);
@@ -1095,7 +1179,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->lut255 = nullptr;
@@ -1536,11 +1620,17 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	}
 	const uint32_t ntri = (d->count + 2u) / 3u;
 	if (ntri == 0 || d->vh == 0) return flush_clear(c);
+	if (ntri > (1u << 30))
+	{   /* list entries are (primitive id << 1) | flag with primitive id = 2t + k */
+		set_err(c, "draw skipped: more than 2^30 triangles in one draw", cudaSuccess);
+		return flush_clear(c);
+	}
 
 	DrawParams P;
 	if (fill_common_params(c, d, P)) return flush_clear(c);
 	P.ntri = ntri;
 	P.th_shift = th_shift_of(raster_path_for(c, ntri));
+	P.lean_prims = (c->opt_lean_prims && P.th_shift == WT_H_SHIFT) ? 1u : 0u;
 	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;
@@ -1779,6 +1869,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "count_fragments")) c->opt_count_fragments = (int)value;
 	else if (!strcmp(name, "raster_path")) c->opt_raster_path = (int)value;
 	else if (!strcmp(name, "diag")) c->opt_diag = (int)value;
+	else if (!strcmp(name, "lean_prims")) c->opt_lean_prims = (int)value;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)

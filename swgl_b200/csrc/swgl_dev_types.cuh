@@ -96,7 +96,8 @@ struct DrawParams
 	float4* clip; float2* clip_xy; float* vary; uint32_t nvf; uint32_t clip_vid_base;
 	Prim* prims; Prim* prims2;  /* primitive 2t at prims[t], 2t+1 (second triangle of a near-clipped input) at prims2[t] */
 	BandEntry* bands; uint32_t cap_bands;
-	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile */
+	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile; entries are (id << 1) | has_record */
+	uint32_t lean_prims;        /* short unclipped primitives have no record (warp rasteriser draws) */
 	Counters* ctr;
 	const float* lut255;        /* byte / 255.0f (swgl.c:2116, 3434-3437), computed once on the device */
 	uint32_t* winner;           /* GL_POINTS: per-pixel index+1 of the last point submitted to it (0 = none) */

@@ -246,8 +246,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 			if (tid < nb)
 			{
 				const uint32_t pid = S.ids[tid];
-				pr.v[0] = prim_at(P, pid)->v[0]; pr.v[1] = prim_at(P, pid)->v[1]; pr.v[2] = prim_at(P, pid)->v[2];
-				pr.band = prim_at(P, pid)->band;
+				pr = load_prim(P, pid);
 				tri_setup(pr.v[0], pr.v[1], pr.v[2], P, w);
 				y_in = max(w.ys, band_first_y);
 				y_out = min(w.ye - 1, band_last_y);
@@ -358,7 +357,8 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 					const uint32_t r = S.row0[lo] + rl;
 					pix = r * SWGL_TILE + lx;
 					pid = S.ids[lo];
-					const Prim* q = prim_at(P, pid);
+					const Prim qv = load_prim(P, pid);
+					const Prim* q = &qv;
 					const float4 a = q->v[0], b = q->v[1], c = q->v[2];
 					BaryConst k;
 					bary_setup(a, b, c, k);
@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 							if (!shaded_early)
 							{
 								/* rare: recompute the weights (same arithmetic, same bits) and shade now */
-								const Prim* q_prim = prim_at(P, pid);
+								const Prim qv2 = load_prim(P, pid);
+								const Prim* q_prim = &qv2;
 								BaryConst k;
 								bary_setup(q_prim->v[0], q_prim->v[1], q_prim->v[2], k);
 								FragIn fi;

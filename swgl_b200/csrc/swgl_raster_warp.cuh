@@ -154,12 +154,25 @@ __device__ __forceinline__ void wt_load8(const DrawParams& P, const ClearParams&
 		}
 }
 
+/* frag_weights() for a fragment outside the fast domain, from the list entry: out of line, the hot loop
+ * only carries the call */
+__device__ __noinline__ float4 weights_slow_entry(const DrawParams& P, uint32_t entry, float px, float py)
+{
+	const Prim q = load_prim(P, entry);
+	BaryConst k;
+	bary_setup(q.v[0], q.v[1], q.v[2], k);
+	float4 r;
+	frag_weights(k, px, py, r.x, r.y, r.z, r.w);
+	return r;
+}
+
 /* Shading of a fragment that failed the depth test before the ordered part and passes in it (an
  * earlier fragment of the same step stored exactly 0.0 = "empty"): rare, kept out of the hot loop. */
 template <int FS>
 __device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, float px, float py)
 {
-	const Prim* q = prim_at(P, pid);
+	const Prim qv = load_prim(P, pid);
+	const Prim* q = &qv;
 	BaryConst k;
 	bary_setup(q->v[0], q->v[1], q->v[2], k);
 	FragIn fi;
@@ -288,17 +301,16 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			for (int r = 0; r < WT_H; r++) sp[r] = 0u;
 			if (lane < nb)
 			{
-				const Prim* q = prim_at(P, pid);
-				const float4 a = q->v[0], b = q->v[1], c = q->v[2];
-				const uint32_t band = q->band;
+				const PrimRef q = prim_ref(P, pid);
+				const float4 a = *q.a, b = *q.b, c = *q.c;
+				const uint32_t band = q.band;
 				TriWalk w;
 				tri_setup(a, b, c, P, w);
 				const int y_in = max(w.ys, band_first_y), y_out = min(w.ye - 1, band_last_y);
 				if (y_out >= y_in)
 				{
 					fast = prim_fast_ok(a, b, c) ? 1u : 0u;
-					const uint32_t vid0 = q->vid[0], vid1 = q->vid[1], vid2 = q->vid[2];
-					prim_consts(a, b, c, vid0, vid1, vid2, pid, &T.pc[lane * PC_VEC4]);
+					prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane * PC_VEC4]);
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
@@ -370,9 +382,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			{
 				const uint32_t nxt = (n_list <= 128) ? (base == 0 ? xs1 : base == 32 ? xs2 : xs3)
 				                                     : (base + 32u + lane < n_list ? sorted[base + 32u + lane] : 0xffffffffu);
-				if (nxt != 0xffffffffu)
+				if (nxt != 0xffffffffu && (nxt & 1u))
 				{
-					const Prim* q = prim_at(P, nxt);
+					const Prim* q = prim_at(P, nxt >> 1);
 					asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
 					asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)q + 32));
 				}
@@ -405,8 +417,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					const float px = (float)(tile_x0 + (int)lx), py = (float)(band_last_y - (int)r);
 					if (!(frag_weights_fast(pc, px, py, u, v, w, z) && ((e >> 26) & 1u)))
 					{
-						const Prim* q = prim_at(P, __float_as_uint(pc[5].w));
-						const float4 s4 = frag_weights_slow(q->v[0], q->v[1], q->v[2], px, py);
+						const float4 s4 = weights_slow_entry(P, __float_as_uint(pc[5].w), px, py);
 						u = s4.x; v = s4.y; w = s4.z; z = s4.w;
 					}
 					/* the fragment shader does not read the framebuffer: run it before the ordered
