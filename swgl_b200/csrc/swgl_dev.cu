@@ -422,11 +422,11 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
                                                    uint32_t& rec_band, bool& rec_pending)
 {
 	/* a, b, c are already ((float)X, (float)Y, z_clip, w_clip) */
-	TriWalk w;
-	if (!tri_setup(a, b, c, P, w)) return 0u;
+	TriSorted ts;
+	if (!tri_rows(a, b, c, P, ts)) return 0u;
 	/* rows [ys, ye) -> storage rows ytop-ys (bottom-most) .. ytop-ye+1: tile rows hi..lo */
-	const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> P.th_shift;
-	const uint32_t tr_lo = (uint32_t)(P.ytop - (w.ye - 1)) >> P.th_shift;
+	const uint32_t tr_hi = (uint32_t)(P.ytop - ts.ys) >> P.th_shift;
+	const uint32_t tr_lo = (uint32_t)(P.ytop - (ts.ye - 1)) >> P.th_shift;
 	if (P.n_ranks > 1)
 	{
 		/* sort-first: a primitive none of whose tile rows belong to this rank is dropped here */
@@ -435,7 +435,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		if (!mine) return 0u;
 	}
 	uint32_t band = 0xffffffffu;
-	if (w.ye - w.ys > (2 << P.th_shift))     /* short = at most two tile heights = at most 3 tile rows */
+	if (ts.ye - ts.ys > (2 << P.th_shift))     /* short = at most two tile heights = at most 3 tile rows */
 	{
 		const uint32_t nb = tr_hi - tr_lo + 1u;
 		band = atomicAdd(&P.ctr->band_cursor, nb);
@@ -479,7 +479,9 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		}
 	}
 
-	/* the walk (swgl.c:3356-3361, 3466-3471) */
+	/* the walk (swgl.c:3356-3361, 3466-3471); the slopes are only needed from here on */
+	TriWalk w;
+	tri_slopes(ts, w);
 	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
 	bool switched = false;
 	uint32_t tr = tr_hi;
@@ -504,6 +506,8 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 				e.x0 = ex0; e.x1 = ex1; e.prim = entry;
 				e.cols = hit ? (c0 | (c1 << 11) | (tr << 22)) : 0xffffffffu;
 				P.bands[band + (tr_hi - tr)] = e;
+				/* few tall primitives in a mesh of small ones: inserted here, k_bin_tall is not launched */
+				if (P.inline_tall && hit) for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);
 			}
 			else if (hit)
 			{
@@ -569,6 +573,8 @@ __global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ Dr
 	if (t < P.ntri)
 	{
 		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
+		if (P.diag & 4u) { if (p0.x + p1.x + p2.x == 12345.678f) P.ctr->prims_out = 1; return; }
+		if (P.diag & 16u) { if (s0 + s1 + s2 == 0x12345678u) P.ctr->prims_out = 1; return; }
 		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
 		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
 		if (in_mask == 7u) live = setup_one_prim<false>(P, 2u * t, p0, p1, p2, s0, s1, s2, tr_top, pk[0], pk[1], pk[2], rec_band, rec_pending);
@@ -1518,7 +1524,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	STAGE(1);
 	k_setup_bin<<<(P.ntri + 127u) / 128u, 128, 0, c->stream>>>(P);
-	k_bin_tall<<<148, 256, 0, c->stream>>>(P);
+	if (!P.inline_tall) k_bin_tall<<<148, 256, 0, c->stream>>>(P);
 	STAGE(2);
 	/* overflow flags are final once set-up is done: snapshot them on the side stream so the next
 	 * draw can be queued while this one is still rasterising */
@@ -1533,7 +1539,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	else launch_raster<SWFS_GENERIC>(c, P);
 	STAGE(3);
 #undef STAGE
-	c->n_launches += 4;
+	c->n_launches += P.inline_tall ? 3 : 4;
 	CK(cudaGetLastError());
 	if (timing)
 	{
@@ -1631,6 +1637,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.ntri = ntri;
 	P.th_shift = th_shift_of(raster_path_for(c, ntri));
 	P.lean_prims = (c->opt_lean_prims && P.th_shift == WT_H_SHIFT) ? 1u : 0u;
+	P.inline_tall = (P.th_shift == WT_H_SHIFT) ? 1u : 0u;
 	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;

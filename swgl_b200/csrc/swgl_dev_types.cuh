@@ -98,6 +98,7 @@ struct DrawParams
 	BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile; entries are (id << 1) | has_record */
 	uint32_t lean_prims;        /* short unclipped primitives have no record (warp rasteriser draws) */
+	uint32_t inline_tall;       /* tall primitives are inserted by the set-up kernel itself (no k_bin_tall launch) */
 	Counters* ctr;
 	const float* lut255;        /* byte / 255.0f (swgl.c:2116, 3434-3437), computed once on the device */
 	uint32_t* winner;           /* GL_POINTS: per-pixel index+1 of the last point submitted to it (0 = none) */

@@ -8,7 +8,7 @@ KSTART = next(i for i, l in enumerate(src) if "k_raster_warp(const __grid_consta
 def find(marker):
     return next(i + 1 for i, l in enumerate(src) if i >= KSTART and marker in l)
 marks = [("helpers(sort32,merge,stage)", 1), ("prologue+stage", find("k_raster_warp(const __grid_constant__")), ("sort", find("ascending primitive id = submission order ----")),
-         ("phaseA", find("for (uint32_t base = 0; base < n_list; base += 32)")), ("scan+spans", find("---- S: one exclusive scan")),
+         ("phaseA", find("for (uint32_t base = 0; base < n_list; base += take)")), ("scan+spans", find("---- S: one exclusive scan")),
          ("locate", find("---- phase B: lane = fragment")), ("fetch+weights", find("FragIn fi;")),
          ("shade", find("the fragment shader does not read the framebuffer")), ("commit", find("---- ordered commit")),
          ("writeback", find("---- write-back"))]
