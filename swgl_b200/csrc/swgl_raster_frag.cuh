@@ -79,7 +79,9 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_t
 		if (lane == (FRAG_THREADS / 32) - 1) *total_out = s;
 	}
 	__syncthreads();
-	return (wid ? warp_tmp[wid - 1] : 0u) + (x - v);
+	const uint32_t before = wid ? warp_tmp[wid - 1] : 0u;
+	__syncthreads();            /* the next scan rewrites warp_tmp: every warp must have read its prefix first */
+	return before + (x - v);
 }
 
 /* blend with the destination unpacked through the byte/255.0f table */
@@ -166,12 +168,12 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 			const uint32_t s = r * SWGL_TILE + (q << 2);
 			*(uint4*)&S.color[s] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
 			*(float4*)&S.depth[s] = make_float4(d4[0], d4[1], d4[2], d4[3]);
-			*(uint4*)&S.owner[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+			*(uint4*)&S.owner[s] = make_uint4(0u, 0u, 0u, 0u);
 		}
 		S.lut[tid] = (float)tid / 255.0f;
 	}
 
-	uint32_t n_tested = 0, n_shaded = 0;
+	uint32_t n_tested = 0, n_shaded = 0, commit_round = 0;
 
 	if (n_list > 0)
 	{
@@ -385,9 +387,13 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 				/* ordered commit */
 				while (__syncthreads_or(pending ? 1 : 0))
 				{
-					if (pending) atomicMin(&S.owner[pix], tid);
+					/* the lowest thread index of this round wins the pixel: keys carry the round number in
+					 * their high bits, so a slot never has to be released (a stale key always loses) */
+					commit_round++;
+					const uint32_t key = (commit_round << 9) | (511u - tid);
+					if (pending) atomicMax(&S.owner[pix], key);
 					__syncthreads();
-					if (pending && S.owner[pix] == tid)
+					if (pending && S.owner[pix] == key)
 					{
 						const float cur = S.depth[pix];
 						if (cur == 0.0f || cur >= z)     /* swgl.c:3387 */
@@ -414,7 +420,6 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 							S.color[pix] = blend_pack_lut(o.x, o.y, o.z, o.w, S.color[pix], S.lut);
 							tile_dirty = true;
 						}
-						S.owner[pix] = 0xffffffffu;
 						pending = false;
 					}
 				}
