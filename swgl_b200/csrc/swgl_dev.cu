@@ -435,7 +435,12 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		if (!mine) return 0u;
 	}
 	uint32_t band = 0xffffffffu;
-	if (ts.ye - ts.ys > (2 << P.th_shift))     /* short = at most two tile heights = at most 3 tile rows */
+	/* short = at most two tile heights = at most 3 tile rows; narrow = the three vertices within 64 columns.
+	 * Unclipped primitives that are not both get band entries: their tile lists are filled per tile row
+	 * (k_bin_tall, or inline for the few of a small-triangle draw) instead of one list at a time here. */
+	const float xmin = fminf(fminf(a.x, b.x), c.x), xmax = fmaxf(fmaxf(a.x, b.x), c.x);
+	const bool narrow = xmin >= -32768.0f && xmax <= 32768.0f && xmax - xmin <= 64.0f;
+	if (ts.ye - ts.ys > (2 << P.th_shift) || (!INLINE_INSERT && !narrow))
 	{
 		const uint32_t nb = tr_hi - tr_lo + 1u;
 		band = atomicAdd(&P.ctr->band_cursor, nb);
@@ -463,8 +468,6 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		 * walk's x0/x1 stay inside the hull of the vertex columns up to the rounding of at most two tile
 		 * heights of slope additions: with |x| <= 2^15 and an extent of at most 64 pixels that is below
 		 * 0.25 pixel, so [xmin - 1, xmax + 1] covers every pixel row_span() can produce. */
-		const float xmin = fminf(fminf(a.x, b.x), c.x), xmax = fmaxf(fmaxf(a.x, b.x), c.x);
-		if (xmin >= -32768.0f && xmax <= 32768.0f && xmax - xmin <= 64.0f)
 		{
 			const int lo = max((int)xmin - 1, max((int)P.fvx, 0));
 			const int hi = min((int)xmax + 1, min((int)ceilf(P.xlimit), (int)P.W) - 1);
@@ -486,6 +489,43 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 	bool switched = false;
 	uint32_t tr = tr_hi;
 	int band_last_y = P.ytop - (int)(tr << P.th_shift);   /* last raster row of this band */
+	if (band != 0xffffffffu && !P.inline_tall)
+	{
+		/* Tall primitive of a big-triangle draw: only the serial part of the walk runs here -- the two
+		 * float recurrences, sampled on entering every tile row.  The spans of each tile row (and the
+		 * tile columns they touch) are worked out by k_bin_tall, one thread per (primitive, tile row),
+		 * so a triangle hundreds of rows tall does not keep one thread busy for all of them.
+		 *
+		 * The state on entering row y is c0x (+) s0, (y - ys) times, and for the second edge c0x (+) s1
+		 * up to the switch row, c1x (+) s2 after it (the switch happens after the first row y with
+		 * (float)y + 1 >= c1y has been drawn, swgl.c:3466-3471); the additions are replayed one by one,
+		 * in the reference's order, in loops that carry nothing else. */
+		const int c1yi = (w.c1y >= 2147483648.0f) ? 0x7fffffff : (w.c1y <= -2147483648.0f) ? (int)0x80000000 : (int)w.c1y;
+		const int ysw = (c1yi <= w.ys) ? w.ys : c1yi - 1;            /* row after which the switch happens */
+		int y = w.ys;
+		for (;;)
+		{
+			BandEntry e;
+			e.x0 = x0; e.x1 = x1; e.prim = entry;
+			e.cols = (owns_tile_row(P, tr) && !(P.diag & 1u)) ? tr : 0xffffffffu;
+			P.bands[band + (tr_hi - tr)] = e;
+			const int y_end = min(band_last_y, w.ye - 1);             /* last row of this band */
+			if (y_end >= w.ye - 1) break;
+			/* advance to the state on entering row y_end + 1 */
+			int n = y_end - y + 1;
+			if (ysw >= y && ysw <= y_end)
+			{
+				for (int i = ysw - y; i > 0; i--) { x0 += w.s0; x1 += s1; }
+				s1 = w.s2; x1 = w.c1x;
+				x0 += w.s0; x1 += s1;
+				n = y_end - ysw;
+			}
+			for (int i = n; i > 0; i--) { x0 += w.s0; x1 += s1; }
+			y = y_end + 1;
+			tr--; band_last_y += 1 << P.th_shift;
+		}
+		return 1u;
+	}
 	float ex0 = x0, ex1 = x1;
 	int cmin = 0x7fffffff, cmax = -1;
 	for (int y = w.ys; y < w.ye; y++)
@@ -560,7 +600,7 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 	return 0u;
 }
 
-__global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ DrawParams P)
+__global__ void __launch_bounds__(128, 6) k_setup_bin(const __grid_constant__ DrawParams P)
 {
 	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,20 +708,6 @@ __global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ Dr
 	if (lane == 0 && live) atomicAdd(&P.ctr->prims_out, live);
 }
 
-/* ---- list insertion for tall primitives: one thread per band entry ---- */
-__global__ void __launch_bounds__(256) k_bin_tall(const __grid_constant__ DrawParams P)
-{
-	if (P.ctr->overflow & 2u) return;
-	const uint32_t total = P.ctr->band_cursor;
-	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
-	{
-		const BandEntry be = P.bands[e];
-		if (be.cols == 0xffffffffu) continue;
-		const uint32_t c0 = be.cols & 0x7ffu, c1 = (be.cols >> 11) & 0x7ffu, tr = be.cols >> 22;
-		for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, be.prim);
-	}
-}
-
 /* ---- fragment shading for the three shader shapes ---- */
 struct FragIn
 {
@@ -773,6 +799,50 @@ __device__ __forceinline__ void walk_to_row(const DrawParams& P, const TriWalk& 
 	{
 		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
 		x0 += w.s0; x1 += s1;
+	}
+}
+
+/* ---- tall or wide primitives of big-triangle draws: one WARP per (primitive, tile row) band entry.
+ * Lane r replays the walk from the state the set-up kernel sampled on entering the band to its own
+ * row (swgl.c:3356-3361, 3466-3471; at most 31 additions), the warp reduces the columns the spans
+ * touch, and the lanes then insert the primitive into one tile list each ---- */
+__global__ void __launch_bounds__(256) k_bin_tall(const __grid_constant__ DrawParams P)
+{
+	if (P.ctr->overflow & 2u) return;
+	const uint32_t total = P.ctr->band_cursor;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += warps)
+	{
+		const BandEntry be = P.bands[e];
+		if (be.cols == 0xffffffffu) continue;
+		const uint32_t tr = be.cols;
+		const Prim* q = prim_at(P, be.prim >> 1);       /* these primitives always have a record */
+		TriWalk w;
+		if (!tri_setup(q->v[0], q->v[1], q->v[2], P, w)) continue;
+		const int band_last_y = P.ytop - (int)(tr << P.th_shift);
+		const int y_in = max(w.ys, band_last_y - ((1 << P.th_shift) - 1)), y_out = min(w.ye - 1, band_last_y);
+		float x0, x1, s1;
+		bool switched;
+		walk_to_row(P, w, q->band, tr, y_in, x0, x1, s1, switched);
+		int cmin = 0x7fffffff, cmax = -1;
+		const int y = y_in + (int)lane;
+		if (y <= y_out)
+		{
+			for (int yy = y_in; yy < y; yy++)
+			{
+				if (!switched && (float)yy + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+				x0 += w.s0; x1 += s1;
+			}
+			int xa, xb;
+			row_span(x0, x1, P, xa, xb);
+			if (xa < xb) { cmin = xa; cmax = xb - 1; }
+		}
+		cmin = __reduce_min_sync(0xffffffffu, cmin);
+		cmax = __reduce_max_sync(0xffffffffu, cmax);
+		if (cmax < 0) continue;
+		const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
+		for (uint32_t cx = c0 + lane; cx <= c1; cx += 32) bin_insert(P, tr * P.tiles_x + cx, be.prim);
 	}
 }
 
@@ -1524,7 +1594,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	STAGE(1);
 	k_setup_bin<<<(P.ntri + 127u) / 128u, 128, 0, c->stream>>>(P);
-	if (!P.inline_tall) k_bin_tall<<<148, 256, 0, c->stream>>>(P);
+	if (!P.inline_tall) k_bin_tall<<<148 * 2, 256, 0, c->stream>>>(P);
 	STAGE(2);
 	/* overflow flags are final once set-up is done: snapshot them on the side stream so the next
 	 * draw can be queued while this one is still rasterising */
