@@ -408,6 +408,89 @@ __device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, u
 	else atomicOr(&P.ctr->overflow, 1u);
 }
 
+/* The walk of a primitive that is not binned by its vertex extent (swgl.c:3356-3361, 3466-3471): tall,
+ * wide or near-clipped ones.  Out of line and by value: the common path of k_setup_bin (short narrow
+ * primitives of a fine mesh) keeps none of this in registers; the slopes are only needed here. */
+__device__ __noinline__ void setup_walk(const DrawParams& P, float c0x, float c0y, float c1x, float c1y, float c2x, float c2y,
+                                        int ys, int ye, uint32_t band, uint32_t entry, uint32_t tr_hi)
+{
+	TriSorted ts;
+	ts.c0x = c0x; ts.c0y = c0y; ts.c1x = c1x; ts.c1y = c1y; ts.c2x = c2x; ts.c2y = c2y; ts.ys = ys; ts.ye = ye;
+	TriWalk w;
+	tri_slopes(ts, w);
+	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
+	bool switched = false;
+	uint32_t tr = tr_hi;
+	int band_last_y = P.ytop - (int)(tr << P.th_shift);   /* last raster row of this band */
+	if (band != 0xffffffffu && !P.inline_tall)
+	{
+		/* Tall primitive of a big-triangle draw: only the serial part of the walk runs here -- the two
+		 * float recurrences, sampled on entering every tile row.  The spans of each tile row (and the
+		 * tile columns they touch) are worked out by k_bin_tall, one thread per (primitive, tile row),
+		 * so a triangle hundreds of rows tall does not keep one thread busy for all of them.
+		 *
+		 * The state on entering row y is c0x (+) s0, (y - ys) times, and for the second edge c0x (+) s1
+		 * up to the switch row, c1x (+) s2 after it (the switch happens after the first row y with
+		 * (float)y + 1 >= c1y has been drawn, swgl.c:3466-3471); the additions are replayed one by one,
+		 * in the reference's order, in loops that carry nothing else. */
+		const int c1yi = (w.c1y >= 2147483648.0f) ? 0x7fffffff : (w.c1y <= -2147483648.0f) ? (int)0x80000000 : (int)w.c1y;
+		const int ysw = (c1yi <= w.ys) ? w.ys : c1yi - 1;            /* row after which the switch happens */
+		int y = w.ys;
+		for (;;)
+		{
+			BandEntry e;
+			e.x0 = x0; e.x1 = x1; e.prim = entry;
+			e.cols = (owns_tile_row(P, tr) && !(P.diag & 1u)) ? tr : 0xffffffffu;
+			P.bands[band + (tr_hi - tr)] = e;
+			const int y_end = min(band_last_y, w.ye - 1);             /* last row of this band */
+			if (y_end >= w.ye - 1) break;
+			/* advance to the state on entering row y_end + 1 */
+			int n = y_end - y + 1;
+			if (ysw >= y && ysw <= y_end)
+			{
+				for (int i = ysw - y; i > 0; i--) { x0 += w.s0; x1 += s1; }
+				s1 = w.s2; x1 = w.c1x;
+				x0 += w.s0; x1 += s1;
+				n = y_end - ysw;
+			}
+			for (int i = n; i > 0; i--) { x0 += w.s0; x1 += s1; }
+			y = y_end + 1;
+			tr--; band_last_y += 1 << P.th_shift;
+		}
+		return;
+	}
+	float ex0 = x0, ex1 = x1;
+	int cmin = 0x7fffffff, cmax = -1;
+	for (int y = w.ys; y < w.ye; y++)
+	{
+		int xa, xb;
+		row_span(x0, x1, P, xa, xb);
+		if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
+		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+		x0 += w.s0; x1 += s1;
+		if (y == band_last_y || y == w.ye - 1)
+		{
+			/* span-exact tile columns of this band */
+			const bool hit = cmax >= 0 && owns_tile_row(P, tr) && !(P.diag & 1u);
+			const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
+			if (band != 0xffffffffu)
+			{
+				BandEntry e;
+				e.x0 = ex0; e.x1 = ex1; e.prim = entry;
+				e.cols = hit ? (c0 | (c1 << 11) | (tr << 22)) : 0xffffffffu;
+				P.bands[band + (tr_hi - tr)] = e;
+				/* few tall primitives in a mesh of small ones: inserted here, k_bin_tall is not launched */
+				if (P.inline_tall && hit) for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);
+			}
+			else if (hit)
+				for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);   /* short near-clipped primitive */
+			tr--; band_last_y += 1 << P.th_shift;
+			ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
+		}
+	}
+}
+
+
 /* One primitive: divide + viewport snap, set-up, span walk.  Returns 1 if the primitive is live
  * (reaches the rasteriser on this rank).
  *   tall (more than two tile heights): one BandEntry per tile row (walk state + tile columns);
@@ -482,87 +565,7 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 		}
 	}
 
-	/* the walk (swgl.c:3356-3361, 3466-3471); the slopes are only needed from here on */
-	TriWalk w;
-	tri_slopes(ts, w);
-	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
-	bool switched = false;
-	uint32_t tr = tr_hi;
-	int band_last_y = P.ytop - (int)(tr << P.th_shift);   /* last raster row of this band */
-	if (band != 0xffffffffu && !P.inline_tall)
-	{
-		/* Tall primitive of a big-triangle draw: only the serial part of the walk runs here -- the two
-		 * float recurrences, sampled on entering every tile row.  The spans of each tile row (and the
-		 * tile columns they touch) are worked out by k_bin_tall, one thread per (primitive, tile row),
-		 * so a triangle hundreds of rows tall does not keep one thread busy for all of them.
-		 *
-		 * The state on entering row y is c0x (+) s0, (y - ys) times, and for the second edge c0x (+) s1
-		 * up to the switch row, c1x (+) s2 after it (the switch happens after the first row y with
-		 * (float)y + 1 >= c1y has been drawn, swgl.c:3466-3471); the additions are replayed one by one,
-		 * in the reference's order, in loops that carry nothing else. */
-		const int c1yi = (w.c1y >= 2147483648.0f) ? 0x7fffffff : (w.c1y <= -2147483648.0f) ? (int)0x80000000 : (int)w.c1y;
-		const int ysw = (c1yi <= w.ys) ? w.ys : c1yi - 1;            /* row after which the switch happens */
-		int y = w.ys;
-		for (;;)
-		{
-			BandEntry e;
-			e.x0 = x0; e.x1 = x1; e.prim = entry;
-			e.cols = (owns_tile_row(P, tr) && !(P.diag & 1u)) ? tr : 0xffffffffu;
-			P.bands[band + (tr_hi - tr)] = e;
-			const int y_end = min(band_last_y, w.ye - 1);             /* last row of this band */
-			if (y_end >= w.ye - 1) break;
-			/* advance to the state on entering row y_end + 1 */
-			int n = y_end - y + 1;
-			if (ysw >= y && ysw <= y_end)
-			{
-				for (int i = ysw - y; i > 0; i--) { x0 += w.s0; x1 += s1; }
-				s1 = w.s2; x1 = w.c1x;
-				x0 += w.s0; x1 += s1;
-				n = y_end - ysw;
-			}
-			for (int i = n; i > 0; i--) { x0 += w.s0; x1 += s1; }
-			y = y_end + 1;
-			tr--; band_last_y += 1 << P.th_shift;
-		}
-		return 1u;
-	}
-	float ex0 = x0, ex1 = x1;
-	int cmin = 0x7fffffff, cmax = -1;
-	for (int y = w.ys; y < w.ye; y++)
-	{
-		int xa, xb;
-		row_span(x0, x1, P, xa, xb);
-		if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
-		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-		x0 += w.s0; x1 += s1;
-		if (y == band_last_y || y == w.ye - 1)
-		{
-			/* span-exact tile columns of this band */
-			const bool hit = cmax >= 0 && owns_tile_row(P, tr) && !(P.diag & 1u);
-			const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
-			if (band != 0xffffffffu)
-			{
-				BandEntry e;
-				e.x0 = ex0; e.x1 = ex1; e.prim = entry;
-				e.cols = hit ? (c0 | (c1 << 11) | (tr << 22)) : 0xffffffffu;
-				P.bands[band + (tr_hi - tr)] = e;
-				/* few tall primitives in a mesh of small ones: inserted here, k_bin_tall is not launched */
-				if (P.inline_tall && hit) for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);
-			}
-			else if (hit)
-			{
-				if (INLINE_INSERT) { for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry); }
-				else
-				{
-					const uint32_t pk = c0 | (c1 << 16);
-					const uint32_t bi = tr_hi - tr;
-					if (bi == 0) pk0 = pk; else if (bi == 1) pk1 = pk; else pk2 = pk;
-				}
-			}
-			tr--; band_last_y += 1 << P.th_shift;
-			ex0 = x0; ex1 = x1; cmin = 0x7fffffff; cmax = -1;
-		}
-	}
+	setup_walk(P, ts.c0x, ts.c0y, ts.c1x, ts.c1y, ts.c2x, ts.c2y, ts.ys, ts.ye, band, entry, tr_hi);
 	return 1u;
 }
 

@@ -69,3 +69,18 @@ def test_no_clear_and_partial_draw(restatement, reference):
     c2, d2 = reference.render(scene, clear=False, fill=(0x80402010, 0.0), first=30, count=600)
     cmp = O.compare(c1, d1, c2, d2)
     assert cmp["depth_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+
+
+def test_restatement_matches_fullsize_golden_c2(restatement):
+    """BASELINE config 2 at full size (1080p, 100,352 triangles): the restatement against the hashes the
+    compiled reference produced (tests/golden/fullsize_kats.json); also the survey's K3 values."""
+    with open(os.path.join(os.path.dirname(GOLDEN), "fullsize_kats.json")) as f:
+        full = json.load(f)
+    k = full["C2"]
+    col, dep, stats = restatement.render(S.config(2))
+    assert f"{restatement.fnv(col):016x}" == k["color_fnv"] == "9254eae11a6abc99"   # SURVEY.md appendix C, K3
+    assert f"{restatement.fnv(dep):016x}" == k["depth_fnv"]
+    assert int((dep.view(np.uint32) != 0).sum()) == k["covered"] == 1538557
+    assert stats["tested"] == k["tested"] and stats["shaded"] == k["shaded"]
+    assert full["C4"]["color_fnv"] == "56d0d4e1a9cd44f1" and full["C4"]["covered"] == 5202381   # K4
+    assert full["C5"]["covered"] == 20795225                                                    # K5

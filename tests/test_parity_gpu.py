@@ -138,3 +138,38 @@ def test_tall_triangles_use_band_entries(gpu_api, restatement):
         col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
         assert err == "" and stats["bands"] > 0
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
+
+
+def test_wide_and_tall_primitives_inside_a_fine_mesh(gpu_api, restatement):
+    """A draw of small triangles binds its few tall (> 2 tile heights) or wide (> 64 columns) primitives
+    inline in the set-up kernel (band entries, no k_bin_tall launch); all others have no primitive
+    record at all.  Mix both kinds into one indexed draw, in the middle of the submission order."""
+    mesh = S.grid_mesh(70, 512, 384, alpha=0.6)
+    rng = np.random.default_rng(7)
+    extra = []
+    for k in range(12):
+        cx, cy = rng.uniform(-0.7, 0.7, 2)
+        if k % 3 == 0:      # wide and flat
+            tri = [(cx - 0.9, cy, 0.5), (cx + 0.9, cy + 0.01, 0.4), (cx, cy + 0.03, 0.6)]
+        elif k % 3 == 1:    # tall and thin
+            tri = [(cx, cy - 0.9, 0.3), (cx + 0.02, cy + 0.9, 0.5), (cx - 0.02, cy + 0.5, 0.7)]
+        else:               # big
+            tri = [(cx - 0.5, cy - 0.4, 0.2), (cx + 0.6, cy - 0.3, 0.8), (cx, cy + 0.7, 0.5)]
+        for (x, y, z) in tri:
+            w = rng.uniform(1.0, 1.5)
+            extra.append([x * w, y * w, z, w, *rng.random(3), 0.6])
+    extra = np.asarray(extra, dtype=np.float32)
+    base = len(mesh.vertices)
+    mesh.vertices = np.ascontiguousarray(np.concatenate([mesh.vertices, extra]))
+    idx = mesh.indices
+    half = (len(idx) // 6) * 3
+    mesh.indices = np.ascontiguousarray(np.concatenate(
+        [idx[:half], np.arange(base, base + len(extra), dtype=np.uint32), idx[half:]]))
+    mesh.name += "_mixed"
+    rc, rd, rstats = restatement.render(mesh)
+    for path in (3, 2):
+        col, dep, stats, err = gpu_render(gpu_api, mesh, options={"raster_path": path})
+        assert err == ""
+        assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
+        assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
+        assert stats["bands"] > 0
