@@ -235,6 +235,11 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	__syncwarp();
 
 	uint32_t n_tested = 0, n_shaded = 0;
+	/* column limits of a row's span folded per tile (fast row walk of phase A): viewport, framebuffer
+	 * and tile; exact when the viewport limits are integers a float holds exactly */
+	const bool tile_fast = fabsf(P.fvx) < 16777216.0f && P.xlimit < 16777216.0f;
+	const int t_lo = max(max((int)P.fvx, 0), tile_x0);
+	const int t_hi = min(min((int)ceilf(P.xlimit), (int)P.W), tile_x0 + SWGL_TILE);
 	/* packed vec4 varying records can be fetched with 128-bit loads */
 	const bool vary_vec4 = ((P.nvf | P.fs_slot) & 3u) == 0 && (((uintptr_t)P.vary) & 15u) == 0;
 	if (n_list > 0)
@@ -314,24 +319,53 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
-#pragma unroll
-					for (int r = WT_H - 1; r >= 0; r--)
+					if (fast && tile_fast)
 					{
-						const int y = band_last_y - r;
-						if (y >= y_in && y <= y_out)
+						/* Bounded coordinates (prim_fast_ok) and a viewport whose limits are exact in float: the
+						 * row's span is trunc(lo) and ceil(hi) clamped once against limits folded per tile --
+						 * trunc and ceil are monotonic, so they commute with the reference's MAX/MIN against
+						 * the viewport (swgl.c:3358-3361) -- and the edge switch is an integer compare. */
+						const int c1yi = (int)w.c1y;
+#pragma unroll
+						for (int r = WT_H - 1; r >= 0; r--)
 						{
-							int xa, xb;
-							row_span(x0, x1, P, xa, xb);
-							xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
-							xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
-							if (xb > xa)
+							const int y = band_last_y - r;
+							if (y >= y_in && y <= y_out)
 							{
-								sp[r] = (uint32_t)xa | ((uint32_t)(xb - xa) << 8);
-								cnt += (uint32_t)(xb - xa);
-								nsp++;
+								const int xa = min(max(__float2int_rz(fminf(x0, x1)), t_lo), tile_x0 + SWGL_TILE);
+								const int xb = max(min(__float2int_ru(fmaxf(x0, x1)), t_hi), tile_x0);
+								if (xb > xa)
+								{
+									sp[r] = (uint32_t)(xa - tile_x0) | ((uint32_t)(xb - xa) << 8);
+									cnt += (uint32_t)(xb - xa);
+									nsp++;
+								}
+								if (!switched && y + 1 >= c1yi) { switched = true; s1 = w.s2; x1 = w.c1x; }
+								x0 += w.s0; x1 += s1;
 							}
-							if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-							x0 += w.s0; x1 += s1;
+						}
+					}
+					else
+					{
+#pragma unroll
+						for (int r = WT_H - 1; r >= 0; r--)
+						{
+							const int y = band_last_y - r;
+							if (y >= y_in && y <= y_out)
+							{
+								int xa, xb;
+								row_span(x0, x1, P, xa, xb);
+								xa = min(max(xa, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
+								xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
+								if (xb > xa)
+								{
+									sp[r] = (uint32_t)xa | ((uint32_t)(xb - xa) << 8);
+									cnt += (uint32_t)(xb - xa);
+									nsp++;
+								}
+								if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+								x0 += w.s0; x1 += s1;
+							}
 						}
 					}
 				}
