@@ -248,6 +248,7 @@ template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawParams P)
 {
 	uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	cudaTriggerProgrammaticLaunchCompletion();   /* the set-up kernel may start loading its indices */
 	if (v == 0 && blockIdx.x == 0)
 	{
 		/* per-draw counters: this kernel is the first of the draw */
@@ -314,6 +315,7 @@ __device__ __forceinline__ Prim* prim_at(const DrawParams& P, uint32_t pid)
 /* The three snapped vertices of input triangle t and their varying records: stream positions 3t,
  * 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611), through the element buffer
  * for glDrawElements; an index past the shaded range reads as a zero clip-space vertex. */
+template <bool WAIT_FOR_VERTEX_KERNEL = false>
 __device__ __forceinline__ void tri_vertices(const DrawParams& P, uint32_t t, float4& p0, float4& p1, float4& p2,
                                              uint32_t& s0, uint32_t& s1, uint32_t& s2)
 {
@@ -325,6 +327,9 @@ __device__ __forceinline__ void tri_vertices(const DrawParams& P, uint32_t t, fl
 		s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
 		s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
 	}
+	/* k_setup_bin is launched while the vertex kernel drains (programmatic dependent launch): the
+	 * indices above do not depend on it, everything below does */
+	if (WAIT_FOR_VERTEX_KERNEL) cudaGridDependencySynchronize();
 	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
 	p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
@@ -615,7 +620,7 @@ __global__ void __launch_bounds__(128, 6) k_setup_bin(const __grid_constant__ Dr
 	uint32_t s0 = 0, s1 = 0, s2 = 0;
 	if (t < P.ntri)
 	{
-		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
+		tri_vertices<true>(P, t, p0, p1, p2, s0, s1, s2);
 		if (P.diag & 4u) { if (p0.x + p1.x + p2.x == 12345.678f) P.ctr->prims_out = 1; return; }
 		if (P.diag & 16u) { if (s0 + s1 + s2 == 0x12345678u) P.ctr->prims_out = 1; return; }
 		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
@@ -1601,7 +1606,18 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
 	STAGE(1);
-	k_setup_bin<<<(P.ntri + 127u) / 128u, 128, 0, c->stream>>>(P);
+	{
+		/* programmatic dependent launch: the set-up CTAs become resident while the vertex kernel's last
+		 * wave runs and wait (cudaGridDependencySynchronize) only before they read its output */
+		cudaLaunchConfig_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.gridDim = dim3((P.ntri + 127u) / 128u); cfg.blockDim = dim3(128); cfg.stream = c->stream;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = timing ? 0 : 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		CK(cudaLaunchKernelEx(&cfg, k_setup_bin, P));
+	}
 	if (!P.inline_tall) k_bin_tall<<<148 * 2, 256, 0, c->stream>>>(P);
 	STAGE(2);
 	/* overflow flags are final once set-up is done: snapshot them on the side stream so the next
