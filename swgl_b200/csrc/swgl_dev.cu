@@ -1242,7 +1242,7 @@ static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 	dim3 grid(P.tiles_x, P.tiles_y);
 	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
 	else if (path == 2) k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
-	else k_raster_warp<FS><<<(P.tiles_x * P.tiles_y + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, 0, c->stream>>>(P);
+	else k_raster_warp<FS><<<(P.tiles_x * P.owned_tile_rows + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, 0, c->stream>>>(P);
 }
 
 extern "C" {
@@ -1730,9 +1730,18 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (fill_common_params(c, d, P)) return flush_clear(c);
 	P.ntri = ntri;
 	P.th_shift = th_shift_of(raster_path_for(c, ntri));
+	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
+	P.owned_tile_rows = P.tiles_y;
+	if (P.n_ranks > 1 && P.th_shift == WT_H_SHIFT)
+	{
+		const uint32_t per = P.band_rows << (5u - WT_H_SHIFT), cycle = per * P.n_ranks;
+		/* whole ownership cycles, plus what the last partial cycle leaves to this rank */
+		const uint32_t full = P.tiles_y / cycle, rest = P.tiles_y % cycle;
+		const uint32_t lo = P.rank * per;
+		P.owned_tile_rows = full * per + (rest > lo ? (rest - lo < per ? rest - lo : per) : 0u);
+	}
 	P.lean_prims = (c->opt_lean_prims && P.th_shift == WT_H_SHIFT) ? 1u : 0u;
 	P.inline_tall = (P.th_shift == WT_H_SHIFT && small_triangle_draw(c, ntri)) ? 1u : 0u;
-	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;
 

@@ -88,6 +88,7 @@ struct DrawParams
 	uint32_t tiles_x, tiles_y;  /* tiles are 32 wide and (1 << th_shift) tall: 32 (CTA kernels) or 8 (warp kernel) */
 	uint32_t th_shift;
 	uint32_t rank, n_ranks, band_rows;   /* sort-first bands, in units of 32 framebuffer rows */
+	uint32_t owned_tile_rows;   /* warp rasteriser: tile rows of this rank (= tiles_y on one GPU) */
 	/* geometry */
 	const uint8_t* vbo; unsigned long long vbo_bytes;
 	const uint32_t* ibo; unsigned long long ibo_count;

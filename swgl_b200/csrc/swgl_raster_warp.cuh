@@ -194,11 +194,19 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
 	__syncthreads();            /* the only block-level barrier */
 
-	const uint32_t n_tiles = P.tiles_x * P.tiles_y;
-	const uint32_t tile = blockIdx.x * WT_WARPS + wid;
-	if (tile >= n_tiles) return;
-	const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-	if (!owns_tile_row(P, ty)) return;
+	/* the grid covers the tile rows this rank owns: owned row i -> tile row (sort-first bands of
+	 * band_rows x 32 framebuffer rows dealt round-robin, see owns_tile_row) */
+	const uint32_t slot = blockIdx.x * WT_WARPS + wid;
+	if (slot >= P.tiles_x * P.owned_tile_rows) return;
+	const uint32_t tx = slot % P.tiles_x;
+	uint32_t ty = slot / P.tiles_x;
+	if (P.n_ranks > 1)
+	{
+		const uint32_t per = P.band_rows << (5u - WT_H_SHIFT);      /* tile rows per ownership group */
+		ty = ((ty / per) * P.n_ranks + P.rank) * per + ty % per;
+		if (ty >= P.tiles_y || !owns_tile_row(P, ty)) return;
+	}
+	const uint32_t tile = ty * P.tiles_x + tx;
 	WarpTile& T = S.w[wid];
 
 	/* list length; the cursor is re-armed for the next draw */
