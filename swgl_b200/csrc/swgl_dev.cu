@@ -608,7 +608,7 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 	return 0u;
 }
 
-__global__ void __launch_bounds__(128, 6) k_setup_bin(const __grid_constant__ DrawParams P)
+__global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ DrawParams P)
 {
 	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
