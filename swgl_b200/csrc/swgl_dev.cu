@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t n, uint64_t 
 		const uint64_t r0 = splitmix64(s), r1 = splitmix64(s), r2 = splitmix64(s);
 		const uint32_t cls = (uint32_t)(i % 3u);
 		/* dividend exponent range, divisor exponent range per domain (see frag_weights_fast) */
-		const int xlo = cls == 0 ? 0 : cls == 1 ? -82 : -98, xhi = cls == 0 ? 61 : cls == 1 ? 62 : 78;
-		const int ylo = cls == 0 ? 0 : cls == 1 ? -16 : -30, yhi = cls == 0 ? 58 : cls == 1 ? 15 : 23;
+		const int xlo = cls == 0 ? 0 : cls == 1 ? -86 : -100, xhi = cls == 0 ? 63 : cls == 1 ? 64 : 78;
+		const int ylo = cls == 0 ? 0 : cls == 1 ? -14 : -30, yhi = cls == 0 ? 62 : cls == 1 ? 13 : 23;
 		const int ex = xlo + (int)((r2 >> 8) % (uint64_t)(xhi - xlo + 1));
 		const int ey = ylo + (int)((r2 >> 24) % (uint64_t)(yhi - ylo + 1));
 		float x = test_float((uint32_t)(r2 & 1u), ex, test_mantissa(r0), cls == 0);

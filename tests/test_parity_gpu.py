@@ -173,3 +173,16 @@ def test_wide_and_tall_primitives_inside_a_fine_mesh(gpu_api, restatement):
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
         assert stats["bands"] > 0
+
+
+@pytest.mark.parametrize("width", [9000, 16000, 40000])
+def test_wide_framebuffers_around_the_fast_division_domain(gpu_api, restatement, width):
+    """The shared-reciprocal division is used for primitives whose snapped coordinates stay within
+    2^14 (swgl_dev_math.cuh); wider framebuffers put some or all primitives outside and on the plain
+    `/` path.  Both must give the reference's bits."""
+    scene = S.random_triangles(400, width, 96, seed=width, extent=0.05, alpha=0.5, near_cross=True, centre_range=1.1)
+    rc, rd, rstats = restatement.render(scene)
+    col, dep, stats, err = gpu_render(gpu_api, scene, indexed=False)
+    assert err == ""
+    assert_bit_exact(O.compare(col, dep, rc, rd), scene.name)
+    assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
