@@ -2,20 +2,27 @@
  * swgl_dev.cu -- CUDA device layer of libswgl_b200.so (sm_100a), behind the C ABI of
  * include/swgl_dev.h.  It replaces the reference's per-draw work:
  *
- *   k_clear          glClear                       swgl.c:3183-3214
- *   k_vertex         attribute fetch + VS + varying capture, one thread per vertex
- *                                                  swgl.c:3618-3666
- *   k_setup_bin      near clip, divide + viewport snap, triangle set-up, span walk and
- *                    single-pass binning into fixed-capacity per-tile lists, one thread per
- *                    input triangle         swgl.c:499-697, 3683-3692, 3316-3361, 3466-3471
- *   k_raster         per-tile: sort the list by primitive id, then per pixel Barycentric,
- *                    perspective correction, depth test, varying interpolation, fragment
- *                    shader, blend, pack; 128-bit write-back
- *                                                  swgl.c:3358-3462
+ *   k_clear          glClear when it cannot be fused into the next draw      swgl.c:3183-3214
+ *   k_vertex         attribute fetch + VS + varying capture + divide/viewport snap, one thread
+ *                    per vertex                          swgl.c:3618-3666, 3683-3692
+ *   k_setup_bin      near clip, triangle set-up and single-pass binning into fixed-capacity
+ *                    per-tile lists, one thread per input triangle; short narrow primitives are
+ *                    binned by vertex extent, tall/wide ones get per-tile-row walk states
+ *                                                        swgl.c:499-697, 3316-3361, 3466-3471
+ *   k_bin_tall       spans and list insertion of tall/wide primitives, a warp per tile row
+ *                    (big-triangle draws only)            swgl.c:3356-3361
+ *   k_raster_warp    (swgl_raster_warp.cuh) per tile: sort the list by primitive id, replay the
+ *                    span walk, then per fragment Barycentric, perspective correction, depth
+ *                    test, varying interpolation, fragment shader, blend, pack; fused clear;
+ *                    128-bit write-back                  swgl.c:3358-3462
+ *   k_raster_frag, k_raster   two older CTA-per-32x32-tile rasterisers, kept as independent
+ *                    cross-checks (raster_path option)
+ *   k_points_claim / k_points_write   GL_POINTS            swgl.c:3496-3608
  *
  * Order dependence: the reference's depth test (LEQUAL with 0.0f = empty) and its
  * unconditional blend make the result depend on submission order, so every pixel sees its
- * fragments in ascending primitive id -- lists are sorted, and one thread owns a pixel.
+ * fragments in ascending primitive id -- lists are sorted, and same-pixel fragments of a step
+ * commit in lane order.
  *
  * No tensor cores: the path is scan/scatter shaped, not a contraction.  Compiled with
  * -fmad=false (see swgl_dev_math.cuh).  There is no CPU fallback anywhere in this file.
@@ -1198,9 +1205,8 @@ __global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ Dr
 #include "swgl_raster_warp.cuh"
 
 /* raster_path: 1 = pixel-owner CTA per 32x32 tile (k_raster), 2 = fragment-parallel CTA per 32x32
- * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = choose per draw: meshes of
- * small triangles (few framebuffer pixels per submitted triangle) go to the warp kernel, everything
- * else to the fragment-parallel CTA kernel.  All three produce identical bits. */
+ * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = default = the warp kernel for
+ * every draw.  All three produce identical bits. */
 /* every draw gets a serial and an event; the allocations it reads remember the serial */
 static int stamp_draw(swgldev_ctx* c, const swgldev_draw* d)
 {

@@ -4,8 +4,9 @@
  * One WARP owns one 32x8 tile from its list to its write-back; there is no block-level barrier
  * anywhere after the prologue.  Per batch of 32 primitives (ascending primitive id):
  *
- *   A  lane = primitive: replay the span walk over the tile's 8 rows (swgl.c:3356-3361,
- *      3466-3471); each row's span stays in a register, fragment and span counts too;
+ *   A  lane = primitive: gather the primitive, replay the span walk over the tile's 8 rows
+ *      (swgl.c:3356-3361, 3466-3471) with each row's span in a register, and stage the constants
+ *      of the fragment arithmetic (prim_consts) in shared memory;
  *   S  one warp shuffle scan of both counts, then every non-empty span is appended to the batch's
  *      span list (first fragment, row, first column, primitive lane) and its first fragment is
  *      marked in a bit map (one word per step of phase B);
