@@ -83,11 +83,14 @@ int swglReadPixelsRGBA8(void* dst);
 /* The current frame as a binary PPM (P6); 0 on success. */
 int swglWritePPM(const char* path);
 
-/* Tuning / test hooks: "raster_path" (0 per-draw choice, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
+/* Tuning / test hooks: "raster_path" (0 default = 3, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
  * "host_mirror" (1 adaptive: when glGetFramePtr follows every draw or two, the raster kernels also store finished
  * tiles into the pinned frame mirror and glGetFramePtr only waits; 0 always copy; 2 whenever the mirror is in sync),
  * "fuse_clear" (0/1), "count_fragments" (0/1), "stage_timing" (0/1: per-kernel CUDA-event timing, synchronous);
- * "bin_cap" (per-tile list capacity, test hook), "bin_limit_bytes";
+ * "bin_cap" (per-tile list capacity, test hook), "bin_limit_bytes", "lean_prims" (1 default: short narrow unclipped
+ * primitives have no record, the rasteriser gathers them through the element buffer; 0 writes a record for every one),
+ * "selftest_division" (value = number of operand pairs: runs the device self-test of the shared-reciprocal division
+ * against `/`, mismatches in "selftest_division_mismatches");
  * read-only: "wt_draws", "mirror_synced", "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
  * "stage_draws", "tile_size", "device". */
 void swglSetOption(const char* name, int64_t value);
