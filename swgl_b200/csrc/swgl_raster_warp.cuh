@@ -232,14 +232,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	/* ---- stage the tile: lane -> row lane/4, 8 pixels from column 8*(lane%4) ---- */
 	bool dirty = false;
 	{
-		uint32_t c8[8]; float d8[8];
 		const int r = (int)(lane >> 2), px0 = tile_x0 + (int)((lane & 3u) << 3);
-		wt_load8(P, cp, tile_r0 + r, px0, c8, d8, dirty);
 		const uint32_t s = (uint32_t)r * SWGL_TILE + ((lane & 3u) << 3);
-		*(uint4*)&T.color[s] = make_uint4(c8[0], c8[1], c8[2], c8[3]);
-		*(uint4*)&T.color[s + 4] = make_uint4(c8[4], c8[5], c8[6], c8[7]);
-		*(float4*)&T.depth[s] = make_float4(d8[0], d8[1], d8[2], d8[3]);
-		*(float4*)&T.depth[s + 4] = make_float4(d8[4], d8[5], d8[6], d8[7]);
+		/* the usual frame: a pending clear of both attachments covers the whole tile, nothing is read */
+		const bool whole = (cp.flags & 3u) == 3u && cp.x0 <= tile_x0 && cp.x1 >= tile_x0 + SWGL_TILE
+		                   && cp.y0 <= tile_r0 && cp.y1 >= tile_r0 + WT_H
+		                   && tile_x0 + SWGL_TILE <= (int)P.W && tile_r0 + WT_H <= (int)P.H;
+		if (whole)
+		{
+			const uint4 cw = make_uint4(cp.word, cp.word, cp.word, cp.word);
+			const float4 dz = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			*(uint4*)&T.color[s] = cw; *(uint4*)&T.color[s + 4] = cw;
+			*(float4*)&T.depth[s] = dz; *(float4*)&T.depth[s + 4] = dz;
+			dirty = true;
+		}
+		else
+		{
+			uint32_t c8[8]; float d8[8];
+			wt_load8(P, cp, tile_r0 + r, px0, c8, d8, dirty);
+			*(uint4*)&T.color[s] = make_uint4(c8[0], c8[1], c8[2], c8[3]);
+			*(uint4*)&T.color[s + 4] = make_uint4(c8[4], c8[5], c8[6], c8[7]);
+			*(float4*)&T.depth[s] = make_float4(d8[0], d8[1], d8[2], d8[3]);
+			*(float4*)&T.depth[s + 4] = make_float4(d8[4], d8[5], d8[6], d8[7]);
+		}
 	}
 	__syncwarp();
 
