@@ -1248,7 +1248,7 @@ static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 	dim3 grid(P.tiles_x, P.tiles_y);
 	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
 	else if (path == 2) k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
-	else k_raster_warp<FS><<<(P.tiles_x * P.owned_tile_rows + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, 0, c->stream>>>(P);
+	else k_raster_warp<FS><<<dim3((P.tiles_x + WT_WARPS - 1) / WT_WARPS, P.owned_tile_rows ? P.owned_tile_rows : 1), WT_WARPS * 32, 0, c->stream>>>(P);
 }
 
 extern "C" {

@@ -197,10 +197,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 
 	/* the grid covers the tile rows this rank owns: owned row i -> tile row (sort-first bands of
 	 * band_rows x 32 framebuffer rows dealt round-robin, see owns_tile_row) */
-	const uint32_t slot = blockIdx.x * WT_WARPS + wid;
-	if (slot >= P.tiles_x * P.owned_tile_rows) return;
-	const uint32_t tx = slot % P.tiles_x;
-	uint32_t ty = slot / P.tiles_x;
+	const uint32_t tx = blockIdx.x * WT_WARPS + wid;     /* grid: (tile columns / WT_WARPS, owned tile rows) */
+	if (tx >= P.tiles_x) return;
+	uint32_t ty = blockIdx.y;
 	if (P.n_ranks > 1)
 	{
 		const uint32_t per = P.band_rows << (5u - WT_H_SHIFT);      /* tile rows per ownership group */
