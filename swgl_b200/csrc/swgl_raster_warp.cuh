@@ -31,7 +31,7 @@
 #define WT_MAX_SPANS (32 * WT_H)             /* (primitive, row) spans of one batch */
 #define WT_MAX_FRAGS 2048                     /* fragments of one batch: a batch that would produce more is cut short */
 
-/* span entry: first fragment (13 bits) | tile row << 13 | first column << 16 | primitive lane << 21
+/* span entry: (tile pixel of the first fragment - its fragment index) mod 2^13 | primitive lane << 21
  * | primitive passed prim_fast_ok() << 26 */
 #define WT_PC_WORDS (4 * PC_VEC4)             /* per-primitive constants of phase B, see prim_consts() */
 struct WarpTile
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				pid = sr == 0 ? v0 : sr == 1 ? v1 : sr == 2 ? v2 : sr == 3 ? v3 : 0xffffffffu;
 			}
 			uint32_t cnt = 0, nsp = 0, fast = 0;
+			uint32_t row0 = 0;                   /* tile row of the primitive's first walked row; sp[k] is the span k rows above it */
 			uint32_t sp[WT_H];
 #pragma unroll
 			for (int r = 0; r < WT_H; r++) sp[r] = 0u;
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				const int y_in = max(w.ys, band_first_y), y_out = min(w.ye - 1, band_last_y);
 				if (y_out >= y_in)
 				{
+					row0 = (uint32_t)(band_last_y - y_in);
 					fast = prim_fast_ok(a, b, c) ? 1u : 0u;
 					prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane * PC_VEC4]);
 					float x0, x1, s1;
@@ -350,16 +352,16 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 						 * the viewport (swgl.c:3358-3361) -- and the edge switch is an integer compare. */
 						const int c1yi = (int)w.c1y;
 #pragma unroll
-						for (int r = WT_H - 1; r >= 0; r--)
+						for (int k = 0; k < WT_H; k++)
 						{
-							const int y = band_last_y - r;
-							if (y >= y_in && y <= y_out)
+							const int y = y_in + k;
+							if (y <= y_out)
 							{
 								const int xa = min(max(__float2int_rz(fminf(x0, x1)), t_lo), tile_x0 + SWGL_TILE);
 								const int xb = max(min(__float2int_ru(fmaxf(x0, x1)), t_hi), tile_x0);
 								if (xb > xa)
 								{
-									sp[r] = (uint32_t)(xa - tile_x0) | ((uint32_t)(xb - xa) << 8);
+									sp[k] = (uint32_t)(xa - tile_x0) | ((uint32_t)(xb - xa) << 8);
 									cnt += (uint32_t)(xb - xa);
 									nsp++;
 								}
@@ -371,10 +373,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					else
 					{
 #pragma unroll
-						for (int r = WT_H - 1; r >= 0; r--)
+						for (int k = 0; k < WT_H; k++)
 						{
-							const int y = band_last_y - r;
-							if (y >= y_in && y <= y_out)
+							const int y = y_in + k;
+							if (y <= y_out)
 							{
 								int xa, xb;
 								row_span(x0, x1, P, xa, xb);
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 								xb = min(max(xb, tile_x0), tile_x0 + SWGL_TILE) - tile_x0;
 								if (xb > xa)
 								{
-									sp[r] = (uint32_t)xa | ((uint32_t)(xb - xa) << 8);
+									sp[k] = (uint32_t)xa | ((uint32_t)(xb - xa) << 8);
 									cnt += (uint32_t)(xb - xa);
 									nsp++;
 								}
@@ -420,13 +422,15 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			__syncwarp();
 			{
 				uint32_t run = excl_k & 0xffffu, k = excl_k >> 16;
+				const uint32_t tag = (lane << 21) | (fast << 26);
 #pragma unroll
-				for (int r = 0; r < WT_H; r++)
+				for (int j = 0; j < WT_H; j++)
 				{
-					const uint32_t len = sp[r] >> 8;
+					const uint32_t len = sp[j] >> 8;
 					if (len)
 					{
-						T.u.b.span[k++] = run | ((uint32_t)r << 13) | ((sp[r] & 31u) << 16) | (lane << 21) | (fast << 26);
+						/* low 13 bits: tile pixel of the span's first fragment minus its fragment index (mod 2^13) */
+						T.u.b.span[k++] = (((row0 - (uint32_t)j) * SWGL_TILE + (sp[j] & 31u) - run) & 0x1fffu) | tag;
 						atomicOr(&T.u.b.start_bits[run >> 5], 1u << (run & 31u));
 						run += len;
 					}
@@ -458,9 +462,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & (0xffffffffu >> (31u - lane))) - 1u];
 				spans_before += (uint32_t)__popc(starts);
 				const float4* pc = &T.pc[((e >> 21) & 31u) * PC_VEC4];
-				const uint32_t r = (e >> 13) & 7u;
-				const uint32_t lx = ((e >> 16) & 31u) + (t - (e & 0x1fffu));
-				const uint32_t pix = active ? r * SWGL_TILE + lx : (0x80000000u | lane);
+				const uint32_t tpix = (e + t) & 0x1fffu;         /* pixel of the tile: row * 32 + column */
+				const uint32_t r = tpix >> SWGL_TILE_SHIFT, lx = tpix & (SWGL_TILE - 1u);
+				const uint32_t pix = active ? tpix : (0x80000000u | lane);
 				/* lanes on the same pixel commit in lane order; the match is issued before the arithmetic
 				 * it does not depend on */
 				const uint32_t peers = __match_any_sync(0xffffffffu, pix);
