@@ -644,6 +644,10 @@ __global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ Dr
 		}
 	}
 
+	/* a warp none of whose primitives is live (sort-first: all in other ranks' bands, or all culled)
+	 * has nothing to store or insert */
+	if (!__any_sync(0xffffffffu, live != 0u)) return;
+
 	/* The unclipped primitives' 64-byte records leave as whole 512-byte runs: a thread storing its own
 	 * record would touch 32 half-written sectors per store instruction. */
 	{
