@@ -83,6 +83,15 @@ int swglReadPixelsRGBA8(void* dst);
 /* The current frame as a binary PPM (P6); 0 on success. */
 int swglWritePPM(const char* path);
 
+/* Page-locked staging memory for the application's vertex / index arrays (the source of glBufferData and
+ * swglBufferRespecify).  write_combined != 0 asks for write-combined pages: the CPU writes them once,
+ * front to back, and never reads them, and host-to-device copies do not have to snoop the CPU caches --
+ * on the boxes measured, freshly written cacheable pinned pages upload at a fraction of the PCIe rate for
+ * the first tens of copies (bench.py's end-to-end step varied 1.27 .. 2.2 ms), write-combined ones at
+ * the full rate from the first.  NULL on failure.  Works without glInit. */
+void* swglHostAlloc(uint64_t bytes, int write_combined);
+void  swglHostFree(void* p);
+
 /* Tuning / test hooks: "raster_path" (0 default = 3, 1 pixel-owner CTA, 2 fragment-parallel CTA, 3 warp per 32x8 tile),
  * "host_mirror" (1 adaptive: when glGetFramePtr follows every draw or two, the raster kernels also store finished
  * tiles into the pinned frame mirror and glGetFramePtr only waits; 0 always copy; 2 whenever the mirror is in sync),

@@ -120,6 +120,9 @@ void         swgldev_free(swgldev_ctx* c, swgldev_ptr p);
 /* largest u32 in an uploaded element buffer (device reduction; the extension glDrawElements
  * shades vertices [0, max] once each) */
 uint32_t     swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
+/* swgldev_upload_overlapped() of element data and swgldev_max_index() of it, with a single wait
+ * (swglBufferRespecify(GL_ELEMENT_ARRAY_BUFFER), the per-frame upload of the end-to-end step). */
+int          swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index);
 
 /* glClear (swgl.c:3183-3214): rectangle is viewport ∩ framebuffer, already resolved. */
 int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,
@@ -142,6 +145,9 @@ uint64_t        swgldev_frame_submit(swgldev_ctx* c);
 const uint32_t* swgldev_frame_wait(swgldev_ctx* c, uint64_t ticket);
 /* colour attachment as bytes R, G, B, A (swizzled on the device) into `dst` (W*H*4 bytes of host memory) */
 int       swgldev_read_rgba8(swgldev_ctx* c, void* dst);
+/* page-locked host memory for upload sources (cudaHostAlloc; write-combined on request); no context needed */
+void*     swgldev_host_alloc(uint64_t bytes, int write_combined);
+void      swgldev_host_free(void* p);
 swgldev_ptr swgldev_color_devptr(swgldev_ctx* c);
 swgldev_ptr swgldev_depth_devptr(swgldev_ctx* c);
 void      swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth); /* whole framebuffer */

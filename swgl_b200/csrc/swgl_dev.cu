@@ -70,6 +70,7 @@ struct swgldev_ctx
 	cudaEvent_t draw_ev[8];
 	uint64_t draw_serial;
 	uint32_t* d_maxidx;
+	uint32_t* h_maxidx;                  /* pinned: a pageable destination sends the 4-byte read-back through the driver's slow staging path */
 	float* lut255;
 	uint32_t draws_since_map;
 	uint32_t* peer_color;
@@ -1281,7 +1282,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
-	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->lut255 = nullptr;
+	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
 	for (int i = 0; i < 8; i++) c->draw_ev[i] = nullptr;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
@@ -1301,6 +1302,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming) == cudaSuccess
 	       && cudaMalloc((void**)&c->d_maxidx, 4) == cudaSuccess
+	       && cudaMallocHost((void**)&c->h_maxidx, 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->lut255, 256 * sizeof(float)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[0], cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[1], cudaEventDisableTiming) == cudaSuccess
@@ -1354,6 +1356,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->h_mirror[1]) cudaFreeHost(c->h_mirror[1]);
 	if (c->rgba_staging) cudaFree(c->rgba_staging);
 	if (c->d_maxidx) cudaFree(c->d_maxidx);
+	if (c->h_maxidx) cudaFreeHost(c->h_maxidx);
 	if (c->lut255) cudaFree(c->lut255);
 	for (int i = 0; i < 2; i++) if (c->frame_ev[i]) cudaEventDestroy(c->frame_ev[i]);
 	for (int i = 0; i < 8; i++) if (c->draw_ev[i]) cudaEventDestroy(c->draw_ev[i]);
@@ -1441,18 +1444,62 @@ int swgldev_upload_overlapped(swgldev_ctx* c, swgldev_ptr dst, const void* src, 
 	return 0;
 }
 
+/* queue the max-index reduction and its read-back behind whatever the upload stream holds */
+static void queue_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
+{
+	const size_t n = bytes / 4u;
+	cudaMemsetAsync(c->d_maxidx, 0, 4, c->upload);
+	if (n) k_max_index<<<148 * 4, 256, 0, c->upload>>>((const uint32_t*)(uintptr_t)indices, n, c->d_maxidx);
+	cudaMemcpyAsync(c->h_maxidx, c->d_maxidx, 4, cudaMemcpyDeviceToHost, c->upload);
+}
+
+void* swgldev_host_alloc(uint64_t bytes, int write_combined)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void swgldev_host_free(void* p) { cudaFreeHost(p); }
+
 uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 {
 	cudaSetDevice(c->device);
-	const size_t n = bytes / 4u;
-	if (!n) return 0;
+	if (bytes < 4u) return 0;
 	/* on the upload stream: the buffer was just written there and nothing later has been queued */
-	cudaMemsetAsync(c->d_maxidx, 0, 4, c->upload);
-	k_max_index<<<148 * 4, 256, 0, c->upload>>>((const uint32_t*)(uintptr_t)indices, n, c->d_maxidx);
-	uint32_t h = 0;
-	cudaMemcpyAsync(&h, c->d_maxidx, 4, cudaMemcpyDeviceToHost, c->upload);
+	queue_max_index(c, indices, bytes);
 	cudaStreamSynchronize(c->upload);
-	return h;
+	return *c->h_maxidx;
+}
+
+/* swgldev_upload_overlapped of element data plus the largest index in it, with one wait for both */
+int swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index)
+{
+	cudaSetDevice(c->device);
+	*max_index = 0;
+	if (settle_last_draw(c)) return -1;
+	auto it = c->last_use.find((uintptr_t)dst);
+	if (it == c->last_use.end())
+	{
+		if (swgldev_upload(c, dst, src, bytes)) return -1;
+		*max_index = swgldev_max_index(c, dst, bytes);
+		return 0;
+	}
+	const uint64_t last_use = it->second;
+	if (last_use)
+	{
+		const uint64_t s = (c->draw_serial - last_use < 8u) ? last_use : c->draw_serial;   /* older than the ring: newest */
+		CK(cudaStreamWaitEvent(c->upload, c->draw_ev[s & 7u], 0));
+	}
+	CK(cudaMemcpyAsync((void*)(uintptr_t)dst, src, bytes, cudaMemcpyHostToDevice, c->upload));
+	queue_max_index(c, dst, bytes);
+	CK(cudaStreamSynchronize(c->upload));
+	*max_index = bytes >= 4u ? *c->h_maxidx : 0u;
+	return 0;
 }
 
 /* ---- deferred overflow check: wait for the counter snapshot of the previous draw and, when

@@ -189,6 +189,8 @@ void swglFinish(void) { if (G.dev) swgldev_sync(G.dev); }
 /* the step after the path */
 uint64_t swglFrameSubmit(void) { return G.dev ? swgldev_frame_submit(G.dev) : 0; }
 const uint32_t* swglFrameWait(uint64_t ticket) { return G.dev ? swgldev_frame_wait(G.dev, ticket) : NULL; }
+void* swglHostAlloc(uint64_t bytes, int write_combined) { return swgldev_host_alloc(bytes, write_combined); }
+void swglHostFree(void* p) { if (p) swgldev_host_free(p); }
 int swglReadPixelsRGBA8(void* dst) { return (G.dev && dst) ? swgldev_read_rgba8(G.dev, dst) : -1; }
 
 int swglWritePPM(const char* path)
@@ -454,8 +456,8 @@ void swglBufferRespecify(GLenum target, GLsizei size, const void* data)
 		b->capacity = size;
 	}
 	b->size = size;
-	swgldev_upload_overlapped(G.dev, b->data, data, size);
-	if (target == GL_ELEMENT_ARRAY_BUFFER) scan_indices(b, data, size);
+	if (target == GL_ELEMENT_ARRAY_BUFFER) swgldev_upload_indices(G.dev, b->data, data, size, &b->max_index);
+	else swgldev_upload_overlapped(G.dev, b->data, data, size);
 	if (b->origin && ((gl_buffer*)b->origin)->size != 0)
 	{
 		/* the named buffer owns this storage too (specified before it was bound into the vertex

@@ -79,6 +79,33 @@ def test_buffer_respecify_streams_new_geometry(gpu_api, restatement):
     assert np.array_equal(col, restatement.render(b)[0])
 
 
+def test_indexed_respecify_from_write_combined_staging_memory(gpu_api, restatement):
+    """The end-to-end step of bench.py: vertex and element arrays staged in swglHostAlloc memory
+    (page-locked, write-combined) and re-specified before the draw; the element upload and the
+    largest-index reduction share one wait (swgldev_upload_indices)."""
+    a, b = S.grid_mesh(20, 320, 240, seed=3), S.grid_mesh(28, 320, 240, seed=4)
+    api = gpu_api
+    api.glInit(a.width, a.height)
+    G.setup_scene(api, a, indexed=True, init=False)
+    staged = []
+    for wc in (1, 0):
+        scene = b if wc else a
+        for target, arr in ((G.GL_ARRAY_BUFFER, scene.vertices), (G.GL_ELEMENT_ARRAY_BUFFER, scene.indices)):
+            arr = np.ascontiguousarray(arr)
+            p = api.swglHostAlloc(arr.nbytes, wc)
+            assert p
+            C.memmove(p, arr.ctypes.data, arr.nbytes)
+            api.swglBufferRespecify(target, arr.nbytes, C.c_void_p(p))
+            staged.append(p)
+        api.glClear(3)
+        api.glDrawElements(G.GL_TRIANGLES, scene.indices.size, G.GL_UNSIGNED_INT, None)
+        col = G.frame_color(api, scene.width, scene.height)
+        assert api.swglGetLastError().decode() == ""
+        assert np.array_equal(col, restatement.render(scene)[0])
+    for p in staged:
+        api.swglHostFree(p)
+
+
 def _fullsize_golden():
     import json, os
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_kats.json")) as f:

@@ -12,6 +12,9 @@ api = sw.load()
 sc = S.config(cfg)
 api.glInit(sc.width, sc.height)
 st = G.setup_scene(api, sc, indexed=sc.indices is not None, init=False)
+for a in sys.argv[5:]:
+    k, v = a.split("=")
+    api.swglSetOption(k.encode(), int(v))
 api.swglSetStripe(rank, world, band)
 def frame():
     api.glClear(3)
