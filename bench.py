@@ -235,7 +235,7 @@ def run_own(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        traffic = tj.get(f"C{args.config}", {}).get(dom)
+        traffic = tj.get(f"C{args.config}", {}).get(dom) if world == 1 else None   # captured on the unsharded frame only
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes,
