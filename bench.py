@@ -129,6 +129,9 @@ def dist_setup(n_gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # NCCL's banner ("NCCL version ...") goes to stdout at the VERSION level: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
