@@ -244,7 +244,8 @@ def run_own(args):
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_us": stage_us[dom], "stage_us": stage_us,
                 "frame_algorithmic_bytes": scene.algorithmic_bytes(),
-                "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak}
+                "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak,
+                "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12}
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     # the application's vertex / index arrays in page-locked, write-combined host memory (swglHostAlloc):
@@ -383,6 +384,39 @@ def _timed_cpu(scene, tris, ref, O):
     return dt, None
 
 
+class pinned_to_one_core:
+    """The reference is single-threaded: run it on one host core, restore the mask afterwards."""
+
+    def __enter__(self):
+        self.mask = None
+        try:
+            self.mask = os.sched_getaffinity(0)
+            core = max(self.mask)            # away from core 0, where interrupt handling tends to land
+            os.sched_setaffinity(0, {core})
+            return core
+        except (AttributeError, OSError):
+            return None
+
+    def __exit__(self, *exc):
+        if self.mask:
+            try:
+                os.sched_setaffinity(0, self.mask)
+            except OSError:
+                pass
+        return False
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_sample(scene, target_seconds: float, tris: int | None = None, reps: int | None = None):
     """Time the compiled reference (oracle/_ref; else the C port) on one host core.
 
@@ -406,11 +440,12 @@ def cpu_reference_sample(scene, target_seconds: float, tris: int | None = None, 
         reps = max(1, int(round(target_seconds / (tris / rate)))) if reps is None else reps
     reps = reps or 1
     times, clear_s = [], None
-    for _ in range(reps):
-        dt, clear_s = _timed_cpu(scene, tris, ref, O)
-        times.append(dt)
+    with pinned_to_one_core() as core:
+        for _ in range(reps):
+            dt, clear_s = _timed_cpu(scene, tris, ref, O)
+            times.append(dt)
     dt = statistics.mean(times)
-    return {"value": tris / dt, "unit": METRIC, "cores": 1, "kind": kind,
+    return {"value": tris / dt, "unit": METRIC, "cores": 1, "kind": kind, "core": core, "cpu_model": cpu_model(),
             "sample": f"first {tris} of {n_tris} triangles of the same scene, full-size framebuffer, "
                       f"glClear+glDrawArrays x{reps} (mean {dt:.2f} s per frame, clear {clear_s if clear_s is None else round(clear_s, 3)} s)",
             "seconds": dt, "tris": tris, "reps": reps, "host_cpus": os.cpu_count()}
