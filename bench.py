@@ -247,6 +247,37 @@ def run_own(args):
                 "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak,
                 "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12}
 
+    # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
+    def assembled_equals_single():
+        barrier()
+        frame()
+        barrier()
+        out = None
+        if rank == 0:
+            multi = G.frame_color(api, scene.width, scene.height)
+            api.swglSetStripe(0, 1, 1)
+            frame()
+            single = G.frame_color(api, scene.width, scene.height)
+            api.swglSetStripe(rank, world, band_rows)
+            out = {"equal_to_single_gpu": bool(np.array_equal(multi, single)),
+                   "mismatching_pixels": int((multi != single).sum())}
+        barrier()
+        return out
+
+    mg_check = assembled_equals_single() if world > 1 else None
+
+    # For the end-to-end step the frame is wanted in HOST memory: the ranks switch from the NVLink target
+    # (rank 0's HBM) to one shared host segment that every rank writes its bands into over its own PCIe link.
+    shared = None
+    if world > 1:
+        peer.close()
+        peer = None
+        try:
+            shared = multigpu.SharedFrameMirror(api, dist, rank, world, scene.width, scene.height)
+        except (RuntimeError, OSError):
+            shared = None
+            peer = multigpu.PeerColorTarget(api, dist, rank, world)
+
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     # the application's vertex / index arrays in page-locked, write-combined host memory (swglHostAlloc):
     # written once by the CPU, read by the copy engine every step without snooping the CPU caches
@@ -261,7 +292,7 @@ def run_own(args):
             api.swglFinish()
             dist.barrier()
         if rank == 0:
-            api.glGetFramePtr()   # sync + D2H of the assembled colour image into the pinned mirror
+            api.glGetFramePtr()   # N = 1: wait for the written-through mirror; N > 1: the shared segment (or sync + D2H)
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -279,6 +310,13 @@ def run_own(args):
            "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes) * world,
            "host_buffers": "page-locked, write-combined (swglHostAlloc)",
            "d2h_bytes_per_step": scene.width * scene.height * 4}
+    if world > 1:
+        e2e["assembly"] = ("shared host frame mirror: every rank writes its bands over its own PCIe link" if shared is not None
+                           else "peer stores into rank 0's HBM, then one D2H copy on rank 0")
+        if shared is not None:
+            e2e["host_mirror_check"] = assembled_equals_single()
+            shared.close()
+            shared = None
 
     # ---- the same step pipelined: two geometry sets and two frame mirrors; step N's
     # upload overlaps frame N-1 on the device, its frame is collected during step N+1 ----
@@ -315,22 +353,6 @@ def run_own(args):
                     "note": "swglFrameSubmit/swglFrameWait, two geometry sets: same bytes per step as e2e, each frame is read one step later"}
 
     clocks = sampler.stop() if rank == 0 else {}   # sampled across the value, roofline and e2e legs
-
-    # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
-    mg_check = None
-    if world > 1:
-        barrier()
-        frame()
-        barrier()
-        if rank == 0:
-            multi = G.frame_color(api, scene.width, scene.height)
-            api.swglSetStripe(0, 1, 1)
-            frame()
-            single = G.frame_color(api, scene.width, scene.height)
-            api.swglSetStripe(rank, world, band_rows)
-            mg_check = {"equal_to_single_gpu": bool(np.array_equal(multi, single)),
-                        "mismatching_pixels": int((multi != single).sum())}
-        barrier()
 
     # ---- CPU baseline: the unmodified reference on one host core, bounded sample ----
     cpu = None

@@ -64,6 +64,16 @@ void swglSetStripe(GLuint rank, GLuint n_ranks, GLuint band_tile_rows);
  * raster write-back also stores each finished tile row into it.  0 disables. */
 void swglSetPeerColorTarget(uint64_t device_ptr);
 
+/* Shared frame mirror: the other way to assemble a sort-first frame, for applications that want it in HOST
+ * memory (glGetFramePtr).  `host_ptr` is W*H*4 bytes (page aligned, `bytes` a multiple of the page size) that
+ * every rank has mapped -- POSIX shared memory, for instance; each rank calls this once.  From then on the raster
+ * kernels of a rank store its finished tiles straight into that memory over the rank's own PCIe link, so N links
+ * carry the frame in parallel instead of rank 0's alone; swglFinish / glGetFramePtr bring the calling rank's
+ * bands up to date (by copies, when a frame did not start from a whole-framebuffer clear), and after the
+ * application's barrier glGetFramePtr on any rank returns the assembled frame: `host_ptr` itself.
+ * NULL switches it off.  Returns 0 on success. */
+int swglSetSharedFrameMirror(void* host_ptr, uint64_t bytes);
+
 /* CUDA IPC plumbing for the peer colour target (one process per GPU): rank 0 exports its colour
  * attachment as a 64-byte handle, the other ranks open it and pass the address to
  * swglSetPeerColorTarget.  Return 0 / an address on success. */

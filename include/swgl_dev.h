@@ -158,6 +158,10 @@ void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out);
 void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_t band_tile_rows);
 /* peer colour target: finished tiles are also stored to this (peer-mapped) colour buffer */
 void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color);
+/* shared frame mirror (W*H*4 bytes of host memory every rank has mapped, e.g. POSIX shared memory): each
+ * rank registers it and its raster kernels store finished tiles there over the rank's own PCIe link;
+ * swgldev_sync copies the rank's bands when a frame could not be written through; NULL disables */
+int         swgldev_set_shared_mirror(swgldev_ctx* c, void* host_ptr, uint64_t bytes);
 /* CUDA IPC for the peer colour target: export this context's colour attachment (64-byte
  * cudaIpcMemHandle_t), open / close a handle exported by another process */
 int         swgldev_ipc_export_color(swgldev_ctx* c, void* handle64);

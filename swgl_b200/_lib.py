@@ -50,6 +50,7 @@ EXTENSION_EXPORTS = {
     "swglFrameWait": (C.POINTER(C.c_uint32), [C.c_uint64]),
     "swglReadPixelsRGBA8": (C.c_int, [C.c_void_p]),
     "swglWritePPM": (C.c_int, [C.c_char_p]),
+    "swglSetSharedFrameMirror": (C.c_int, [C.c_void_p, C.c_uint64]),
     "swglHostAlloc": (C.c_void_p, [C.c_uint64, C.c_int]),
     "swglHostFree": (None, [C.c_void_p]),
 }

@@ -74,6 +74,10 @@ struct swgldev_ctx
 	float* lut255;
 	uint32_t draws_since_map;
 	uint32_t* peer_color;
+	/* Shared frame mirror (sort-first, one process per GPU): page-locked host memory that every rank has
+	 * mapped; each rank's raster kernels store its finished tiles there over its own PCIe link, so the
+	 * assembled frame is in host memory when the ranks have finished -- no gather, no copy on rank 0. */
+	uint32_t* shared_mirror; uint32_t* shared_mirror_dev; size_t shared_mirror_bytes;
 	uint32_t rank, n_ranks, band_rows;
 
 	/* grow-only scratch */
@@ -1273,6 +1277,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tiles_y = (height + SWGL_TILE - 1) / SWGL_TILE;
 	c->stream = nullptr; c->color = nullptr; c->depth = nullptr; c->h_color = nullptr; c->h_depth = nullptr;
 	c->peer_color = nullptr; c->rank = 0; c->n_ranks = 1; c->band_rows = 1;
+	c->shared_mirror = nullptr; c->shared_mirror_dev = nullptr; c->shared_mirror_bytes = 0;
 	c->clip = nullptr; c->cap_clip = 0; c->clip_xy = nullptr; c->cap_clip_xy = 0; c->vary = nullptr; c->cap_vary = 0;
 	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
@@ -1347,6 +1352,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->shared_mirror) { cudaHostUnregister(c->shared_mirror); c->shared_mirror = nullptr; }
 	for (void* p : c->allocations) cudaFree(p);
 	for (auto& kv : c->code_cache) cudaFree(kv.second);
 	if (c->upload) { cudaStreamSynchronize(c->upload); cudaStreamDestroy(c->upload); }
@@ -1594,6 +1600,8 @@ static int flush_clear(swgldev_ctx* c)
 	return 0;
 }
 
+static int flush_owned_bands(swgldev_ctx* c);
+
 int swgldev_sync(swgldev_ctx* c)
 {
 	cudaSetDevice(c->device);
@@ -1601,6 +1609,11 @@ int swgldev_sync(swgldev_ctx* c)
 	if (flush_clear(c)) return -1;
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->copy_inflight) CK(cudaStreamSynchronize(c->copy));
+	if (c->shared_mirror && !c->mirror_synced && !c->color_exposed)
+	{
+		if (flush_owned_bands(c)) return -1;
+		c->mirror_synced = 1;
+	}
 	return 0;
 }
 
@@ -1826,7 +1839,13 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	/* a fused clear of the whole framebuffer makes every tile dirty: the mirror is complete afterwards */
 	const bool full_clear = (P.clear.flags & 1u) && P.clear.x0 <= 0 && P.clear.y0 <= 0
 	                        && P.clear.x1 >= (int32_t)c->W && P.clear.y1 >= (int32_t)c->H;
-	if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && !c->color_exposed && (c->mirror_synced || full_clear)
+	if (c->shared_mirror)
+	{
+		/* shared frame mirror: this rank's bands of it stay in sync as long as every colour write goes through */
+		if (!c->color_exposed && (c->mirror_synced || full_clear)) { c->mirror_synced = 1; P.peer_color = c->shared_mirror_dev; c->wt_draws++; }
+		else { c->mirror_synced = 0; P.peer_color = nullptr; }
+	}
+	else if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && !c->color_exposed && (c->mirror_synced || full_clear)
 	    && (c->opt_host_mirror == 2 || (c->wt_predict && c->draws_since_map <= 2)))
 	{
 		c->mirror_synced = 1;
@@ -1885,8 +1904,30 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 	return stamp_draw(c, d);
 }
 
+/* rows [r0, r1) of the colour attachment this rank owns (storage rows), band by band */
+static int flush_owned_bands(swgldev_ctx* c)
+{
+	const uint32_t band_px = 32u * (c->band_rows ? c->band_rows : 1u);
+	for (uint32_t b = 0; (size_t)b * band_px < c->H; b++)
+	{
+		if (c->n_ranks > 1 && b % c->n_ranks != c->rank) continue;
+		const size_t r0 = (size_t)b * band_px, r1 = (r0 + band_px < c->H) ? r0 + band_px : c->H;
+		CK(cudaMemcpyAsync(c->shared_mirror + r0 * c->W, c->color + r0 * c->W, (r1 - r0) * c->W * 4, cudaMemcpyDeviceToHost, c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
 uint32_t* swgldev_map_color(swgldev_ctx* c)
 {
+	if (c->shared_mirror)
+	{
+		/* swgldev_sync has brought this rank's bands up to date; the other ranks' are theirs to finish
+		 * (the application's barrier, as with the peer colour target) */
+		swgldev_sync(c);
+		c->draws_since_map = 0;
+		return c->shared_mirror;
+	}
 	if (swgldev_sync(c)) { c->mirror_synced = 0; return c->h_color; }
 	if (!c->mirror_synced)
 	{
@@ -1904,6 +1945,7 @@ uint32_t* swgldev_map_color(swgldev_ctx* c)
 uint64_t swgldev_frame_submit(swgldev_ctx* c)
 {
 	cudaSetDevice(c->device);
+	if (c->shared_mirror) { set_err(c, "swglFrameSubmit: not available with a shared frame mirror", cudaSuccess); return 0; }
 	if (settle_last_draw(c) || flush_clear(c)) return 0;
 	const size_t bytes = (size_t)c->W * c->H * 4;
 	if (!c->h_mirror[1])
@@ -1996,12 +2038,35 @@ void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_
 {
 	swgldev_sync(c);
 	c->rank = rank; c->n_ranks = n_ranks ? n_ranks : 1; c->band_rows = band_tile_rows ? band_tile_rows : 1;
+	if (c->shared_mirror) c->mirror_synced = 0;     /* other bands are this rank's now */
 }
 
 void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color)
 {
 	swgldev_sync(c);
 	c->peer_color = (uint32_t*)(uintptr_t)peer_color;
+}
+
+int swgldev_set_shared_mirror(swgldev_ctx* c, void* host_ptr, uint64_t bytes)
+{
+	cudaSetDevice(c->device);
+	swgldev_sync(c);
+	if (c->shared_mirror)
+	{
+		cudaHostUnregister(c->shared_mirror);
+		c->shared_mirror = nullptr; c->shared_mirror_dev = nullptr; c->shared_mirror_bytes = 0;
+		c->mirror_synced = 0;
+	}
+	if (!host_ptr) return 0;
+	if (bytes < (uint64_t)c->W * c->H * 4) { set_err(c, "swglSetSharedFrameMirror: the memory is smaller than the colour attachment", cudaSuccess); return -1; }
+	cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+	if (e != cudaSuccess) { set_err(c, "cudaHostRegister (shared frame mirror)", e); return -1; }
+	void* d = nullptr;
+	e = cudaHostGetDevicePointer(&d, host_ptr, 0);
+	if (e != cudaSuccess) { cudaHostUnregister(host_ptr); set_err(c, "cudaHostGetDevicePointer (shared frame mirror)", e); return -1; }
+	c->shared_mirror = (uint32_t*)host_ptr; c->shared_mirror_dev = (uint32_t*)d; c->shared_mirror_bytes = bytes;
+	c->mirror_synced = 0;      /* the next swgldev_sync copies this rank's bands unless a cleared frame has been written through */
+	return 0;
 }
 
 int swgldev_ipc_export_color(swgldev_ctx* c, void* handle64)

@@ -248,6 +248,7 @@ uint64_t swglGetDepthDevicePtr(void) { return G.dev ? swgldev_depth_devptr(G.dev
 void swglFillFramebuffer(uint32_t color_word, float depth) { if (G.dev) swgldev_fill(G.dev, color_word, depth); }
 void swglSetStripe(GLuint rank, GLuint n_ranks, GLuint band_tile_rows) { if (G.dev) swgldev_set_stripe(G.dev, rank, n_ranks, band_tile_rows); }
 void swglSetPeerColorTarget(uint64_t p) { if (G.dev) swgldev_set_peer_color(G.dev, p); }
+int swglSetSharedFrameMirror(void* host_ptr, uint64_t bytes) { return G.dev ? swgldev_set_shared_mirror(G.dev, host_ptr, bytes) : -1; }
 int swglIpcExportColor(void* handle64) { return G.dev ? swgldev_ipc_export_color(G.dev, handle64) : -1; }
 uint64_t swglIpcOpen(const void* handle64) { return G.dev ? swgldev_ipc_open(G.dev, handle64) : 0; }
 void swglIpcClose(uint64_t p) { if (G.dev) swgldev_ipc_close(G.dev, p); }

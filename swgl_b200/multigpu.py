@@ -2,12 +2,14 @@
 
 The frame is split by tile-row bands dealt round-robin to the ranks (``swglSetStripe``);
 geometry is replicated, so there is no exchange until the image is assembled on rank 0.
-Two ways to assemble it:
+Three ways to assemble it:
 
 * ``PeerColorTarget`` -- rank 0 exports its colour attachment through CUDA IPC, every other rank
   maps it and the raster kernel's 128-bit write-back stores each finished strip straight into
   rank 0's framebuffer over NVLink (the collective is fused into the kernel epilogue; only a
   barrier remains);
+* ``SharedFrameMirror`` -- for frames that are wanted in host memory: every rank maps one shared
+  host segment and its raster kernels write finished tiles there over the rank's own PCIe link;
 * ``gather_color`` -- plain NCCL: every rank contributes its band rows, rank 0 receives them
   (the baseline the fused variant is measured against).
 
@@ -90,6 +92,82 @@ class PeerColorTarget:
             self.api.swglSetPeerColorTarget(0)
             self.api.swglIpcClose(self.ptr)
             self.ptr = 0
+
+
+class SharedFrameMirror:
+    """Assemble the frame in HOST memory: one POSIX shared-memory segment mapped by every rank
+    (``swglSetSharedFrameMirror``).  Each rank's raster kernels store its finished tiles there over the
+    rank's own PCIe link, so the frame reaches the host over N links in parallel and rank 0's
+    ``glGetFramePtr`` has nothing left to copy.  ``dist`` may be None (single process)."""
+
+    PAGE = 4096
+
+    def __init__(self, api, dist, rank: int, world: int, width: int, height: int):
+        import mmap
+        import os
+
+        self.api, self.rank, self.active = api, rank, False
+        self.nbytes = width * height * 4
+        size = (self.nbytes + self.PAGE - 1) // self.PAGE * self.PAGE
+        box = [None]
+        if rank == 0:
+            box[0] = f"/dev/shm/swgl_b200_frame_{os.getpid()}"
+            with open(box[0], "wb") as f:
+                f.truncate(size)
+        if dist is not None:
+            dist.broadcast_object_list(box, src=0)
+        self.path = box[0]
+        self.map, self.addr, ok = None, 0, False
+        try:
+            fd = os.open(self.path, os.O_RDWR)
+            try:
+                self.map = mmap.mmap(fd, size)
+            finally:
+                os.close(fd)
+            self.addr = C.addressof(C.c_char.from_buffer(self.map))
+            ok = api.swglSetSharedFrameMirror(C.c_void_p(self.addr), size) == 0
+        except (OSError, ValueError, TypeError):
+            ok = False          # every rank still reaches the vote below
+        if dist is not None:
+            import torch
+
+            flag = torch.tensor([1 if ok else 0], device=f"cuda:{torch.cuda.current_device()}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            all_ok = bool(flag.item())
+        else:
+            all_ok = ok
+        if not all_ok:          # some rank could not register the segment: nobody uses it
+            if ok:
+                api.swglSetSharedFrameMirror(None, 0)
+            self._unmap()
+            raise RuntimeError("swglSetSharedFrameMirror failed: " + api.swglGetLastError().decode())
+        self.active = True
+        if dist is not None:
+            dist.barrier()
+
+    def frame(self, height: int, width: int) -> np.ndarray:
+        """The assembled frame ([H, W] uint32 view of the shared segment)."""
+        return np.frombuffer(self.map, dtype=np.uint32, count=height * width).reshape(height, width)
+
+    def _unmap(self):
+        import os
+
+        try:
+            if self.map is not None:
+                self.map.close()
+        except (BufferError, ValueError):
+            pass                # a numpy view is still alive: the mapping goes with the process
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+    def close(self):
+        if self.active:
+            self.api.swglSetSharedFrameMirror(None, 0)
+            self.active = False
+            self._unmap()
 
 
 def gather_rows(img, dist, rank: int, world: int, height: int, band_tile_rows: int):

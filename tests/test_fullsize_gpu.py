@@ -59,6 +59,41 @@ def test_stripe_emulation_equals_single_gpu(gpu_api, n_ranks, band):
     assert total_shaded == full[2]["shaded"]
 
 
+@pytest.mark.parametrize("n_ranks,band,clear", [(1, 1, True), (4, 1, True), (3, 2, False)])
+def test_shared_frame_mirror_assembles_the_frame_in_host_memory(gpu_api, n_ranks, band, clear):
+    """swglSetSharedFrameMirror: every rank writes its bands of the frame into one host segment (the
+    ranks are emulated one after the other on this GPU).  With a whole-framebuffer clear the raster
+    kernels write through; without one swglFinish copies the rank's bands."""
+    scene = S.config(2)
+    api = gpu_api
+    fill = (0x10203040, 0.0)
+    full = gpu_render(api, scene, clear=clear, fill=fill)
+    mirror = None
+    for r in range(n_ranks):
+        api.glInit(scene.width, scene.height)
+        api.swglSetStripe(r, n_ranks, band)      # first: registering the mirror makes the rank responsible for ITS bands
+        if mirror is None:
+            mirror = multigpu.SharedFrameMirror(api, None, 0, 1, scene.width, scene.height)
+        else:
+            assert api.swglSetSharedFrameMirror(C.c_void_p(mirror.addr), len(mirror.map)) == 0
+        st = G.setup_scene(api, scene, indexed=True, init=False)
+        api.swglFillFramebuffer(fill[0], C.c_float(fill[1]))
+        if clear:
+            api.glClear(3)
+        api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
+        api.swglFinish()
+        assert api.swglGetLastError().decode() == ""
+        if clear:
+            assert api.swglGetOption(b"wt_draws") == 1      # written through by the raster kernel
+        ptr = api.glGetFramePtr()
+        assert C.cast(ptr, C.c_void_p).value == mirror.addr  # glGetFramePtr hands out the segment itself
+        assert api.swglSetSharedFrameMirror(None, 0) == 0
+    img = mirror.frame(scene.height, scene.width).copy()
+    mirror.active = False
+    mirror._unmap()
+    assert np.array_equal(img, full[0])
+
+
 def test_buffer_respecify_streams_new_geometry(gpu_api, restatement):
     """swglBufferRespecify (extension) replaces buffer contents; glBufferData ignores a second
     specification like the reference does (swgl.c:3140)."""

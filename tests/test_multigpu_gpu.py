@@ -1,6 +1,6 @@
 """GPU (needs >= 2 devices, skipped otherwise): two processes, NCCL control plane, each rank
-rasterises its tile-row bands; both assembly paths (peer stores over CUDA IPC, NCCL send/recv)
-must reproduce the single-GPU frame bit for bit."""
+rasterises its tile-row bands; the three assembly paths (peer stores over CUDA IPC, NCCL send/recv,
+write-through into a shared host segment) must reproduce the single-GPU frame bit for bit."""
 import os
 import socket
 
@@ -37,6 +37,8 @@ def _worker(rank, world, port, mode, q):
     api.swglFillFramebuffer(0x01020304, C.c_float(0.0))
     api.swglSetStripe(rank, world, band)
     peer = multigpu.PeerColorTarget(api, dist, rank, world) if mode == "peer" else None
+    if mode == "host":
+        peer = multigpu.SharedFrameMirror(api, dist, rank, world, scene.width, scene.height)
     api.glClear(3)
     api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
     api.swglFinish()
@@ -44,7 +46,11 @@ def _worker(rank, world, port, mode, q):
     if mode == "nccl":
         multigpu.gather_color(api, dist, rank, world, scene.height, scene.width, band, torch.device("cuda", rank))
     if rank == 0:
-        multi = G.frame_color(api, scene.width, scene.height)
+        multi = G.frame_color(api, scene.width, scene.height).copy()
+        if mode == "host":
+            assert np.array_equal(multi, peer.frame(scene.height, scene.width))
+            peer.close()
+            peer = None
         api.swglSetStripe(0, 1, 1)
         api.glClear(3)
         api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
@@ -56,7 +62,7 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "nccl"])
+@pytest.mark.parametrize("mode", ["peer", "nccl", "host"])
 def test_two_ranks_assemble_the_single_gpu_frame(mode):
     import torch
 
