@@ -105,24 +105,6 @@ class ClockSampler:
         return out
 
 
-class HostArray:
-    """A numpy array copied into page-locked (write-combined) host memory of the library."""
-
-    def __init__(self, api, a):
-        a = np.ascontiguousarray(a)
-        self.api = api
-        self.nbytes = int(a.nbytes)
-        self.ptr = api.swglHostAlloc(self.nbytes, 1)
-        if not self.ptr:
-            raise RuntimeError("swglHostAlloc failed")
-        C.memmove(self.ptr, a.ctypes.data, self.nbytes)
-
-    def free(self):
-        if self.ptr:
-            self.api.swglHostFree(self.ptr)
-            self.ptr = None
-
-
 def dist_setup(n_gpus: int):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -281,12 +263,21 @@ def run_own(args):
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     # the application's vertex / index arrays in page-locked, write-combined host memory (swglHostAlloc):
     # written once by the CPU, read by the copy engine every step without snooping the CPU caches
-    verts = HostArray(api, scene.vertices)
-    idx = HostArray(api, scene.indices)
+    verts = multigpu.HostArray(api, scene.vertices)
+    idx = multigpu.HostArray(api, scene.indices)
+    # N > 1: every rank uploads 1/N of the arrays over its own PCIe link, an NCCL all-gather over NVLink on the
+    # library's stream replicates them (falls back to N full uploads when the sizes do not divide)
+    sharded = None
+    if world > 1 and multigpu.ShardedUpload.divisible(verts.nbytes, world) and multigpu.ShardedUpload.divisible(idx.nbytes, world):
+        sharded = multigpu.ShardedUpload(api, dist, rank, world, torch.device("cuda", local))
 
     def e2e_step():
-        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
-        api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
+        if sharded is not None:
+            sharded.upload(G.GL_ARRAY_BUFFER, verts)
+            sharded.upload(G.GL_ELEMENT_ARRAY_BUFFER, idx)
+        else:
+            api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
+            api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
         frame()
         if dist is not None:
             api.swglFinish()
@@ -307,10 +298,14 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = {"value": n_tris / e2e_s, "unit": METRIC, "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes) * world,
+           "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes) * (1 if sharded is not None else world),
            "host_buffers": "page-locked, write-combined (swglHostAlloc)",
            "d2h_bytes_per_step": scene.width * scene.height * 4}
     if world > 1:
+        e2e["upload"] = ("1/N of the arrays per rank over its own PCIe link + NCCL all-gather over NVLink" if sharded is not None
+                         else "every rank uploads the whole arrays")
+        if sharded is not None:
+            e2e["nvlink_bytes_per_step_per_rank"] = int(verts.nbytes + idx.nbytes) * (world - 1) // world
         e2e["assembly"] = ("shared host frame mirror: every rank writes its bands over its own PCIe link" if shared is not None
                            else "peer stores into rank 0's HBM, then one D2H copy on rank 0")
         if shared is not None:

@@ -93,6 +93,17 @@ int swglReadPixelsRGBA8(void* dst);
 /* The current frame as a binary PPM (P6); 0 on success. */
 int swglWritePPM(const char* path);
 
+/* Geometry that reaches the device in pieces (sort-first ranks: every rank uploads 1/N of the arrays over its own
+ * PCIe link and an all-gather over NVLink, queued on swglGetStream(), replicates them).
+ * swglBufferSubData copies `size` bytes to byte `offset` of the bound buffer (already specified with that size or
+ * more; the copy completes before the call returns and waits only for draws that read the buffer);
+ * swglGetBufferDevicePtr is the device address of the bound buffer's storage;
+ * swglBufferDeviceWritten tells the library that work queued on its stream has rewritten the bound buffer (element
+ * data: the largest index is recomputed behind that work). */
+void     swglBufferSubData(GLenum target, uint64_t offset, GLsizei size, const void* data);
+uint64_t swglGetBufferDevicePtr(GLenum target);
+void     swglBufferDeviceWritten(GLenum target);
+
 /* Page-locked staging memory for the application's vertex / index arrays (the source of glBufferData and
  * swglBufferRespecify).  write_combined != 0 asks for write-combined pages: the CPU writes them once,
  * front to back, and never reads them, and host-to-device copies do not have to snoop the CPU caches --

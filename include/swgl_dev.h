@@ -120,6 +120,11 @@ void         swgldev_free(swgldev_ctx* c, swgldev_ptr p);
 /* largest u32 in an uploaded element buffer (device reduction; the extension glDrawElements
  * shades vertices [0, max] once each) */
 uint32_t     swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
+/* swgldev_upload_overlapped() into part of an allocation (`base` + offset); and the largest index of element
+ * data that work on the library's stream has written (multi-GPU: each rank uploads a slice, an all-gather over
+ * NVLink on the library's stream replicates it) */
+int          swgldev_upload_range(swgldev_ctx* c, swgldev_ptr base, uint64_t offset, const void* src, uint64_t bytes);
+uint32_t     swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
 /* swgldev_upload_overlapped() of element data and swgldev_max_index() of it, with a single wait
  * (swglBufferRespecify(GL_ELEMENT_ARRAY_BUFFER), the per-frame upload of the end-to-end step). */
 int          swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index);

@@ -1482,6 +1482,37 @@ uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 	return *c->h_maxidx;
 }
 
+/* Part of an allocation: `base` names it (for the read hazards), the copy goes to base + offset. */
+int swgldev_upload_range(swgldev_ctx* c, swgldev_ptr base, uint64_t offset, const void* src, uint64_t bytes)
+{
+	cudaSetDevice(c->device);
+	if (settle_last_draw(c)) return -1;
+	auto it = c->last_use.find((uintptr_t)base);
+	if (it == c->last_use.end()) return swgldev_upload(c, base + offset, src, bytes);
+	const uint64_t last_use = it->second;
+	if (last_use)
+	{
+		const uint64_t s = (c->draw_serial - last_use < 8u) ? last_use : c->draw_serial;
+		CK(cudaStreamWaitEvent(c->upload, c->draw_ev[s & 7u], 0));
+	}
+	CK(cudaMemcpyAsync((void*)(uintptr_t)(base + offset), src, bytes, cudaMemcpyHostToDevice, c->upload));
+	CK(cudaStreamSynchronize(c->upload));
+	return 0;
+}
+
+/* Largest index of element data that work queued on the library's stream (an all-gather of the
+ * application's, say) has just written: the reduction runs behind that work. */
+uint32_t swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
+{
+	cudaSetDevice(c->device);
+	if (bytes < 4u) return 0;
+	if (cudaEventRecord(c->setup_event, c->stream) != cudaSuccess) return 0;      /* any event of the context will do: it is re-recorded by the next draw */
+	cudaStreamWaitEvent(c->upload, c->setup_event, 0);
+	queue_max_index(c, indices, bytes);
+	cudaStreamSynchronize(c->upload);
+	return *c->h_maxidx;
+}
+
 /* swgldev_upload_overlapped of element data plus the largest index in it, with one wait for both */
 int swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index)
 {

@@ -468,6 +468,43 @@ void swglBufferRespecify(GLenum target, GLsizei size, const void* data)
 	}
 }
 
+static gl_buffer* bound_buffer(GLenum target)
+{
+	return target == GL_ARRAY_BUFFER ? G.array_buffer : target == GL_ELEMENT_ARRAY_BUFFER ? G.element_buffer : NULL;
+}
+
+static void sync_origin(gl_buffer* b)
+{
+	if (b->origin && ((gl_buffer*)b->origin)->size != 0)
+	{
+		gl_buffer* o = (gl_buffer*)b->origin;
+		o->data = b->data; o->size = b->size; o->capacity = b->capacity; o->max_index = b->max_index;
+	}
+}
+
+void swglBufferSubData(GLenum target, uint64_t offset, GLsizei size, const void* data)
+{
+	gl_buffer* b = bound_buffer(target);
+	if (!b || !G.dev || !data || size == 0 || !b->data) return;
+	if (offset + (uint64_t)size > (uint64_t)b->size) { set_error("swglBufferSubData: range outside the buffer"); return; }
+	swgldev_upload_range(G.dev, b->data, offset, data, size);
+	/* element data: the largest index is refreshed by swglBufferDeviceWritten once the whole buffer is in place */
+}
+
+uint64_t swglGetBufferDevicePtr(GLenum target)
+{
+	gl_buffer* b = bound_buffer(target);
+	return (b && G.dev) ? (uint64_t)b->data : 0;
+}
+
+void swglBufferDeviceWritten(GLenum target)
+{
+	gl_buffer* b = bound_buffer(target);
+	if (!b || !G.dev || !b->data || b->size == 0) return;
+	if (target == GL_ELEMENT_ARRAY_BUFFER) b->max_index = swgldev_max_index_after_stream(G.dev, b->data, b->size);
+	sync_origin(b);
+}
+
 /* ---------------------------------------------------------------------------------------- */
 /* textures (swgl.c:2038-2173) */
 void glGenTextures(GLsizei n, GLuint* textures)

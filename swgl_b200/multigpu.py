@@ -94,6 +94,63 @@ class PeerColorTarget:
             self.ptr = 0
 
 
+class HostArray:
+    """A numpy array copied into page-locked, write-combined host memory of the library (swglHostAlloc)."""
+
+    def __init__(self, api, a):
+        a = np.ascontiguousarray(a)
+        self.api = api
+        self.nbytes = int(a.nbytes)
+        self.ptr = api.swglHostAlloc(self.nbytes, 1)
+        if not self.ptr:
+            raise RuntimeError("swglHostAlloc failed")
+        C.memmove(self.ptr, a.ctypes.data, self.nbytes)
+
+    def free(self):
+        if self.ptr:
+            self.api.swglHostFree(self.ptr)
+            self.ptr = None
+
+
+class ShardedUpload:
+    """Replicated geometry without replicated PCIe traffic: every rank copies 1/N of an array into the
+    bound buffer over its own PCIe link (``swglBufferSubData``) and an in-place NCCL all-gather over
+    NVLink, queued on the library's stream, hands every rank the rest."""
+
+    def __init__(self, api, dist, rank: int, world: int, device):
+        import torch
+
+        self.api, self.dist, self.rank, self.world, self.device = api, dist, rank, world, device
+        self.stream = torch.cuda.ExternalStream(api.swglGetStream(), device=device)
+        self._views = {}
+
+    @staticmethod
+    def divisible(nbytes: int, world: int) -> bool:
+        return nbytes % (4 * world) == 0       # equal chunks of whole 32-bit words
+
+    def _view(self, ptr: int, nbytes: int):
+        import torch
+
+        key = (ptr, nbytes)
+        if key not in self._views:
+            self._views[key] = torch.as_tensor(_DevArray(ptr, (nbytes // 4,), "<i4"), device=self.device)
+        return self._views[key]
+
+    def upload(self, target: int, host: HostArray):
+        import torch
+
+        n, w, r = host.nbytes, self.world, self.rank
+        if not self.divisible(n, w):
+            raise ValueError("array size is not a multiple of 4 bytes x ranks")
+        chunk = n // w
+        self.api.swglBufferSubData(target, r * chunk, chunk, C.c_void_p(host.ptr + r * chunk))
+        full = self._view(self.api.swglGetBufferDevicePtr(target), n)
+        mine = full[r * chunk // 4:(r + 1) * chunk // 4]
+        with torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(full, mine)
+        self.api.swglBufferDeviceWritten(target)
+
+
 class SharedFrameMirror:
     """Assemble the frame in HOST memory: one POSIX shared-memory segment mapped by every rank
     (``swglSetSharedFrameMirror``).  Each rank's raster kernels store its finished tiles there over the

@@ -39,6 +39,14 @@ def _worker(rank, world, port, mode, q):
     peer = multigpu.PeerColorTarget(api, dist, rank, world) if mode == "peer" else None
     if mode == "host":
         peer = multigpu.SharedFrameMirror(api, dist, rank, world, scene.width, scene.height)
+        # the geometry again, this time 1/N per rank over PCIe + all-gather over NVLink: scrub the buffers first
+        hv, hi = multigpu.HostArray(api, scene.vertices), multigpu.HostArray(api, scene.indices)
+        junk = multigpu.HostArray(api, np.zeros(scene.vertices.size, np.float32))
+        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, junk.nbytes, C.c_void_p(junk.ptr))
+        up = multigpu.ShardedUpload(api, dist, rank, world, torch.device("cuda", rank))
+        assert up.divisible(hv.nbytes, world) and up.divisible(hi.nbytes, world)
+        up.upload(G.GL_ARRAY_BUFFER, hv)
+        up.upload(G.GL_ELEMENT_ARRAY_BUFFER, hi)
     api.glClear(3)
     api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
     api.swglFinish()
