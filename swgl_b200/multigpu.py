@@ -186,11 +186,9 @@ class SharedFrameMirror:
         except (OSError, ValueError, TypeError):
             ok = False          # every rank still reaches the vote below
         if dist is not None:
-            import torch
-
-            flag = torch.tensor([1 if ok else 0], device=f"cuda:{torch.cuda.current_device()}")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            all_ok = bool(flag.item())
+            votes = [None] * world
+            dist.all_gather_object(votes, bool(ok))
+            all_ok = all(votes)
         else:
             all_ok = ok
         if not all_ok:          # some rank could not register the segment: nobody uses it

@@ -78,3 +78,73 @@ def test_gather_rows_world2_gloo(band):
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+class _FakeMirrorApi:
+    """Stands in for the library on a box without a GPU: records the registered segment."""
+
+    def __init__(self, fail=False):
+        self.addr, self.fail = None, fail
+
+    def swglSetSharedFrameMirror(self, ptr, nbytes):
+        if ptr is not None and self.fail:
+            return -1
+        self.addr = ptr
+        return 0
+
+    def swglGetLastError(self):
+        return b"refused (test)"
+
+
+def _mirror_worker(rank, world, port, height, width, band, fail_rank, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    api = _FakeMirrorApi(fail=(rank == fail_rank))
+    try:
+        m = multigpu.SharedFrameMirror(api, dist, rank, world, width, height)
+    except RuntimeError:
+        if rank == 0:
+            q.put("refused")        # one rank could not register: every rank backs out together
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    frame = m.frame(height, width)
+    for r0, r1 in multigpu.rows_of_rank(height, rank, world, band):
+        frame[r0:r1] = rank + 1      # what the rank's raster kernels do through the mapping
+    dist.barrier()
+    if rank == 0:
+        want = np.zeros((height, width), np.uint32)
+        for r in range(world):
+            for r0, r1 in multigpu.rows_of_rank(height, r, world, band):
+                want[r0:r1] = r + 1
+        q.put("ok" if np.array_equal(frame, want) else "mismatch")
+    dist.barrier()
+    del frame
+    m.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank,expect", [(-1, "ok"), (1, "refused")])
+def test_shared_frame_mirror_world2_gloo(fail_rank, expect):
+    """The host-side half of swglSetSharedFrameMirror: one POSIX shared-memory segment, mapped by both
+    ranks, each writing its bands; a rank that cannot register it makes both back out."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mirror_worker, args=(r, 2, port, 200, 64, 1, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert got == expect
+
+
+def test_sharded_upload_chunking():
+    assert multigpu.ShardedUpload.divisible(16_085_792, 8) and multigpu.ShardedUpload.divisible(12_030_336, 8)
+    assert not multigpu.ShardedUpload.divisible(16_085_792 + 4, 8)
