@@ -84,3 +84,25 @@ def test_restatement_matches_fullsize_golden_c2(restatement):
     assert stats["tested"] == k["tested"] and stats["shaded"] == k["shaded"]
     assert full["C4"]["color_fnv"] == "56d0d4e1a9cd44f1" and full["C4"]["covered"] == 5202381   # K4
     assert full["C5"]["covered"] == 20795225                                                    # K5
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU path, oracle/_ref): one JSON line with the
+    keys the measurement contract names; C1 so that it takes a second."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "triangles/s" and d["unit"] == "triangles/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("C1")
