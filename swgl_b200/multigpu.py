@@ -168,14 +168,26 @@ class SharedFrameMirror:
         size = (self.nbytes + self.PAGE - 1) // self.PAGE * self.PAGE
         box = [None]
         if rank == 0:
-            box[0] = f"/dev/shm/swgl_b200_frame_{os.getpid()}"
-            with open(box[0], "wb") as f:
-                f.truncate(size)
+            path = f"/dev/shm/swgl_b200_frame_{os.getpid()}"
+            try:
+                fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, size)     # a shared-memory file system that is too small says so here, not by SIGBUS later
+                finally:
+                    os.close(fd)
+                box[0] = path
+            except OSError:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
         if dist is not None:
             dist.broadcast_object_list(box, src=0)
         self.path = box[0]
         self.map, self.addr, ok = None, 0, False
         try:
+            if self.path is None:
+                raise OSError("no shared segment")
             fd = os.open(self.path, os.O_RDWR)
             try:
                 self.map = mmap.mmap(fd, size)
@@ -212,7 +224,7 @@ class SharedFrameMirror:
                 self.map.close()
         except (BufferError, ValueError):
             pass                # a numpy view is still alive: the mapping goes with the process
-        if self.rank == 0:
+        if self.rank == 0 and self.path is not None:
             try:
                 os.unlink(self.path)
             except OSError:
