@@ -93,6 +93,7 @@ struct swgldev_ctx
 	Counters* ctr; Counters* h_ctr;      /* device counters, pinned snapshot */
 	cudaStream_t side;                   /* counter snapshots travel here, off the critical path */
 	cudaEvent_t setup_event;             /* set-up kernel of the last draw finished */
+	cudaEvent_t app_event;               /* "whatever is queued on the stream now" (swgldev_max_index_after_stream) */
 	cudaEvent_t ctr_event;
 	int ctr_pending;                     /* a snapshot copy is in flight for last_draw */
 
@@ -1279,7 +1280,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->peer_color = nullptr; c->rank = 0; c->n_ranks = 1; c->band_rows = 1;
 	c->shared_mirror = nullptr; c->shared_mirror_dev = nullptr; c->shared_mirror_bytes = 0;
 	c->clip = nullptr; c->cap_clip = 0; c->clip_xy = nullptr; c->cap_clip_xy = 0; c->vary = nullptr; c->cap_vary = 0;
-	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr;
+	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr; c->app_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
@@ -1315,6 +1316,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMalloc((void**)&c->tile_count, (ntiles + 1) * 4) == cudaSuccess
 	       && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->setup_event, cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->app_event, cudaEventDisableTiming) == cudaSuccess
 	       && cudaMalloc((void**)&c->ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->ctr_event, cudaEventDisableTiming) == cudaSuccess
@@ -1370,6 +1372,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->winner) cudaFree(c->winner);
 	if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
 	if (c->setup_event) cudaEventDestroy(c->setup_event);
+	if (c->app_event) cudaEventDestroy(c->app_event);
 	if (c->clip) cudaFree(c->clip);
 	if (c->clip_xy) cudaFree(c->clip_xy);
 	if (c->vary) cudaFree(c->vary);
@@ -1506,8 +1509,8 @@ uint32_t swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices, uin
 {
 	cudaSetDevice(c->device);
 	if (bytes < 4u) return 0;
-	if (cudaEventRecord(c->setup_event, c->stream) != cudaSuccess) return 0;      /* any event of the context will do: it is re-recorded by the next draw */
-	cudaStreamWaitEvent(c->upload, c->setup_event, 0);
+	if (cudaEventRecord(c->app_event, c->stream) != cudaSuccess) return 0;
+	cudaStreamWaitEvent(c->upload, c->app_event, 0);
 	queue_max_index(c, indices, bytes);
 	cudaStreamSynchronize(c->upload);
 	return *c->h_maxidx;

@@ -87,3 +87,23 @@ def test_object_id_conventions_without_device():
     assert api.glGenVertexArrays(1, C.byref(vao)) == 0 and vao.value >= 1
     buf = C.c_uint32(0)
     assert api.glGenBuffers(1, C.byref(buf)) == 0 and buf.value >= 1
+
+
+def test_extensions_are_safe_without_a_device_context():
+    """The round's extensions before glInit (or on a box without a GPU): no-ops with the documented
+    failure values, never a crash -- and never a CPU fallback."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("the context-less behaviour is checked on the CPU box")
+    api = swgl_b200.load()
+    word = (C.c_uint32 * 4)(1, 2, 3, 4)
+    api.swglBufferSubData(G.GL_ARRAY_BUFFER, 0, 16, C.cast(word, C.c_void_p))
+    api.swglBufferDeviceWritten(G.GL_ELEMENT_ARRAY_BUFFER)
+    assert api.swglGetBufferDevicePtr(G.GL_ARRAY_BUFFER) == 0
+    assert api.swglSetSharedFrameMirror(C.cast(word, C.c_void_p), 16) == -1
+    assert not api.swglHostAlloc(4096, 1)          # cudaHostAlloc needs a device: NULL, not malloc
+    api.swglHostFree(None)
+    assert not api.glGetFramePtr()
