@@ -272,10 +272,15 @@ def run_own(args):
         sharded = multigpu.ShardedUpload(api, dist, rank, world, torch.device("cuda", local))
 
     def e2e_step():
+        nonlocal sharded
         if sharded is not None:
-            sharded.upload(G.GL_ARRAY_BUFFER, verts)
-            sharded.upload(G.GL_ELEMENT_ARRAY_BUFFER, idx)
-        else:
+            try:
+                sharded.upload(G.GL_ARRAY_BUFFER, verts)
+                sharded.upload(G.GL_ELEMENT_ARRAY_BUFFER, idx)
+            except Exception as exc:      # the same call fails the same way on every rank: all fall back together
+                print(f"bench: sharded upload unavailable ({exc!r}); every rank uploads the whole arrays", file=sys.stderr)
+                sharded = None
+        if sharded is None:
             api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
             api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
         frame()
