@@ -2094,10 +2094,10 @@ int swgldev_set_shared_mirror(swgldev_ctx* c, void* host_ptr, uint64_t bytes)
 	if (!host_ptr) return 0;
 	if (bytes < (uint64_t)c->W * c->H * 4) { set_err(c, "swglSetSharedFrameMirror: the memory is smaller than the colour attachment", cudaSuccess); return -1; }
 	cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
-	if (e != cudaSuccess) { set_err(c, "cudaHostRegister (shared frame mirror)", e); return -1; }
+	if (e != cudaSuccess) { cudaGetLastError(); set_err(c, "cudaHostRegister (shared frame mirror)", e); return -1; }   /* do not leave the error for the next launch check */
 	void* d = nullptr;
 	e = cudaHostGetDevicePointer(&d, host_ptr, 0);
-	if (e != cudaSuccess) { cudaHostUnregister(host_ptr); set_err(c, "cudaHostGetDevicePointer (shared frame mirror)", e); return -1; }
+	if (e != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(host_ptr); set_err(c, "cudaHostGetDevicePointer (shared frame mirror)", e); return -1; }
 	c->shared_mirror = (uint32_t*)host_ptr; c->shared_mirror_dev = (uint32_t*)d; c->shared_mirror_bytes = bytes;
 	c->mirror_synced = 0;      /* the next swgldev_sync copies this rank's bands unless a cleared frame has been written through */
 	return 0;
