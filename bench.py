@@ -227,7 +227,9 @@ def run_own(args):
                 "kernel_us": stage_us[dom], "stage_us": stage_us,
                 "frame_algorithmic_bytes": scene.algorithmic_bytes(),
                 "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak,
-                "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12}
+                "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12,
+                "note": "HBM is the roofline the contract names; ncu shows the raster kernel SM-issue-bound "
+                        "(C4: 74 % issue-active, DRAM 4 % busy, profiles/r01_ncu_summary_c4.md, DESIGN.md section 4)"}
 
     # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
     def assembled_equals_single():
