@@ -51,6 +51,12 @@ typedef struct
 	int32_t  fpp;          /* channels per texel, 1..4 (swgl.c:2099-2102) */
 	int32_t  is_float;     /* 0: bytes, converted with /255.0f at sample time; 1: floats */
 	int32_t  wrap_s_repeat, wrap_t_repeat;
+	/* glGenerateMipmap chain (swgl.c:2122-2173), built by swgldev_build_mipmaps: 16 words of level
+	 * offsets (in floats, relative to the end of the header) followed by the levels as floats;
+	 * level k is (width >> (k + 1)) x (height >> (k + 1)).  0 = no chain. */
+	swgldev_ptr mips;
+	int32_t  n_mips;
+	int32_t  _pad;
 } swgldev_texture;
 
 struct swgl_ir_code;       /* swgl_ir.h */
@@ -128,6 +134,11 @@ uint32_t     swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices,
 /* swgldev_upload_overlapped() of element data and swgldev_max_index() of it, with a single wait
  * (swglBufferRespecify(GL_ELEMENT_ARRAY_BUFFER), the per-frame upload of the end-to-end step). */
 int          swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index);
+
+/* glGenerateMipmap (swgl.c:2122-2173): the 2x2 box chain of `base` as one allocation (layout: see
+ * swgldev_texture.mips); *n_levels = levels built (0: the base level is too small, nothing allocated).
+ * The chain is only sampled when the "mip_lod" option selects the defined LOD (swgl_b200.h). */
+swgldev_ptr  swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, int32_t* n_levels);
 
 /* glClear (swgl.c:3183-3214): rectangle is viewport ∩ framebuffer, already resolved. */
 int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,

@@ -22,6 +22,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libswgl_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libswgl_ref.so")
+# the same reference with rsqrt()'s `long` pun made 32-bit (oracle/ref_shim.c): the mip-map row's checker
+REF_LOD_SO = os.path.join(HERE, "_ref", "libswgl_ref_lod.so")
 
 
 def build(quiet: bool = True) -> None:
@@ -194,15 +196,16 @@ class Restatement:
 class Reference:
     """The unmodified reference, driven through its own API (swgl.h)."""
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
+    def __init__(self, defined_rsqrt: bool = False):
+        so = REF_LOD_SO if defined_rsqrt else REF_SO
+        if not os.path.exists(so):
             build()
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO)
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
         from swgl_b200 import gl as G
 
         self.G = G
-        self.lib = C.CDLL(REF_SO)
+        self.lib = C.CDLL(so)
         self.api = G.GLApi(self.lib)
         self.lib.swglref_depth_ptr.restype = C.POINTER(C.c_float)
         self.lib.swglref_fill.argtypes = [C.c_uint32, C.c_float]

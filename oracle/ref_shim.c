@@ -31,8 +31,24 @@ static void* swglref_padded_malloc(size_t n)
 }
 #define malloc(n) swglref_padded_malloc(n)
 
+/* Second build of the same file (oracle/Makefile, _ref/libswgl_ref_lod.so) for the mip-map row
+ * (SURVEY.md 8f n2): the reference's rsqrt() puns a 4-byte float through `long` (8 bytes on LP64,
+ * swgl.c:3240-3246), which is undefined behaviour -- in the plain build the level it feeds is never
+ * positive and no mip level is ever sampled.  `long` occurs nowhere else in swgl.c, so mapping it to a
+ * 32-bit integer for the span of the include turns rsqrt() into the defined routine its author meant
+ * (0x5f3759df with a 32-bit pun, three Newton steps) without editing a line of the reference.  Every
+ * system header swgl.c pulls in has been included above, guarded, before the macro exists. */
+#ifdef SWGLREF_DEFINED_RSQRT
+#include <stddef.h>
+#include <memory.h>
+#define long int32_t
+#endif
+
 #include "swgl.c" /* resolved via -I/root/reference; the reference, verbatim */
 
+#ifdef SWGLREF_DEFINED_RSQRT
+#undef long
+#endif
 #undef malloc
 
 /* ---- accessors the tests need (the reference has no depth readback) ---- */

@@ -108,6 +108,7 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_mip_lod;                     /* sample mip chains with the defined per-triangle LOD (default 0: bug-compatible, base level) */
 	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
 	int64_t selftest_mismatches;
@@ -174,6 +175,28 @@ __global__ void k_fill_fb(uint32_t* __restrict__ color, float* __restrict__ dept
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (; i < n; i += stride) { color[i] = word; depth[i] = d; }
+}
+
+/* ---- glGenerateMipmap (swgl.c:2129-2171): one level of the 2x2 box chain, a thread per texel.  The
+ * previous level is addressed with a row stride of 2 * CurWidth texels, as in the reference (for an odd
+ * width that is NOT the previous level's own stride); the sum starts from 0.0f and adds the four texels
+ * in the reference's order (sY outer, sX inner), then divides by 4.0f. ---- */
+__global__ void __launch_bounds__(256) k_mipmap_box(const void* __restrict__ prev, int prev_is_u8, const float* __restrict__ lut255,
+                                                    int fpp, int cw, int ch, float* __restrict__ out)
+{
+	const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+	if (x >= cw || y >= ch) return;
+	for (int k = 0; k < fpp; k++)
+	{
+		float acc = 0.0f;
+		for (int sy = 0; sy < 2; sy++)
+			for (int sx = 0; sx < 2; sx++)
+			{
+				const size_t at = ((size_t)(x * 2 + sx) + (size_t)(y * 2 + sy) * (size_t)cw * 2u) * (size_t)fpp + (size_t)k;
+				acc += prev_is_u8 ? lut255[((const uint8_t*)prev)[at]] : ((const float*)prev)[at];
+			}
+		out[((size_t)x + (size_t)y * (size_t)cw) * (size_t)fpp + (size_t)k] = acc / 4.0f;
+	}
 }
 
 /* ---- largest index of an element buffer (decides how many vertices an indexed draw shades) ---- */
@@ -286,7 +309,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 				fetch_floats(P, (unsigned long long)vid, P.fetch[f].src_offset, P.fetch[f].stride, n, tmp);
 				for (uint32_t k = 0; k < n; k++) V[P.fetch[f].dst_word + k] = __float_as_uint(tmp[k]);
 			}
-		ir_execute(P.vs_ops, P.vs_nops, V, P);
+		ir_execute(P.vs_ops, P.vs_nops, V, P, 0.0f);   /* texture() in a vertex shader reads the base level */
 		pos = make_float4(__uint_as_float(V[P.pos_word]), __uint_as_float(V[P.pos_word + 1]),
 		                  __uint_as_float(V[P.pos_word + 2]), __uint_as_float(V[P.pos_word + 3]));
 		for (uint32_t k = 0; k < P.n_varying; k++)
@@ -387,6 +410,14 @@ __device__ __forceinline__ Prim load_prim(const DrawParams& P, uint32_t entry)
 	tri_vertices(P, entry >> 2, r.v[0], r.v[1], r.v[2], r.vid[0], r.vid[1], r.vid[2]);
 	r.band = 0xffffffffu;
 	return r;
+}
+
+/* MipMapLevel of the primitive behind a list entry (swgl.c:3316: computed from the snapped vertices in
+ * submission order, before the y sort); only draws with the mip_lod option call it */
+__device__ __noinline__ float prim_lod(const DrawParams& P, uint32_t entry)
+{
+	const Prim q = load_prim(P, entry);
+	return mip_level(q.v[0].x, q.v[0].y, q.v[1].x, q.v[1].y, q.v[2].x, q.v[2].y);
 }
 
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
@@ -742,6 +773,7 @@ struct FragIn
 	 * (stride 1 = straight from the packed records, SWGL_BATCH = staged in shared memory) */
 	const float* a; const float* b; const float* c;
 	uint32_t stride;
+	float lod;                    /* generic shape, mip_lod draws: MipMapLevel of the primitive (swgl.c:3316) */
 };
 
 /* InterpolateLinearEx (swgl.c:3270-3297): a*u + b*v + c*w, left to right */
@@ -781,7 +813,7 @@ __device__ __forceinline__ float4 run_fragment(const DrawParams& P, const FragIn
 			const uint32_t s = P.varying[k].slot + j;
 			V[P.varying[k].fs_word + j] = __float_as_uint(va[s] * f.u + vb[s] * f.v + vc[s] * f.w);
 		}
-	ir_execute(P.fs_ops, P.fs_nops, V, P);
+	ir_execute(P.fs_ops, P.fs_nops, V, P, f.lod);
 	float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 	for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
 	return make_float4(o[0], o[1], o[2], o[3]);
@@ -1089,6 +1121,7 @@ __global__ void __launch_bounds__(SWGL_RASTER_THREADS) k_raster(const __grid_con
 							n_shaded++;
 							f.vid0 = S.vid[0][j]; f.vid1 = S.vid[1][j]; f.vid2 = S.vid[2][j];
 							f.a = &S.sv[0][j]; f.b = &S.sv[4][j]; f.c = &S.sv[8][j]; f.stride = SWGL_BATCH;
+							f.lod = (FS == SWFS_GENERIC && P.mip_lod) ? prim_lod(P, ids[base + j]) : 0.0f;
 							const float4 o = run_fragment<FS>(P, f);
 							col[kk] = blend_pack(o.x, o.y, o.z, o.w, col[kk]);
 							dirty = true;
@@ -1196,7 +1229,7 @@ __global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ Dr
 		for (uint32_t k = 0; k < P.n_varying; k++)
 			for (uint32_t j = 0; j < P.varying[k].n_floats; j++)
 				V[P.varying[k].fs_word + j] = __float_as_uint(vv[P.varying[k].slot + j]);
-		ir_execute(P.fs_ops, P.fs_nops, V, P);
+		ir_execute(P.fs_ops, P.fs_nops, V, P, 0.0f);   /* points: base level (the reference keeps the last triangle's level) */
 		for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
 	}
 	const float r = RMIN(RMAX(o[0], 0.0f), 1.0f), g = RMIN(RMAX(o[1], 0.0f), 1.0f);
@@ -1285,7 +1318,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -1407,9 +1440,15 @@ swgldev_ptr swgldev_alloc(swgldev_ctx* c, uint64_t bytes)
 	return (swgldev_ptr)(uintptr_t)p;
 }
 
+static int settle_last_draw(swgldev_ctx* c);
+
 void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 {
 	void* q = (void*)(uintptr_t)p;
+	/* an overflowed draw is re-issued from the raw pointers it was launched with: resolve it while
+	 * the memory it reads is still there */
+	cudaSetDevice(c->device);
+	settle_last_draw(c);
 	for (size_t i = 0; i < c->allocations.size(); i++)
 		if (c->allocations[i] == q)
 		{
@@ -1422,10 +1461,11 @@ void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 		}
 }
 
-static int settle_last_draw(swgldev_ctx* c);
-
 int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes)
 {
+	/* ... and before the contents it reads are replaced */
+	cudaSetDevice(c->device);
+	if (settle_last_draw(c)) return -1;
 	/* the caller may free `src` on return (swgl.c:3142-3144), so the copy completes here;
 	 * pinned sources go at full PCIe rate, pageable ones through the driver's staging */
 	CK(cudaMemcpyAsync((void*)(uintptr_t)dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -1643,12 +1683,65 @@ int swgldev_sync(swgldev_ctx* c)
 	if (flush_clear(c)) return -1;
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->copy_inflight) CK(cudaStreamSynchronize(c->copy));
-	if (c->shared_mirror && !c->mirror_synced && !c->color_exposed)
+	if (c->shared_mirror && !c->mirror_synced)
 	{
+		/* a handed-out device pointer (color_exposed) only means the copy has to be repeated every time:
+		 * the attachment may change behind the library's back */
 		if (flush_owned_bands(c)) return -1;
-		c->mirror_synced = 1;
+		c->mirror_synced = c->color_exposed ? 0 : 1;
 	}
 	return 0;
+}
+
+swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, int32_t* n_levels)
+{
+	cudaSetDevice(c->device);
+	*n_levels = 0;
+	if (!base->data || base->fpp < 1 || base->fpp > 4) return 0;
+	/* levels while CurWidth + CurHeight > 4, halving with integer division (swgl.c:2129-2135, 2167-2168) */
+	uint32_t off[16];
+	int cw = base->width / 2, ch = base->height / 2, n = 0;
+	size_t floats = 0;
+	while (cw + ch > 4 && n < 16)
+	{
+		if (floats > 0xffffffffull) { set_err(c, "glGenerateMipmap: chain too large", cudaSuccess); return 0; }
+		off[n++] = (uint32_t)floats;
+		floats += (size_t)cw * (size_t)ch * (size_t)base->fpp;
+		cw /= 2; ch /= 2;
+	}
+	if (n == 0) return 0;
+	for (int k = n; k < 16; k++) off[k] = 0;
+	const swgldev_ptr chain = swgldev_alloc(c, 64 + floats * 4 + 4);
+	if (!chain) return 0;
+	if (cudaMemcpyAsync((void*)(uintptr_t)chain, off, 64, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+	{
+		set_err(c, "glGenerateMipmap: upload of the level table", cudaGetLastError());
+		swgldev_free(c, chain);
+		return 0;
+	}
+	float* data = (float*)(uintptr_t)(chain + 64);
+	const void* prev = (const void*)(uintptr_t)base->data;
+	int prev_u8 = base->is_float ? 0 : 1;
+	cw = base->width / 2; ch = base->height / 2;
+	for (int k = 0; k < n; k++)
+	{
+		if (cw > 0 && ch > 0)
+		{
+			k_mipmap_box<<<dim3(((uint32_t)cw + 255u) / 256u, (uint32_t)ch), 256, 0, c->stream>>>(prev, prev_u8, c->lut255, base->fpp, cw, ch, data + off[k]);
+			c->n_launches++;
+		}
+		prev = data + off[k]; prev_u8 = 0;
+		cw /= 2; ch /= 2;
+	}
+	/* off[] is on this stack: the copy must have read it before returning */
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+	{
+		set_err(c, "glGenerateMipmap: k_mipmap_box", cudaGetLastError());
+		swgldev_free(c, chain);
+		return 0;
+	}
+	*n_levels = n;
+	return chain;
 }
 
 int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
@@ -1788,7 +1881,11 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 		P.tex[u].data = (const void*)(uintptr_t)d->tex[u].data;
 		P.tex[u].w = d->tex[u].width; P.tex[u].h = d->tex[u].height; P.tex[u].fpp = d->tex[u].fpp;
 		P.tex[u].is_float = d->tex[u].is_float; P.tex[u].rep_s = d->tex[u].wrap_s_repeat; P.tex[u].rep_t = d->tex[u].wrap_t_repeat;
+		P.tex[u].mips = (const uint32_t*)(uintptr_t)d->tex[u].mips; P.tex[u].n_mips = d->tex[u].mips ? d->tex[u].n_mips : 0;
+		if (c->opt_mip_lod && P.tex[u].n_mips > 0) P.mip_lod = 1u;
 	}
+	/* the per-triangle LOD lives in the generic fragment path: a texture-shaped shader takes it too */
+	if (P.mip_lod && P.fs_kind == SWFS_TEXTURE) P.fs_kind = SWFS_GENERIC;
 	if (d->vs_image) memcpy(P.vs_image, d->vs_image, 4u * d->vs_words);
 	if (d->fs_image) memcpy(P.fs_image, d->fs_image, 4u * d->fs_words);
 	P.count_fragments = (uint32_t)c->opt_count_fragments;
@@ -2136,6 +2233,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "raster_path")) c->opt_raster_path = (int)value;
 	else if (!strcmp(name, "diag")) c->opt_diag = (int)value;
 	else if (!strcmp(name, "lean_prims")) c->opt_lean_prims = (int)value;
+	else if (!strcmp(name, "mip_lod")) c->opt_mip_lod = value ? 1 : 0;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
@@ -2172,6 +2270,7 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "count_fragments")) return c->opt_count_fragments;
 	if (!strcmp(name, "raster_path")) return c->opt_raster_path;
 	if (!strcmp(name, "host_mirror")) return c->opt_host_mirror;
+	if (!strcmp(name, "mip_lod")) return c->opt_mip_lod;
 	if (!strcmp(name, "mirror_synced")) return c->mirror_synced;
 	if (!strcmp(name, "wt_draws")) return (int64_t)c->wt_draws;
 	if (!strcmp(name, "last_raster_path")) return c->last_raster_path;

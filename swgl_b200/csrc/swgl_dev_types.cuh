@@ -65,6 +65,8 @@ struct DevTex
 {
 	const void* data;
 	int32_t w, h, fpp, is_float, rep_s, rep_t;
+	const uint32_t* mips;       /* glGenerateMipmap chain: 16 offset words, then float levels (swgldev_texture.mips) */
+	int32_t n_mips, _pad;
 };
 
 struct ClearParams
@@ -117,6 +119,7 @@ struct DrawParams
 	/* fused clear */
 	ClearParams clear;
 	uint32_t count_fragments;
+	uint32_t mip_lod;           /* 1: textures with a mip chain are sampled with the per-triangle LOD (defined rsqrt) */
 	uint32_t diag;              /* development only: skip parts of kernels to attribute time */
 	/* initial variable files (uniform values) for the generic evaluator */
 	uint32_t vs_image[SWGL_MAX_VAR_WORDS];

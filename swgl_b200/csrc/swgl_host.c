@@ -76,6 +76,7 @@ typedef struct
 	swgldev_ptr data;
 	int32_t width, height, fpp, is_float;
 	uint32_t wrap_s, wrap_t;
+	swgldev_ptr mips;            /* glGenerateMipmap chain (swgldev_build_mipmaps), 0 = none */
 	int32_t n_mipmaps;
 } gl_texture;
 
@@ -540,7 +541,11 @@ void glTexImage2D(GLenum target, GLint level, GLint internalformat, GLsizei widt
 	(void)level;
 	if (!data || border != 0 || target != GL_TEXTURE_2D || !G.active_texture || !G.dev) return;
 	gl_texture* t = G.active_texture;
-	if (t->data) { swgldev_free(G.dev, t->data); t->data = 0; t->n_mipmaps = 0; }
+	if (t->data) { swgldev_free(G.dev, t->data); t->data = 0; }
+	/* the reference keeps the old chain (MipMaps is never cleared, swgl.c:2094) and so keeps sampling the old
+	 * image's levels; not reproduced: the chain goes with the image it was built from */
+	if (t->mips) { swgldev_free(G.dev, t->mips); t->mips = 0; }
+	t->n_mipmaps = 0;
 	if (internalformat != (GLint)format) return; /* the reference returns here with the old data freed */
 	if (internalformat == GL_RGBA) t->fpp = 4;
 	if (internalformat == GL_RGB) t->fpp = 3;
@@ -559,16 +564,25 @@ void glTexImage2D(GLenum target, GLint level, GLint internalformat, GLsizei widt
 
 void glGenerateMipmap(GLenum target)
 {
-	if (target != GL_TEXTURE_2D || !G.active_texture || !G.active_texture->data) return;
-	/* The reference builds a 2x2-box chain here (swgl.c:2129-2171) that is only ever read when
+	if (target != GL_TEXTURE_2D || !G.active_texture || !G.active_texture->data || !G.dev) return;
+	/* The reference builds a 2x2-box chain here (swgl.c:2129-2171) that is only read when
 	 * MipMapLevel > 0 (swgl.c:2527).  MipMapLevel is 40 / DistBetweenPointAndLine(...) and that
 	 * distance is multiplied by rsqrt(), whose 8-byte pun of a 4-byte float (swgl.c:3246) folds
 	 * the low bit of the adjacent stack word -- rsqrt's own return address -- into the sign:
 	 * in the compiled reference (gcc -O2, oracle/_ref) that bit is 1, rsqrt is negative for every
-	 * input, MipMapLevel is never positive and the base level is always sampled.  Bug-compatible
-	 * behaviour is therefore: accept the call, keep sampling level 0
-	 * (tests/test_next_rows_gpu.py compares against the compiled reference). */
-	G.active_texture->n_mipmaps = 1;
+	 * input, MipMapLevel is never positive and the base level is always sampled.  That is the
+	 * DEFAULT here too (tests/test_next_rows_gpu.py compares against the compiled reference).
+	 * The chain is built all the same (k_mipmap_box); swglSetOption("mip_lod", 1) selects the
+	 * defined variant -- rsqrt with a 32-bit pun -- in which the chain is sampled with the
+	 * per-triangle level (tests/test_mipmap_gpu.py, against the reference built the same way). */
+	gl_texture* t = G.active_texture;
+	if (t->n_mipmaps > 0) return;   /* a second call appends levels of the smallest level in the reference: not reproduced */
+	swgldev_texture base;
+	memset(&base, 0, sizeof(base));
+	base.data = t->data; base.width = t->width; base.height = t->height; base.fpp = t->fpp; base.is_float = t->is_float;
+	int32_t n = 0;
+	t->mips = swgldev_build_mipmaps(G.dev, &base, &n);
+	t->n_mipmaps = t->mips ? n : 0;
 }
 
 /* ---------------------------------------------------------------------------------------- */
@@ -816,6 +830,7 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 		d.tex[u].data = t->data; d.tex[u].width = t->width; d.tex[u].height = t->height;
 		d.tex[u].fpp = t->fpp; d.tex[u].is_float = t->is_float;
 		d.tex[u].wrap_s_repeat = t->wrap_s == GL_REPEAT; d.tex[u].wrap_t_repeat = t->wrap_t == GL_REPEAT;
+		d.tex[u].mips = t->mips; d.tex[u].n_mips = t->n_mipmaps;
 	}
 
 	if (mode == GL_POINTS) swgldev_draw_points(G.dev, &d);

@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 						fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 						fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 						fi.stride = 1;
+						fi.lod = (FS == SWFS_GENERIC && P.mip_lod) ? mip_level(a.x, a.y, b.x, b.y, c.x, c.y) : 0.0f;
 						o = clamp_color(run_fragment<FS>(P, fi));
 						shaded_early = true;
 					}
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_co
 								fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 								fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 								fi.stride = 1;
+								fi.lod = (FS == SWFS_GENERIC && P.mip_lod) ? mip_level(q_prim->v[0].x, q_prim->v[0].y, q_prim->v[1].x, q_prim->v[1].y, q_prim->v[2].x, q_prim->v[2].y) : 0.0f;
 								o = clamp_color(run_fragment<FS>(P, fi));
 							}
 							S.color[pix] = blend_pack_lut(o.x, o.y, o.z, o.w, S.color[pix], S.lut);

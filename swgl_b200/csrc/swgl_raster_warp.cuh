@@ -184,6 +184,7 @@ __device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, flo
 	fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 	fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 	fi.stride = 1;
+	fi.lod = (FS == SWFS_GENERIC && P.mip_lod) ? mip_level(q->v[0].x, q->v[0].y, q->v[1].x, q->v[1].y, q->v[2].x, q->v[2].y) : 0.0f;
 	return clamp_color(run_fragment<FS>(P, fi));
 }
 
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 							fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 							fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 							fi.stride = 1;
+							fi.lod = P.mip_lod ? prim_lod(P, __float_as_uint(ids.w)) : 0.0f;
 							col = run_fragment<FS>(P, fi);
 						}
 						col = clamp_color(col);

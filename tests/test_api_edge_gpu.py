@@ -266,3 +266,32 @@ def test_extreme_coordinates_and_w(gpu_api, reference, seed, path):
         api.glDrawArrays(G.GL_TRIANGLES, 0, len(v))
     a, b = _both(gpu_api, reference, script)
     _assert_same(a, b, 100)
+
+
+def test_texture_respecified_right_after_a_draw_that_overflowed(gpu_api, reference):
+    """A draw whose tile lists overflowed is dropped on the device and re-issued later from the
+    pointers it was launched with: glTexImage2D on the texture it samples (free + upload) must
+    resolve it first (the reference has drawn with the old texels by then)."""
+    ta = S.lcg_texture(32, seed=9)
+    tb = 255 - ta
+    fs = "in vec4 vCol;\nuniform sampler2D tex;\nout vec4 FragColor;\nvoid main()\n{\nFragColor = texture(tex,vCol.xy);\n}\n"
+
+    def script(api):
+        if api is gpu_api:
+            api.swglSetOption(b"bin_cap", 4)         # every list overflows on the first attempt
+        p, _, _ = _program(api, S.VS_PASSTHROUGH, fs)
+        api.glUseProgram(p)
+        _vao(api, VERTS, [(0, 4, 0), (1, 4, 16)])
+        t = C.c_uint32(0)
+        api.glGenTextures(1, C.byref(t))
+        api.glActiveTexture(G.GL_TEXTURE0)
+        api.glBindTexture(G.GL_TEXTURE_2D, t.value)
+        api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 32, 32, 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(ta))
+        api.glUniform1i(api.glGetUniformLocation(p, b"tex"), 0)
+        api.glClear(3)
+        api.glDrawArrays(G.GL_TRIANGLES, 0, len(VERTS))
+        # same size: the allocator is likely to hand the freed block straight back
+        api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 32, 32, 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(tb))
+    a, b = _both(gpu_api, reference, script)
+    assert gpu_api.swglGetOption(b"bin_cap") > 4
+    _assert_same(a, b, 100)

@@ -94,6 +94,32 @@ def test_shared_frame_mirror_assembles_the_frame_in_host_memory(gpu_api, n_ranks
     assert np.array_equal(img, full[0])
 
 
+def test_shared_frame_mirror_after_the_device_pointer_was_handed_out(gpu_api):
+    """swglGetColorDevicePtr switches write-through off for good (the caller may write the attachment);
+    glGetFramePtr must then copy the rank's bands into the shared segment every time instead of
+    returning a stale frame."""
+    scene = S.config(2)
+    api = gpu_api
+    full = gpu_render(api, scene)
+    api.glInit(scene.width, scene.height)
+    assert api.swglGetColorDevicePtr() != 0
+    mirror = multigpu.SharedFrameMirror(api, None, 0, 1, scene.width, scene.height)
+    st = G.setup_scene(api, scene, indexed=True, init=False)
+    for _ in range(2):                               # the second frame must be copied again
+        api.swglFillFramebuffer(0, C.c_float(0.0))
+        api.glClear(3)
+        api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
+        ptr = api.glGetFramePtr()
+        assert C.cast(ptr, C.c_void_p).value == mirror.addr
+        assert api.swglGetOption(b"wt_draws") == 0
+        img = mirror.frame(scene.height, scene.width).copy()
+        assert np.array_equal(img, full[0])
+        mirror.frame(scene.height, scene.width)[:] = 0
+    assert api.swglSetSharedFrameMirror(None, 0) == 0
+    mirror.active = False
+    mirror._unmap()
+
+
 def test_buffer_respecify_streams_new_geometry(gpu_api, restatement):
     """swglBufferRespecify (extension) replaces buffer contents; glBufferData ignores a second
     specification like the reference does (swgl.c:3140)."""
