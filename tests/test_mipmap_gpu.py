@@ -73,11 +73,11 @@ def _check(a, b):
 @pytest.mark.parametrize("grid,tex", [(24, "lcg1024"), (9, "lcg1024"), (60, "odd")])
 def test_mip_chain_with_defined_lod_matches_the_reference_built_the_same_way(gpu_api, reference_lod, grid, tex, path):
     """Texture-shaped shader (the LOD moves it onto the generic fragment path): small, medium and large
-    triangles pick different levels; the odd-sized float RGB texture exercises the reference's 2*CurWidth
+    triangles pick different levels; the odd-sized float texture exercises the reference's 2*CurWidth
     row stride in the box filter and CLAMP addressing of the levels."""
     scene = S.grid_mesh(grid, W, H, textured=True)
     rng = np.random.default_rng(5)
-    odd = rng.uniform(0.0, 1.0, (77, 93, 3)).astype(np.float32)
+    odd = rng.uniform(0.0, 1.0, (77, 93, 4)).astype(np.float32)   # RGBA: an RGB texture reads alpha 0 and blends to nothing
     frames = {}
     for mip in (False, True):
         def script(api, mip=mip):
@@ -87,7 +87,7 @@ def test_mip_chain_with_defined_lod_matches_the_reference_built_the_same_way(gpu
                 api.glGenTextures(1, C.byref(t))
                 api.glBindTexture(G.GL_TEXTURE_2D, t.value)
                 api.glTexParameteri(G.GL_TEXTURE_2D, G.GL_TEXTURE_WRAP_S, G.GL_CLAMP)
-                api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGB, 93, 77, 0, G.GL_RGB, G.GL_FLOAT, _ptr(odd))
+                api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 93, 77, 0, G.GL_RGBA, G.GL_FLOAT, _ptr(odd))
             if mip:
                 api.glGenerateMipmap(G.GL_TEXTURE_2D)
             api.glClear(3)
