@@ -34,6 +34,13 @@ void swglFinish(void);
  * diagnostics land here; the reference-compatible entry points keep their silent returns. */
 const char* swglGetLastError(void);
 
+/* Shaders outside the built-in shapes (pass-through / matrix vertex shader, varying / texture fragment
+ * shader) are turned into kernels at run time, at the first draw that uses them (about a second, once
+ * per program and vertex layout per process).  This compiles the kernels of the program in use with the
+ * bound vertex array now.  Without a device the code is generated and compiled but not loaded.
+ * Returns 0 on success (or nothing to compile), -1 on failure (swglGetLastError). */
+int swglPrecompileProgram(void);
+
 /* Fragment / primitive counters of the last draw (synchronises). */
 void swglGetStats(swglStats* out);
 

@@ -12,8 +12,10 @@
 #ifndef SWGL_DEV_H
 #define SWGL_DEV_H
 
+#ifndef __CUDACC_RTC__   /* NVRTC (run-time compiled shader kernels) brings its own fixed-width types */
 #include <stdint.h>
 #include <stddef.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -108,6 +110,7 @@ typedef struct
 	uint64_t bands;            /* band-entry records */
 } swgldev_stats;
 
+#ifndef __CUDACC_RTC__   /* host entry points: not part of a run-time compiled kernel's translation unit */
 /* context ------------------------------------------------------------------------------ */
 /* glInit (swgl.c:3713-3736): device = CUDA ordinal, or -1 for the current / LOCAL_RANK one. */
 swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height);
@@ -146,6 +149,11 @@ int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word,
 
 /* glDrawArrays(GL_TRIANGLES) / glDrawElements (swgl.c:3609-3710 + DrawTriangle 3314-3473). */
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d);
+
+/* Shaders outside the built-in shapes are compiled to kernels at run time (NVRTC, swgl_jit.cpp) on the
+ * first draw that uses them; this does it ahead of that draw.  `c` may be NULL (no device): the code is
+ * generated and compiled but not loaded.  0 = nothing to compile or compiled; -1 = failed, reason in msg. */
+int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t msg_len);
 
 /* glDrawArrays(GL_POINTS) (swgl.c:3496-3608): one pixel per vertex, x scaled by VH/2 (sic), no
  * near clip, no depth test, no blend, no Y flip; the last point submitted to a pixel wins. */
@@ -186,6 +194,7 @@ void        swgldev_ipc_close(swgldev_ctx* c, swgldev_ptr p);
 /* tuning / test hooks */
 void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value);
 int64_t swgldev_get_option(swgldev_ctx* c, const char* name);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

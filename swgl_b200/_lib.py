@@ -34,6 +34,7 @@ EXTENSION_EXPORTS = {
     "swglSetDevice": (None, [C.c_int]),
     "swglGetStream": (C.c_void_p, []),
     "swglGetColorDevicePtr": (C.c_uint64, []),
+    "swglPrecompileProgram": (C.c_int, []),
     "swglGetDepthDevicePtr": (C.c_uint64, []),
     "swglFillFramebuffer": (None, [C.c_uint32, C.c_float]),
     "swglBufferRespecify": (None, [C.c_uint32, C.c_uint32, C.c_void_p]),

@@ -36,7 +36,8 @@
 #include <map>
 #include <vector>
 
-#include "swgl_dev_math.cuh"
+#include "swgl_dev_common.cuh"
+#include "swgl_jit.h"
 
 /* ========================================================================================
  * context
@@ -108,6 +109,9 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_jit;                         /* compile generic shaders to kernels at run time (default 1; 0: on-device interpreter) */
+	int jit_failed;                      /* a compilation failed: reported once, the interpreter draws */
+	int last_vs_kind, last_fs_kind;      /* of the last triangle draw, as launched */
 	int opt_mip_lod;                     /* sample mip chains with the defined per-triangle LOD (default 0: bug-compatible, base level) */
 	size_t opt_bin_limit;
 	uint64_t n_launches;                 /* kernels launched since creation */
@@ -271,162 +275,7 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t n, uint64_t 
 	if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
-__device__ __forceinline__ float4 to_screen(const float4& p, const DrawParams& P)
-{
-	/* swgl.c:3685-3691: int <- x / w * (VW/2) + (VW/2) + VX, stored back as float */
-	int X = cvt_x86((fdiv(p.x, p.w) * P.hw + P.hw) + P.fvx);
-	int Y = cvt_x86((fdiv(p.y, p.w) * P.hh + P.hh) + P.fvy);
-	return make_float4((float)X, (float)Y, p.z, p.w);
-}
-
-/* ---- vertex stage (swgl.c:3618-3666) ---- */
-template <int VS>
-__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawParams P)
-{
-	uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	cudaTriggerProgrammaticLaunchCompletion();   /* the set-up kernel may start loading its indices */
-	if (v == 0 && blockIdx.x == 0)
-	{
-		/* per-draw counters: this kernel is the first of the draw */
-		P.ctr->band_cursor = 0; P.ctr->max_list = 0; P.ctr->overflow = 0; P.ctr->prims_out = 0; P.ctr->pair_total = 0ull;
-	}
-	if (v < SWGL_CTR_SLOTS && blockIdx.x == 0) { P.ctr->tested[v] = 0ull; P.ctr->shaded[v] = 0ull; }
-	if (v >= P.n_shade) return;
-	/* glDrawArrays: stream vertex first + v;  glDrawElements: unique vertex v */
-	long long vid = P.ibo ? (long long)v : (long long)P.first + (long long)v;
-	float4 pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	float* vout = P.vary + (size_t)v * P.nvf;
-
-	if (VS == SWVS_GENERIC)
-	{
-		uint32_t V[SWGL_MAX_VAR_WORDS];
-		for (uint32_t k = 0; k < P.vs_words; k++) V[k] = P.vs_image[k];
-		if (vid >= 0)
-			for (uint32_t f = 0; f < P.n_fetch; f++)
-			{
-				float tmp[16];
-				uint32_t n = P.fetch[f].n_floats;
-				fetch_floats(P, (unsigned long long)vid, P.fetch[f].src_offset, P.fetch[f].stride, n, tmp);
-				for (uint32_t k = 0; k < n; k++) V[P.fetch[f].dst_word + k] = __float_as_uint(tmp[k]);
-			}
-		ir_execute(P.vs_ops, P.vs_nops, V, P, 0.0f);   /* texture() in a vertex shader reads the base level */
-		pos = make_float4(__uint_as_float(V[P.pos_word]), __uint_as_float(V[P.pos_word + 1]),
-		                  __uint_as_float(V[P.pos_word + 2]), __uint_as_float(V[P.pos_word + 3]));
-		for (uint32_t k = 0; k < P.n_varying; k++)
-			for (uint32_t j = 0; j < P.varying[k].n_floats; j++)
-				vout[P.varying[k].slot + j] = __uint_as_float(V[P.varying[k].vs_word + j]);
-	}
-	else
-	{
-		float a[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-		if (vid >= 0) fetch_floats(P, (unsigned long long)vid, P.pos_src_offset, P.pos_src_stride, P.pos_src_floats, a);
-		if (VS == SWVS_PASS) pos = make_float4(a[0], a[1], a[2], a[3]);
-		else
-		{   /* MatMulMat4Vec (swgl.c:758-768), left to right, no FMA */
-			const float* m = P.pos_matrix;
-			pos.x = m[0] * a[0] + m[1] * a[1] + m[2] * a[2] + m[3] * a[3];
-			pos.y = m[4] * a[0] + m[5] * a[1] + m[6] * a[2] + m[7] * a[3];
-			pos.z = m[8] * a[0] + m[9] * a[1] + m[10] * a[2] + m[11] * a[3];
-			pos.w = m[12] * a[0] + m[13] * a[1] + m[14] * a[2] + m[15] * a[3];
-		}
-		for (uint32_t k = 0; k < P.n_varying; k++)
-		{
-			float t[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-			if (vid >= 0) fetch_floats(P, (unsigned long long)vid, P.varying[k].src_offset, P.varying[k].src_stride, P.varying[k].src_floats, t);
-			for (uint32_t j = 0; j < P.varying[k].n_floats; j++) vout[P.varying[k].slot + j] = t[j];
-		}
-	}
-	/* divide + viewport snap here, once per vertex (swgl.c:3685-3691 does it per triangle corner);
-	 * the clip-space x, y are kept for triangles that cross the near plane */
-	P.clip[v] = to_screen(pos, P);
-	P.clip_xy[v] = make_float2(pos.x, pos.y);
-}
-
-/* primitive 2t+k (k = 1: the second triangle the near clipper makes of input triangle t, rare) */
-__device__ __forceinline__ Prim* prim_at(const DrawParams& P, uint32_t pid)
-{
-	return ((pid & 1u) ? P.prims2 : P.prims) + (pid >> 1);
-}
-
-/* The three snapped vertices of input triangle t and their varying records: stream positions 3t,
- * 3t+1, 3t+2 (a trailing partial triangle is still drawn, swgl.c:3611), through the element buffer
- * for glDrawElements; an index past the shaded range reads as a zero clip-space vertex. */
-template <bool WAIT_FOR_VERTEX_KERNEL = false>
-__device__ __forceinline__ void tri_vertices(const DrawParams& P, uint32_t t, float4& p0, float4& p1, float4& p2,
-                                             uint32_t& s0, uint32_t& s1, uint32_t& s2)
-{
-	s0 = 3u * t; s1 = s0 + 1u; s2 = s0 + 2u;
-	if (P.ibo)
-	{
-		const unsigned long long at = (unsigned long long)(long long)P.first + s0;
-		s0 = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
-		s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
-		s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
-	}
-	/* k_setup_bin is launched while the vertex kernel drains (programmatic dependent launch): the
-	 * indices above do not depend on it, everything below does */
-	if (WAIT_FOR_VERTEX_KERNEL) cudaGridDependencySynchronize();
-	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
-	p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
-	p2 = (s2 < P.n_shade) ? P.clip[s2] : to_screen(zero, P);
-}
-
-/* A tile-list entry is (primitive id << 1) | has_record.  Short, unclipped primitives of a draw that
- * goes to the warp rasteriser have no record: the consumer gathers the three vertices through the
- * element buffer again (the per-vertex data is shared by the neighbouring triangles and stays in
- * cache) instead of the set-up kernel writing 64 bytes per triangle. */
-/* Same, as three vertex addresses: the vertex loads and everything behind them are shared by both
- * kinds of entry.  A record-less entry always has its three indices inside the shaded range (the
- * set-up kernel writes a record otherwise). */
-struct PrimRef { const float4* a; const float4* b; const float4* c; uint32_t vid0, vid1, vid2, band; };
-__device__ __forceinline__ PrimRef prim_ref(const DrawParams& P, uint32_t entry)
-{
-	PrimRef r;
-	if (entry & 1u)
-	{
-		const Prim* q = prim_at(P, entry >> 1);
-		const uint4 m = *(const uint4*)q->vid;
-		r.a = q->v; r.b = q->v + 1; r.c = q->v + 2;
-		r.vid0 = m.x; r.vid1 = m.y; r.vid2 = m.z; r.band = m.w;
-		return r;
-	}
-	const uint32_t s = 3u * (entry >> 2);
-	r.vid0 = s; r.vid1 = s + 1u; r.vid2 = s + 2u;
-	if (P.ibo)
-	{
-		const uint32_t* ix = P.ibo + ((unsigned long long)(long long)P.first + s);
-		r.vid0 = __ldg(ix); r.vid1 = __ldg(ix + 1); r.vid2 = __ldg(ix + 2);
-	}
-	r.a = P.clip + r.vid0; r.b = P.clip + r.vid1; r.c = P.clip + r.vid2;
-	r.band = 0xffffffffu;
-	return r;
-}
-
-__device__ __forceinline__ Prim load_prim(const DrawParams& P, uint32_t entry)
-{
-	if (entry & 1u) return *prim_at(P, entry >> 1);
-	Prim r;
-	tri_vertices(P, entry >> 2, r.v[0], r.v[1], r.v[2], r.vid[0], r.vid[1], r.vid[2]);
-	r.band = 0xffffffffu;
-	return r;
-}
-
-/* MipMapLevel of the primitive behind a list entry (swgl.c:3316: computed from the snapped vertices in
- * submission order, before the y sort); only draws with the mip_lod option call it */
-__device__ __noinline__ float prim_lod(const DrawParams& P, uint32_t entry)
-{
-	const Prim q = load_prim(P, entry);
-	return mip_level(q.v[0].x, q.v[0].y, q.v[1].x, q.v[1].y, q.v[2].x, q.v[2].y);
-}
-
 /* ---- near clip + snap + set-up + span walk + binning counts, one thread per triangle ---- */
-__device__ __forceinline__ bool owns_tile_row(const DrawParams& P, uint32_t tr)
-{
-	/* ownership is decided per band of 32 framebuffer rows whatever the tile height */
-	return P.n_ranks <= 1 || (((((tr << P.th_shift) >> 5) / P.band_rows) % P.n_ranks) == P.rank);
-}
-
 __device__ __forceinline__ float4 near_intersect(const float4& a, const float4& b, float& t)
 {
 	/* IntersectNearPlane (swgl.c:455-466) */
@@ -764,61 +613,6 @@ __global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ Dr
 	if (lane == 0 && live) atomicAdd(&P.ctr->prims_out, live);
 }
 
-/* ---- fragment shading for the three shader shapes ---- */
-struct FragIn
-{
-	float u, v, w;                /* perspective-corrected weights */
-	uint32_t vid0, vid1, vid2;    /* varying records (generic shape) */
-	/* fast shapes: the varying the shader consumes, per vertex; component k is at [k * stride]
-	 * (stride 1 = straight from the packed records, SWGL_BATCH = staged in shared memory) */
-	const float* a; const float* b; const float* c;
-	uint32_t stride;
-	float lod;                    /* generic shape, mip_lod draws: MipMapLevel of the primitive (swgl.c:3316) */
-};
-
-/* InterpolateLinearEx (swgl.c:3270-3297): a*u + b*v + c*w, left to right */
-__device__ __forceinline__ float lerp3(const FragIn& f, uint32_t k)
-{
-	return f.a[k * f.stride] * f.u + f.b[k * f.stride] * f.v + f.c[k * f.stride] * f.w;
-}
-
-template <int FS>
-__device__ __forceinline__ float4 run_fragment(const DrawParams& P, const FragIn& f)
-{
-	if (FS == SWFS_VARYING)
-	{
-		if (f.stride == 1 && (((uintptr_t)f.a | (uintptr_t)f.b | (uintptr_t)f.c) & 15u) == 0)
-		{
-			/* packed vec4 records: three 128-bit loads */
-			const float4 a = __ldg((const float4*)f.a), b = __ldg((const float4*)f.b), c = __ldg((const float4*)f.c);
-			return make_float4(a.x * f.u + b.x * f.v + c.x * f.w, a.y * f.u + b.y * f.v + c.y * f.w,
-			                   a.z * f.u + b.z * f.v + c.z * f.w, a.w * f.u + b.w * f.v + c.w * f.w);
-		}
-		return make_float4(lerp3(f, 0), lerp3(f, 1), lerp3(f, 2), lerp3(f, 3));
-	}
-	if (FS == SWFS_TEXTURE)
-	{
-		const float tu = lerp3(f, P.fs_swz_u), tv = lerp3(f, P.fs_swz_v);
-		return sample_nearest(P.tex[P.fs_tex_unit], tu, tv);
-	}
-	/* generic: interpolate every linked varying into the FS variable file, run the op list */
-	uint32_t V[SWGL_MAX_VAR_WORDS];
-	for (uint32_t k = 0; k < P.fs_words; k++) V[k] = P.fs_image[k];
-	const float* va = P.vary + (size_t)f.vid0 * P.nvf;
-	const float* vb = P.vary + (size_t)f.vid1 * P.nvf;
-	const float* vc = P.vary + (size_t)f.vid2 * P.nvf;
-	for (uint32_t k = 0; k < P.n_varying; k++)
-		for (uint32_t j = 0; j < P.varying[k].n_floats; j++)
-		{
-			const uint32_t s = P.varying[k].slot + j;
-			V[P.varying[k].fs_word + j] = __float_as_uint(va[s] * f.u + vb[s] * f.v + vc[s] * f.w);
-		}
-	ir_execute(P.fs_ops, P.fs_nops, V, P, f.lod);
-	float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-	for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
-	return make_float4(o[0], o[1], o[2], o[3]);
-}
-
 /* The tile's list length; the cursor is re-armed (zeroed) for the next draw.  Whole CTA calls it. */
 __device__ __forceinline__ uint32_t take_tile_list(const DrawParams& P, uint32_t tile)
 {
@@ -833,30 +627,6 @@ __device__ __forceinline__ uint32_t take_tile_list(const DrawParams& P, uint32_t
 	}
 	__syncthreads();
 	return min(n_s, P.bin_cap);
-}
-
-/* Walk state (x0, x1, s1, switched) of a primitive on entering row y_in of tile row `ty`
- * (swgl.c:3350-3356, 3466-3471): from the band entry for tall primitives, by replaying the
- * additions from the first row for short ones (at most two tile heights of float additions). */
-__device__ __forceinline__ void walk_to_row(const DrawParams& P, const TriWalk& w, uint32_t band, uint32_t ty, int y_in,
-                                            float& x0, float& x1, float& s1, bool& switched)
-{
-	if (y_in == w.ys) { x0 = w.c0x; x1 = w.c0x; s1 = w.s1; switched = false; return; }
-	if (band != 0xffffffffu)
-	{
-		const uint32_t tr_hi = (uint32_t)(P.ytop - w.ys) >> P.th_shift;
-		const BandEntry be = P.bands[band + (tr_hi - ty)];
-		x0 = be.x0; x1 = be.x1;
-		switched = (float)y_in >= w.c1y;
-		s1 = switched ? w.s2 : w.s1;
-		return;
-	}
-	x0 = w.c0x; x1 = w.c0x; s1 = w.s1; switched = false;
-	for (int y = w.ys; y < y_in; y++)
-	{
-		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
-		x0 += w.s0; x1 += s1;
-	}
 }
 
 /* ---- tall or wide primitives of big-triangle draws: one WARP per (primitive, tile row) band entry.
@@ -1318,7 +1088,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -1788,6 +1558,39 @@ static const swgl_ir_op* upload_code(swgldev_ctx* c, uint64_t id, const swgl_ir_
 	return d;
 }
 
+static int launch_vertex(swgldev_ctx* c, DrawParams& P, uint32_t blocks)
+{
+	if (P.vs_kind == SWVS_JIT)
+	{
+		void* args[] = { (void*)&P };
+		CK(cudaLaunchKernel((const void*)P.jit_vertex, dim3(blocks), dim3(256), args, 0, c->stream));
+	}
+	else if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<blocks, 256, 0, c->stream>>>(P);
+	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<blocks, 256, 0, c->stream>>>(P);
+	else k_vertex<SWVS_GENERIC><<<blocks, 256, 0, c->stream>>>(P);
+	return 0;
+}
+
+/* Generic shaders: swap the on-device interpreter for kernels compiled from the program's IR
+ * (swgl_jit.cpp).  A failure is reported once through the error string and the interpreter draws. */
+static void apply_jit(swgldev_ctx* c, const swgldev_draw* d, DrawParams& P, bool raster_ok)
+{
+	const int want_v = P.vs_kind == SWVS_GENERIC, want_r = raster_ok && P.fs_kind == SWFS_GENERIC;
+	if (!c->opt_jit || c->jit_failed || (!want_v && !want_r)) return;
+	swgljit_kernels k;
+	char msg[2048];
+	if (swgljit_get(c->device, d, want_v, want_r, &k, msg, sizeof(msg)))
+	{
+		c->jit_failed = 1;
+		char full[2300];
+		snprintf(full, sizeof(full), "run-time shader compilation failed, the interpreter draws instead: %s", msg);
+		set_err(c, full, cudaSuccess);
+		return;
+	}
+	if (want_v && k.vertex) { P.vs_kind = SWVS_JIT; P.jit_vertex = k.vertex; }
+	if (want_r && k.raster) { P.fs_kind = SWFS_JIT; P.jit_raster = k.raster; }
+}
+
 static int launch_draw(swgldev_ctx* c, DrawParams& P)
 {
 	P.cap_bands = (uint32_t)(c->cap_bands > 0xffffffffull ? 0xffffffffull : c->cap_bands);
@@ -1799,9 +1602,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 #define STAGE(i) do { if (timing) cudaEventRecord(c->stage_ev[i], c->stream); } while (0)
 	const uint32_t vb = (P.n_shade + 255u) / 256u;
 	STAGE(0);
-	if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
-	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
-	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	if (launch_vertex(c, P, vb ? vb : 1)) return -1;
 	STAGE(1);
 	{
 		/* programmatic dependent launch: the set-up CTAs become resident while the vertex kernel's last
@@ -1825,9 +1626,17 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	CK(cudaEventRecord(c->ctr_event, c->side));
 	c->ctr_pending = 1;
 	if (guard_color_write(c)) return -1;
-	if (P.fs_kind == SWFS_VARYING) launch_raster<SWFS_VARYING>(c, P);
+	if (P.fs_kind == SWFS_JIT)
+	{
+		/* the program's own raster kernel (warp rasteriser only: apply_jit() checks the path) */
+		void* args[] = { (void*)&P };
+		c->last_raster_path = 3;
+		CK(cudaLaunchKernel((const void*)P.jit_raster, dim3((P.tiles_x + WT_WARPS - 1) / WT_WARPS, P.owned_tile_rows ? P.owned_tile_rows : 1), dim3(WT_WARPS * 32), args, 0, c->stream));
+	}
+	else if (P.fs_kind == SWFS_VARYING) launch_raster<SWFS_VARYING>(c, P);
 	else if (P.fs_kind == SWFS_TEXTURE) launch_raster<SWFS_TEXTURE>(c, P);
 	else launch_raster<SWFS_GENERIC>(c, P);
+	c->last_vs_kind = P.vs_kind; c->last_fs_kind = P.fs_kind;
 	STAGE(3);
 #undef STAGE
 	c->n_launches += P.inline_tall ? 3 : 4;
@@ -1941,6 +1750,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		const uint32_t lo = P.rank * per;
 		P.owned_tile_rows = full * per + (rest > lo ? (rest - lo < per ? rest - lo : per) : 0u);
 	}
+	apply_jit(c, d, P, P.th_shift == WT_H_SHIFT);
 	P.lean_prims = (c->opt_lean_prims && P.th_shift == WT_H_SHIFT) ? 1u : 0u;
 	P.inline_tall = (P.th_shift == WT_H_SHIFT && small_triangle_draw(c, ntri)) ? 1u : 0u;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
@@ -1993,6 +1803,16 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	return stamp_draw(c, d);
 }
 
+int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t msg_len)
+{
+	if (msg_len) msg[0] = 0;
+	const int want_v = d->vs_kind == SWVS_GENERIC, want_r = d->fs_kind == SWFS_GENERIC;
+	if (!want_v && !want_r) return 0;
+	if (c) cudaSetDevice(c->device);
+	swgljit_kernels k;
+	return swgljit_get(c ? c->device : -1, d, want_v, want_r, &k, msg, msg_len);
+}
+
 int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 {
 	cudaSetDevice(c->device);
@@ -2018,9 +1838,8 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.winner = c->winner;
 
 	const uint32_t vb = (P.n_shade + 255u) / 256u, pb = (P.count + 255u) / 256u;
-	if (P.vs_kind == SWVS_PASS) k_vertex<SWVS_PASS><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
-	else if (P.vs_kind == SWVS_MATRIX) k_vertex<SWVS_MATRIX><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
-	else k_vertex<SWVS_GENERIC><<<vb ? vb : 1, 256, 0, c->stream>>>(P);
+	apply_jit(c, d, P, false);                /* the vertex stage; k_points_write keeps the interpreter for generic shaders */
+	if (launch_vertex(c, P, vb ? vb : 1)) return -1;
 	if (guard_color_write(c)) return -1;
 	k_points_claim<<<pb, 256, 0, c->stream>>>(P);
 	if (P.fs_kind == SWFS_VARYING) k_points_write<SWFS_VARYING><<<pb, 256, 0, c->stream>>>(P);
@@ -2234,6 +2053,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "diag")) c->opt_diag = (int)value;
 	else if (!strcmp(name, "lean_prims")) c->opt_lean_prims = (int)value;
 	else if (!strcmp(name, "mip_lod")) c->opt_mip_lod = value ? 1 : 0;
+	else if (!strcmp(name, "jit")) c->opt_jit = value ? 1 : 0;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
@@ -2266,11 +2086,26 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 
 int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 {
+	if (!strncmp(name, "jit_", 4))
+	{
+		/* process-wide (the compiled programs outlive a context); `c` may be NULL */
+		swgljit_stats js;
+		swgljit_get_stats(&js);
+		if (!strcmp(name, "jit_compiles")) return (int64_t)js.compiles;
+		if (!strcmp(name, "jit_cache_hits")) return (int64_t)js.cache_hits;
+		if (!strcmp(name, "jit_compile_us_total")) return (int64_t)(js.compile_ms_total * 1e3);
+		if (!strcmp(name, "jit_cubin_bytes")) return (int64_t)js.cubin_bytes;
+		return -1;
+	}
+	if (!c) return -1;
 	if (!strcmp(name, "fuse_clear")) return c->opt_fuse_clear;
 	if (!strcmp(name, "count_fragments")) return c->opt_count_fragments;
 	if (!strcmp(name, "raster_path")) return c->opt_raster_path;
 	if (!strcmp(name, "host_mirror")) return c->opt_host_mirror;
 	if (!strcmp(name, "mip_lod")) return c->opt_mip_lod;
+	if (!strcmp(name, "jit")) return c->opt_jit;
+	if (!strcmp(name, "last_vs_kind")) return c->last_vs_kind;
+	if (!strcmp(name, "last_fs_kind")) return c->last_fs_kind;
 	if (!strcmp(name, "mirror_synced")) return c->mirror_synced;
 	if (!strcmp(name, "wt_draws")) return (int64_t)c->wt_draws;
 	if (!strcmp(name, "last_raster_path")) return c->last_raster_path;

@@ -21,8 +21,15 @@
 #ifndef SWGL_DEV_TYPES_CUH
 #define SWGL_DEV_TYPES_CUH
 
+#ifdef __CUDACC_RTC__
+/* NVRTC translation unit (swgl_jit.cpp): no host headers */
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <stdint.h>
 #include <cuda_runtime.h>
+#endif
 
 #include "swgl_dev.h"
 #include "swgl_ir.h"
@@ -124,6 +131,8 @@ struct DrawParams
 	/* initial variable files (uniform values) for the generic evaluator */
 	uint32_t vs_image[SWGL_MAX_VAR_WORDS];
 	uint32_t fs_image[SWGL_MAX_VAR_WORDS];
+	/* host side only: run-time compiled kernels of this draw (vs_kind SWVS_JIT / fs_kind SWFS_JIT) */
+	void* jit_vertex; void* jit_raster;
 };
 
 #endif

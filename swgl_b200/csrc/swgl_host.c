@@ -254,7 +254,7 @@ int swglIpcExportColor(void* handle64) { return G.dev ? swgldev_ipc_export_color
 uint64_t swglIpcOpen(const void* handle64) { return G.dev ? swgldev_ipc_open(G.dev, handle64) : 0; }
 void swglIpcClose(uint64_t p) { if (G.dev) swgldev_ipc_close(G.dev, p); }
 void swglSetOption(const char* name, int64_t value) { if (G.dev) swgldev_set_option(G.dev, name, value); }
-int64_t swglGetOption(const char* name) { return G.dev ? swgldev_get_option(G.dev, name) : -1; }
+int64_t swglGetOption(const char* name) { return swgldev_get_option(G.dev, name); }   /* without a device: -1, except the process-wide jit_* counters */
 
 /* ---------------------------------------------------------------------------------------- */
 /* shaders (swgl.c:2870-2898) */
@@ -695,34 +695,37 @@ static int find_fetch_for_word(const swgldev_draw* d, uint32_t word)
 	return found;
 }
 
-static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, uint32_t index_byte_offset)
+/* Everything a draw needs, gathered from the GL state into `d` (returns 0 when nothing is to be drawn).
+ * compile_only: the caller only wants the shader interface (swglPrecompileProgram): no device, buffer
+ * contents or count are required. */
+static int assemble_draw(GLenum mode, GLint first, GLsizei count, int indexed, uint32_t index_byte_offset, swgldev_draw* dp, int compile_only)
 {
-	if (!G.active_vao) return;     /* swgl.c:3477-3478 */
-	if (!G.active_program) return;
-	if (!G.dev) return;
+#define d (*dp)
+	if (!G.active_vao) return 0;     /* swgl.c:3477-3478 */
+	if (!G.active_program) return 0;
+	if (!G.dev && !compile_only) return 0;
 	if (mode != GL_TRIANGLES && mode != GL_POINTS)
 	{
 		/* GL_LINES has an enumerator but no implementation in the reference either (swgl.h:65) */
-		return;
+		return 0;
 	}
 	gl_program* p = G.active_program;
 	if (!p->linked || !p->vs || !p->fs || !p->vs->ok || !p->fs->ok)
 	{
 		set_error("glDraw*: program is not linked or a shader is outside the executable subset; nothing drawn");
-		return;
+		return 0;
 	}
 	gl_vao* vao = G.active_vao;
-	if (!vao->vertex.data || count == 0) return;
+	if (!compile_only && (!vao->vertex.data || count == 0)) return 0;
 
-	swgldev_draw d;
 	memset(&d, 0, sizeof(d));
 	d.vx = G.vx; d.vy = G.vy; d.vw = G.vw; d.vh = G.vh;
 	d.vbo = vao->vertex.data; d.vbo_bytes = vao->vertex.size;
 	d.first = first; d.count = count;
 	if (indexed)
 	{
-		if (!vao->element.data) return;
-		if (index_byte_offset & 3u) { set_error("glDrawElements: index offset must be a multiple of 4"); return; }
+		if (!vao->element.data) return 0;
+		if (index_byte_offset & 3u) { set_error("glDrawElements: index offset must be a multiple of 4"); return 0; }
 		d.ibo = vao->element.data; d.ibo_bytes = vao->element.size;
 		d.first = (int32_t)(index_byte_offset / 4u);
 		d.n_vertices = vao->element.max_index + 1u;
@@ -746,11 +749,11 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 			if (p->layouts[l].sh != vs) continue; /* fragment-stage layout variables are never observable */
 			const swgl_var* lv = &vs->vars[p->layouts[l].var];
 			if (lv->location != (int32_t)at->index) continue;
-			if (d.n_fetch >= SWGL_MAX_FETCH) { set_error("glDraw*: too many attribute bindings"); return; }
+			if (d.n_fetch >= SWGL_MAX_FETCH) { set_error("glDraw*: too many attribute bindings"); return 0; }
 			int n = at->size;
 			if (n > swt_words(lv->type)) n = swt_words(lv->type); /* the reference overflows the variable here */
 			if (n < 0) n = 0;
-			if (at->offset < 0) { set_error("glDraw*: negative attribute offset"); return; }
+			if (at->offset < 0) { set_error("glDraw*: negative attribute offset"); return 0; }
 			swgldev_fetch* f = &d.fetch[d.n_fetch++];
 			f->src_offset = (uint32_t)at->offset; f->stride = at->stride; f->n_floats = (uint32_t)n; f->dst_word = lv->word;
 		}
@@ -766,7 +769,7 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 		if (fi->type != vo->type) continue;
 		int n = vec_floats(fi->type);
 		if (n == 0) continue; /* int varyings interpolate to an unspecified value in the reference */
-		if (d.n_varying >= 8 || slot + (uint32_t)n > SWGL_MAX_VARYING_FLOATS) { set_error("glDraw*: too many varyings"); return; }
+		if (d.n_varying >= 8 || slot + (uint32_t)n > SWGL_MAX_VARYING_FLOATS) { set_error("glDraw*: too many varyings"); return 0; }
 		swgldev_varying* v = &d.varying[d.n_varying++];
 		v->vs_word = vo->word; v->fs_word = fi->word; v->n_floats = (uint32_t)n; v->slot = slot;
 		slot += (uint32_t)n;
@@ -799,7 +802,7 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 	/* fragment output: the first `out` global, four floats (swgl.c:3412-3426) */
 	int out_var = -1;
 	for (int v = 0; v < fs->n_vars; v++) if (!fs->vars[v].is_local && fs->vars[v].is_out) { out_var = v; break; }
-	if (out_var < 0) { set_error("glDraw*: fragment shader has no `out` variable"); return; }
+	if (out_var < 0) { set_error("glDraw*: fragment shader has no `out` variable"); return 0; }
 	d.out_word = fs->vars[out_var].word;
 	d.out_floats = (uint32_t)RMIN(4, swt_words(fs->vars[out_var].type));
 
@@ -833,8 +836,29 @@ static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, ui
 		d.tex[u].mips = t->mips; d.tex[u].n_mips = t->n_mipmaps;
 	}
 
+	return 1;
+#undef d
+}
+
+static void draw_common(GLenum mode, GLint first, GLsizei count, int indexed, uint32_t index_byte_offset)
+{
+	swgldev_draw d;
+	if (!assemble_draw(mode, first, count, indexed, index_byte_offset, &d, 0)) return;
 	if (mode == GL_POINTS) swgldev_draw_points(G.dev, &d);
 	else swgldev_draw_triangles(G.dev, &d);
+}
+
+/* Compile the kernels the bound program + vertex array need now instead of at the first draw (a shader
+ * outside the built-in shapes is compiled at run time, swgl_jit.cpp).  Works without a device: the code is
+ * then generated and compiled, not loaded. */
+int swglPrecompileProgram(void)
+{
+	swgldev_draw d;
+	if (!assemble_draw(GL_TRIANGLES, 0, 3, 0, 0, &d, 1)) return -1;
+	char msg[2048];
+	msg[0] = 0;
+	if (swgldev_precompile(G.dev, &d, msg, sizeof(msg))) { set_error(msg); return -1; }
+	return 0;
 }
 
 void glDrawArrays(GLenum mode, GLint first, GLsizei count)

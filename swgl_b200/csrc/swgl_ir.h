@@ -14,7 +14,9 @@
 #ifndef SWGL_IR_H
 #define SWGL_IR_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -35,6 +37,7 @@ enum
 	SWT_UNKNOWN
 };
 
+#ifndef __CUDACC_RTC__   /* host helpers */
 /* storage words of a variable of each type (VerifyVar, swgl.c:1880-1892) */
 static inline int swt_words(int t)
 {
@@ -54,6 +57,7 @@ static inline int swt_words(int t)
 }
 static inline int swt_is_mat(int t) { return t == SWT_MAT2 || t == SWT_MAT3 || t == SWT_MAT4; }
 static inline int swt_mat_dim(int t) { return t == SWT_MAT2 ? 2 : t == SWT_MAT3 ? 3 : t == SWT_MAT4 ? 4 : 0; }
+#endif
 
 /*
  * Register model.  A vector temp carries what a glslExValue carries besides its matrices
@@ -130,13 +134,15 @@ enum
 {
 	SWVS_GENERIC = 0, /* run the op list */
 	SWVS_PASS,        /* gl_Position = <vec4 attribute>;  every linked varying = attribute copy */
-	SWVS_MATRIX       /* gl_Position = <mat4 uniform> * <vec4 attribute>; varyings = attribute copies */
+	SWVS_MATRIX,      /* gl_Position = <mat4 uniform> * <vec4 attribute>; varyings = attribute copies */
+	SWVS_JIT          /* device layer only: the op list compiled to a __device__ function at run time (swgl_jit.cpp) */
 };
 enum
 {
 	SWFS_GENERIC = 0, /* run the op list */
 	SWFS_VARYING,     /* out = <vec4 varying> */
-	SWFS_TEXTURE      /* out = texture(<sampler uniform>, <varying>[.swizzle to vec2]) */
+	SWFS_TEXTURE,     /* out = texture(<sampler uniform>, <varying>[.swizzle to vec2]) */
+	SWFS_JIT          /* device layer only: the op list compiled to a __device__ function at run time (swgl_jit.cpp) */
 };
 
 #ifdef __cplusplus

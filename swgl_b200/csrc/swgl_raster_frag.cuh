@@ -84,34 +84,6 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_t
 	return before + (x - v);
 }
 
-/* blend with the destination unpacked through the byte/255.0f table */
-__device__ __forceinline__ float4 clamp_color(float4 o)
-{
-	/* swgl.c:3428-3431, ternary MIN/MAX: NaN -> 0 */
-	o.x = RMIN(RMAX(o.x, 0.0f), 1.0f);
-	o.y = RMIN(RMAX(o.y, 0.0f), 1.0f);
-	o.z = RMIN(RMAX(o.z, 0.0f), 1.0f);
-	o.w = RMIN(RMAX(o.w, 0.0f), 1.0f);
-	return o;
-}
-
-/* r, g, b, a already clamped */
-__device__ __forceinline__ uint32_t blend_pack_lut(float r, float g, float b, float a, uint32_t cur, const float* lut)
-{
-	const float cr = lut[(cur >> 24) & 0xFF], cg = lut[(cur >> 16) & 0xFF];
-	const float cb = lut[(cur >> 8) & 0xFF], ca = lut[cur & 0xFF];
-	r = cr + a * (r - cr);
-	g = cg + a * (g - cg);
-	b = cb + a * (b - cb);
-	a = ca + a * (a - ca);
-	uint32_t word = 0;
-	word |= (uint32_t)(int)(r * 255.0f) << 24;
-	word |= (uint32_t)(int)(g * 255.0f) << 16;
-	word |= (uint32_t)(int)(b * 255.0f) << 8;
-	word |= (uint32_t)(int)(a * 255.0f);
-	return word;
-}
-
 template <int FS>
 __global__ void __launch_bounds__(FRAG_THREADS, 6) k_raster_frag(const __grid_constant__ DrawParams P)
 {

@@ -184,7 +184,7 @@ __device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, flo
 	fi.b = P.vary + (size_t)fi.vid1 * P.nvf + P.fs_slot;
 	fi.c = P.vary + (size_t)fi.vid2 * P.nvf + P.fs_slot;
 	fi.stride = 1;
-	fi.lod = (FS == SWFS_GENERIC && P.mip_lod) ? mip_level(q->v[0].x, q->v[0].y, q->v[1].x, q->v[1].y, q->v[2].x, q->v[2].y) : 0.0f;
+	fi.lod = ((FS == SWFS_GENERIC || FS == SWFS_JIT) && P.mip_lod) ? mip_level(q->v[0].x, q->v[0].y, q->v[1].x, q->v[1].y, q->v[2].x, q->v[2].y) : 0.0f;
 	return clamp_color(run_fragment<FS>(P, fi));
 }
 
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					if (cur == 0.0f || cur >= z)
 					{
 						float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va, vc = va;
-						if (FS != SWFS_GENERIC)
+						if (FS != SWFS_GENERIC && FS != SWFS_JIT)
 						{
 							const float4 ids = pc[5];
 							const float* pa = P.vary + (size_t)__float_as_uint(ids.x) * P.nvf + P.fs_slot;
