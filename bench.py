@@ -44,6 +44,135 @@ STAGES = ["k_vertex", "k_setup_bin", "k_raster"]
 L2_FLUSH_BYTES = 256 << 20
 
 
+def band_rows_for(height: int, world: int) -> int:
+    """Sort-first ownership: >= 16 interleaved bands of 32 rows per rank."""
+    if world <= 1:
+        return 1
+    return max(1, ((height + 31) // 32) // (world * 16))
+
+
+def config_dict(cfg: int, scene, world: int) -> dict:
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)."""
+    from swgl_b200 import scenes as S
+
+    br = band_rows_for(scene.height, world)
+    return {"workload": S.CONFIG_NAMES[cfg], "triangles": scene.n_triangles,
+            "framebuffer": f"{scene.width}x{scene.height} RGBA8 + f32 depth",
+            "l2": "GPU arm: flushed between steps (256 MiB write, untimed); CPU arm: n/a",
+            "parallelism": f"GPU arm: sort-first tile-row bands x{world}" + (f", band={br} tile rows, peer stores to rank 0" if world > 1 else "")
+                           + "; CPU arm: one host core"}
+
+
+def golden_for(cfg: int):
+    """Known-answer frame of a BASELINE config rendered by the compiled, unmodified reference
+    (tests/golden/*.json, committed with the scripts that made them)."""
+    name, key = ("oracle_kats.json", "k1_config1") if cfg == 1 else ("fullsize_kats.json", f"C{cfg}")
+    path = os.path.join(ROOT, "tests", "golden", name)
+    try:
+        with open(path) as f:
+            return json.load(f).get(key)
+    except OSError:
+        return None
+
+
+def ncu_counters(cfg: int, kernel: str):
+    """Per-launch counters of one `ncu --set full` capture (profiles/ncu_counters.json, written by
+    tools/ncu_summary.py with the commit it was captured at); None when there is no capture of this config."""
+    path = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except OSError:
+        return None, None
+    return d.get(f"C{cfg}", {}).get(kernel), d.get("captured_at")
+
+
+def parity_block(api, scene, cfg: int, stats: dict) -> dict:
+    """The frame just rendered against the reference's known-answer frame of this config: FNV-1a64 of the colour
+    words and of the depth bits, covered pixels, tested / shaded fragments."""
+    want = golden_for(cfg)
+    W, H = scene.width, scene.height
+    n = W * H
+    col = api.glGetFramePtr()
+    color_fnv = api.swglHashWords(col, n)
+    dep = api.swglGetDepthPtr()
+    depth_fnv = api.swglHashWords(dep, n)
+    d = np.ctypeslib.as_array(dep, shape=(H, W))
+    covered = int((d.view(np.uint32) != 0).sum())
+    out = {"color_fnv": f"{color_fnv:016x}", "depth_fnv": f"{depth_fnv:016x}", "covered": covered,
+           "tested": int(stats["tested"]), "shaded": int(stats["shaded"])}
+    if want is None:
+        out["golden"] = None
+        return out
+    out["golden"] = "tests/golden (compiled reference)"
+    out["color_equal"] = out["color_fnv"] == want["color_fnv"]
+    out["depth_equal"] = out["depth_fnv"] == want["depth_fnv"]
+    out["covered_delta"] = covered - int(want["covered"])
+    out["tested_delta"] = out["tested"] - int(want["tested"])
+    out["shaded_delta"] = out["shaded"] - int(want["shaded"])
+    out["bit_exact"] = bool(out["color_equal"] and out["depth_equal"] and out["covered_delta"] == 0
+                            and out["tested_delta"] == 0 and out["shaded_delta"] == 0)
+    return out
+
+
+def measure_config(api, sw, G, S, torch, cfg: int, steps: int, stream_of, flush, peak: float) -> dict:
+    """One of the other BASELINE configs on this GPU: device-resident frame time (CUDA events, L2 flushed),
+    per-stage times, roofline fraction of the frame's algorithmic bytes, parity against the golden frame."""
+    scene = S.config(cfg)
+    api.glInit(scene.width, scene.height)
+    err = api.swglGetLastError().decode()
+    if err:
+        return {"error": err}
+    st = G.setup_scene(api, scene, indexed=scene.indices is not None, init=False)
+    stream = stream_of()
+
+    def frame():
+        api.glClear(G.GL_COLOR_BUFFER_BIT | G.GL_DEPTH_BUFFER_BIT)
+        if st["indexed"]:
+            api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
+        else:
+            api.glDrawArrays(G.GL_TRIANGLES, 0, st["n_draw"])
+
+    for _ in range(3):
+        frame()
+    api.swglFinish()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        a.record(stream)
+        frame()
+        b.record(stream)
+    api.swglFinish()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    api.swglSetOption(b"stage_timing", 1)
+    for _ in range(steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        frame()
+    api.swglFinish()
+    nd = max(1, api.swglGetOption(b"stage_draws"))
+    stage_us = {n: api.swglGetOption(f"stage_ns_{i}".encode()) / 1e3 / nd for i, n in enumerate(STAGES)}
+    api.swglSetOption(b"stage_timing", 0)
+    frame()
+    stats = sw.swglStats()
+    api.swglGetStats(C.byref(stats))
+    sd = stats.as_dict()
+    par = parity_block(api, scene, cfg, sd)
+    err = api.swglGetLastError().decode()
+    out = {"workload": S.CONFIG_NAMES[cfg], "triangles": scene.n_triangles, "frame_ms": ms,
+           "triangles_per_s": scene.n_triangles / (ms * 1e-3), "shaded_fragments_per_s": sd["shaded"] / (ms * 1e-3),
+           "tested_fragments_per_s": sd["tested"] / (ms * 1e-3), "stage_us": stage_us,
+           "frame_algorithmic_bytes": scene.algorithmic_bytes(),
+           "frame_frac": scene.algorithmic_bytes() / (ms * 1e-3) / 1e9 / peak,
+           "raster_frac": scene.width * scene.height * 8 / (stage_us["k_raster"] * 1e-6) / 1e9 / peak if stage_us["k_raster"] > 0 else None,
+           "parity": par}
+    if err:
+        out["error"] = err
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -145,8 +274,7 @@ def run_own(args):
     band_rows = 1
     peer = None
     if world > 1:
-        tiles_y = (scene.height + 31) // 32
-        band_rows = max(1, tiles_y // (world * 16))  # >= 16 interleaved bands of 32 rows per rank
+        band_rows = band_rows_for(scene.height, world)
         api.swglSetStripe(rank, world, band_rows)
         peer = multigpu.PeerColorTarget(api, dist, rank, world)
 
@@ -215,21 +343,24 @@ def run_own(args):
     fb_bytes = scene.width * scene.height * 8 // world
     dom_bytes = fb_bytes if dom == "k_raster" else scene.algorithmic_bytes()
     achieved = dom_bytes / (stage_us[dom] * 1e-6) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj.get(f"C{args.config}", {}).get(dom) if world == 1 else None   # captured on the unsharded frame only
+    # per-launch counters of the dominant kernel from the committed ncu capture of this config (stamped with the
+    # commit it was taken at): DRAM traffic, and the warp-instruction count behind the SM-issue roofline
+    ctr, captured_at = ncu_counters(args.config, dom) if world == 1 else (None, None)
+    traffic = ctr.get("dram_bytes") if ctr else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_us": stage_us[dom], "stage_us": stage_us,
                 "frame_algorithmic_bytes": scene.algorithmic_bytes(),
                 "frame_frac": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 1e9 / peak,
-                "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12,
-                "note": "HBM is the roofline the contract names; ncu shows the raster kernel SM-issue-bound "
-                        "(C4: 74 % issue-active, DRAM 4 % busy, profiles/r01_ncu_summary_c4.md, DESIGN.md section 4)"}
+                "frame_frac_nominal_8TBs": scene.algorithmic_bytes() / (ms_per_step * 1e-3) / 8.0e12}
+    if ctr and ctr.get("warp_inst"):
+        # what actually bounds the kernel: warp instructions per launch (ncu) / its live duration against the
+        # issue rate of 148 SMs x 4 schedulers x 1 instruction per clock at the SM clock sampled below
+        roofline["issue"] = {"warp_inst_per_launch": int(ctr["warp_inst"]), "kernel_us": stage_us[dom],
+                             "achieved_ginst_s": ctr["warp_inst"] / (stage_us[dom] * 1e-6) / 1e9,
+                             "ncu_issue_active_pct": ctr.get("issue_active_pct"), "ncu_dram_pct": ctr.get("dram_pct"),
+                             "source": f"profiles/ncu_counters.json, captured at {captured_at}"}
 
     # ---- N > 1: the image assembled on rank 0 must equal the unsharded render, bit for bit ----
     def assembled_equals_single():
@@ -355,6 +486,19 @@ def run_own(args):
                     "note": "swglFrameSubmit/swglFrameWait, two geometry sets: same bytes per step as e2e, each frame is read one step later"}
 
     clocks = sampler.stop() if rank == 0 else {}   # sampled across the value, roofline and e2e legs
+    if "issue" in roofline:
+        mhz = clocks.get("sm_mhz") or 1965.0
+        roofline["issue"]["peak_ginst_s"] = 148 * 4 * mhz * 1e6 / 1e9
+        roofline["issue"]["frac"] = roofline["issue"]["achieved_ginst_s"] / roofline["issue"]["peak_ginst_s"]
+
+    # ---- parity of the timed workload against the reference's known-answer frame (N = 1; at N > 1 the assembled
+    # image has been compared with the single-GPU one above) ----
+    parity = None
+    if world == 1:
+        frame()
+        st1 = sw.swglStats()
+        api.swglGetStats(C.byref(st1))
+        parity = parity_block(api, scene, args.config, st1.as_dict())
 
     # ---- CPU baseline: the unmodified reference on one host core, bounded sample ----
     cpu = None
@@ -366,15 +510,23 @@ def run_own(args):
     if peer is not None:
         peer.close()
     err = api.swglGetLastError().decode()
+
+    # ---- the other BASELINE configs (N = 1): frame time, stages, roofline fraction, parity ----
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        for cfg in (1, 2, 3, 5):
+            if cfg == args.config:
+                continue
+            configs[f"C{cfg}"] = measure_config(
+                api, sw, G, S, torch, cfg, max(5, args.steps // 2),
+                lambda: torch.cuda.ExternalStream(api.swglGetStream(), device=torch.device("cuda", local)), flush, peak)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": S.CONFIG_NAMES[args.config], "triangles": n_tris,
-                       "framebuffer": f"{scene.width}x{scene.height} RGBA8 + f32 depth",
-                       "l2": "flushed between steps (256 MiB write, untimed)",
-                       "parallelism": f"sort-first tile-row bands x{world}" + (f", band={band_rows} tile rows, peer stores to rank 0" if world > 1 else "")},
+            "config": config_dict(args.config, scene, world),
             "shaded_fragments_per_s": shaded / (ms_per_step * 1e-3),
             "tested_fragments_per_s": tested / (ms_per_step * 1e-3),
             "frame_ms": ms_per_step, "shaded_fragments": shaded, "tested_fragments": tested,
@@ -386,6 +538,10 @@ def run_own(args):
             line["cpu_baseline"] = cpu
         if mg_check is not None:
             line["multi_gpu_check"] = mg_check
+        if parity is not None:
+            line["parity"] = parity
+        if configs is not None:
+            line["configs"] = configs
         if err:
             line["error"] = err
         print(json.dumps(line))
@@ -499,8 +655,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": S.CONFIG_NAMES[args.config], "triangles": scene.n_triangles,
-                   "framebuffer": f"{scene.width}x{scene.height} RGBA8 + f32 depth"},
+        "config": config_dict(args.config, scene, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": 1, "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -516,6 +671,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", type=int, default=4, help="BASELINE.json config 1..5 (default 4: 4K, 1M triangles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1, C2, C3, C5) of the N=1 line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -99,6 +99,9 @@ const uint32_t* swglFrameWait(uint64_t ticket);
 int swglReadPixelsRGBA8(void* dst);
 /* The current frame as a binary PPM (P6); 0 on success. */
 int swglWritePPM(const char* path);
+/* FNV-1a over 32-bit words (h = (h ^ word) * 1099511628211 from 1469598103934665603): the image hash of the
+ * committed known-answer frames (tests/golden), for applications and bench.py to check a frame they read back. */
+uint64_t swglHashWords(const void* words, uint64_t n_words);
 
 /* Geometry that reaches the device in pieces (sort-first ranks: every rank uploads 1/N of the arrays over its own
  * PCIe link and an all-gather over NVLink, queued on swglGetStream(), replicates them).

@@ -51,6 +51,7 @@ EXTENSION_EXPORTS = {
     "swglFrameWait": (C.POINTER(C.c_uint32), [C.c_uint64]),
     "swglReadPixelsRGBA8": (C.c_int, [C.c_void_p]),
     "swglWritePPM": (C.c_int, [C.c_char_p]),
+    "swglHashWords": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "swglBufferSubData": (None, [C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "swglGetBufferDevicePtr": (C.c_uint64, [C.c_uint32]),
     "swglBufferDeviceWritten": (None, [C.c_uint32]),

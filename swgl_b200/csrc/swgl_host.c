@@ -218,6 +218,14 @@ int swglWritePPM(const char* path)
 	return rc;
 }
 
+uint64_t swglHashWords(const void* words, uint64_t n_words)
+{
+	const uint32_t* w = (const uint32_t*)words;
+	uint64_t h = 1469598103934665603ull;
+	for (uint64_t i = 0; i < n_words; i++) h = (h ^ (uint64_t)w[i]) * 1099511628211ull;
+	return h;
+}
+
 const char* swglGetLastError(void)
 {
 	static char out[512];

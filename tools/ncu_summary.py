@@ -1,6 +1,9 @@
 """Summarise an ncu --set full report: one row per kernel launch (markdown) + traffic json.
 
-usage: python tools/ncu_summary.py <report.ncu-rep> <out.md> [traffic.json config-key]
+usage: python tools/ncu_summary.py <report.ncu-rep> <out.md> [ncu_counters.json config-key commit]
+
+The counters file feeds bench.py's `roofline.traffic` and `roofline.issue` (per-launch DRAM bytes and warp
+instructions of each kernel), stamped with the commit the capture was taken at.
 """
 import csv, json, subprocess, sys, os
 
@@ -42,7 +45,17 @@ for r in rows[2:]:
     scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
     rdb = rd * scale.get(units[ix["dram__bytes_read.sum"]], 1.0)
     wrb = wr * scale.get(units[ix["dram__bytes_write.sum"]], 1.0)
-    traffic["k_raster" if name.startswith("k_raster") else name] = int(rdb + wrb)
+    def num(key):
+        try:
+            return float(r[ix[key]])
+        except (KeyError, ValueError):
+            return None
+    traffic["k_raster" if name.startswith("k_raster") else name] = {
+        "dram_bytes": int(rdb + wrb), "warp_inst": int(num("smsp__inst_executed.sum") or 0),
+        "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "dram_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "threads_per_inst": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "ncu_time_us": num("gpu__time_duration.sum")}
 with open(out_md, "w") as f:
     f.write(f"# ncu --set full summary of `{os.path.basename(rep)}`\n\n")
     f.write("One frame of the workload (glClear fused + glDrawElements); per-launch values, cold-cache and\n"
@@ -53,6 +66,8 @@ if len(sys.argv) > 4:
     cur = {}
     if os.path.exists(path):
         cur = json.load(open(path))
-    cur[key] = traffic
+    cur.setdefault(key, {}).update(traffic)
+    if len(sys.argv) > 5:
+        cur["captured_at"] = sys.argv[5]
     json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
 print("\n".join(lines))
