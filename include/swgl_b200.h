@@ -47,6 +47,15 @@ void swglGetStats(swglStats* out);
 /* Select the CUDA device used by the NEXT glInit (default: $LOCAL_RANK, else 0). */
 void swglSetDevice(int ordinal);
 
+/* Number of CUDA devices the NEXT glInit drives from the calling thread (default 1): ordinals d .. d+n-1 with d
+ * the swglSetDevice ordinal (default 0).  The frame is sharded sort-first by tile-row bands, buffers and textures
+ * are replicated (swglBufferRespecify splits the transfer over the devices' PCIe links and completes it over
+ * NVLink), and glGetFramePtr returns one pinned frame every device has written its bands into.  The
+ * reference-compatible entry points need no other change.  Not available in this mode: swglFrameSubmit,
+ * swglSetStripe and the peer / shared-mirror targets (the group does its own assembly); swglGetColorDevicePtr
+ * returns device d's attachment, which only holds that device's bands. */
+void swglSetDeviceCount(int count);
+
 /* cudaStream_t (as void*) on which glClear / glDraw* queue their kernels. */
 void* swglGetStream(void);
 

@@ -114,6 +114,11 @@ typedef struct
 /* context ------------------------------------------------------------------------------ */
 /* glInit (swgl.c:3713-3736): device = CUDA ordinal, or -1 for the current / LOCAL_RANK one. */
 swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height);
+/* glInit after swglSetDeviceCount(n): a group of n device contexts (ordinals device .. device+n-1) behind one
+ * handle, driven by the calling thread.  Every function below fans out to the members: allocations are replicated,
+ * per-frame uploads are split over the members' PCIe links and completed over NVLink, draws are sharded
+ * sort-first by tile-row bands, and the frame is assembled in one pinned host mirror all members write into. */
+swgldev_ctx* swgldev_create_group(int device, int count, uint32_t width, uint32_t height);
 void         swgldev_destroy(swgldev_ctx* c);
 const char*  swgldev_last_error(swgldev_ctx* c);      /* "" when none; sticky until read */
 void*        swgldev_stream(swgldev_ctx* c);          /* cudaStream_t all work is queued on */

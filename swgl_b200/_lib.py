@@ -35,6 +35,7 @@ EXTENSION_EXPORTS = {
     "swglGetStream": (C.c_void_p, []),
     "swglGetColorDevicePtr": (C.c_uint64, []),
     "swglPrecompileProgram": (C.c_int, []),
+    "swglSetDeviceCount": (None, [C.c_int]),
     "swglGetDepthDevicePtr": (C.c_uint64, []),
     "swglFillFramebuffer": (None, [C.c_uint32, C.c_float]),
     "swglBufferRespecify": (None, [C.c_uint32, C.c_uint32, C.c_void_p]),

@@ -39,6 +39,8 @@
 #include "swgl_dev_common.cuh"
 #include "swgl_jit.h"
 
+#define SWGL_MAX_GROUP 16
+
 /* ========================================================================================
  * context
  * ====================================================================================== */
@@ -123,7 +125,22 @@ struct swgldev_ctx
 	swgldev_stats stats;
 	uint64_t n_draws;
 	char error[512];
+
+	/* Device group (swgldev_create_group): one host thread drives several GPUs.  The leader (member 0, the
+	 * handle the host layer holds) carries the member list and the table that maps an allocation of member 0
+	 * to its replicas on the other devices; every entry point called on the leader fans out to the members
+	 * (sort-first bands, geometry replicated, every member stores its finished tiles into the leader's pinned
+	 * frame mirror over its own PCIe link).  `solo` > 0: the call is the fan-out itself. */
+	swgldev_ctx* group[SWGL_MAX_GROUP];
+	int n_group, solo;
+	std::map<uintptr_t, std::vector<swgldev_ptr>> replicas;
+	int mirror_borrowed;                 /* shared_mirror is the leader's pinned mirror: nothing to unregister */
+	cudaEvent_t slice_ev, gather_ev;     /* group uploads: this member's slice has arrived / its replica is complete */
+	int gather_pending;
 };
+
+#define IS_GROUP(c) ((c)->n_group > 1 && !(c)->solo)
+struct Solo { swgldev_ctx* m; explicit Solo(swgldev_ctx* m_) : m(m_) { m->solo++; } ~Solo() { m->solo--; } };
 
 static void set_err(swgldev_ctx* c, const char* what, cudaError_t e)
 {
@@ -1097,6 +1114,8 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->n_draws = 0; c->error[0] = 0;
+	for (int i = 0; i < SWGL_MAX_GROUP; i++) c->group[i] = nullptr;
+	c->n_group = 1; c->solo = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0;
 
 	const size_t npx = (size_t)width * height;
 	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
@@ -1106,7 +1125,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaMalloc((void**)&c->color, (npx ? npx : 1) * 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->depth, (npx ? npx : 1) * 4) == cudaSuccess
-	       && cudaMallocHost((void**)&c->h_mirror[0], (npx ? npx : 1) * 4) == cudaSuccess
+	       && cudaHostAlloc((void**)&c->h_mirror[0], (npx ? npx : 1) * 4, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess   /* portable: the members of a device group write into it */
 	       && cudaStreamCreateWithPriority(&c->upload, cudaStreamNonBlocking, prio_hi) == cudaSuccess
 	       && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming) == cudaSuccess
@@ -1115,7 +1134,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMalloc((void**)&c->lut255, 256 * sizeof(float)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[0], cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[1], cudaEventDisableTiming) == cudaSuccess
-	       && cudaMallocHost((void**)&c->h_depth, (npx ? npx : 1) * 4) == cudaSuccess
+	       && cudaHostAlloc((void**)&c->h_depth, (npx ? npx : 1) * 4, cudaHostAllocPortable) == cudaSuccess
 	       && cudaMalloc((void**)&c->tile_count, (ntiles + 1) * 4) == cudaSuccess
 	       && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->setup_event, cudaEventDisableTiming) == cudaSuccess
@@ -1123,6 +1142,8 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMalloc((void**)&c->ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_ctr, sizeof(Counters)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->ctr_event, cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->slice_ev, cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->gather_ev, cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[0]) == cudaSuccess && cudaEventCreate(&c->stage_ev[1]) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[2]) == cudaSuccess && cudaEventCreate(&c->stage_ev[3]) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[4]) == cudaSuccess && cudaEventCreate(&c->stage_ev[5]) == cudaSuccess
@@ -1152,12 +1173,81 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	return c;
 }
 
+/* glInit with swglSetDeviceCount(n): n device contexts on ordinals device .. device+n-1 driven by the calling
+ * thread (SURVEY.md 7 step 3, 8b "one host thread drives all GPUs").  Sort-first: tile-row bands of 32 rows are
+ * dealt round-robin (at least 16 bands per member), geometry and textures are replicated, and every member
+ * stores the tiles it finishes into the leader's pinned frame mirror over its own PCIe link. */
+swgldev_ctx* swgldev_create_group(int device, int count, uint32_t width, uint32_t height)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return nullptr; }
+	if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+	if (count <= 1) return swgldev_create(device, width, height);
+	/* SWGL_B200_GROUP_EMULATE=1 (tests on a box with fewer GPUs): members beyond the visible devices wrap around
+	 * and share a device -- same code path, same bands, same copies, no speed-up */
+	const char* emu = getenv("SWGL_B200_GROUP_EMULATE");
+	const bool wrap = emu && emu[0] == '1';
+	if (count > SWGL_MAX_GROUP || (!wrap && device + count > n))
+	{
+		fprintf(stderr, "swgl_b200: %d devices from ordinal %d requested, %d visible\n", count, device, n);
+		return nullptr;
+	}
+	swgldev_ctx* members[SWGL_MAX_GROUP];
+	int ord[SWGL_MAX_GROUP];
+	for (int i = 0; i < count; i++)
+	{
+		ord[i] = (device + i) % n;
+		members[i] = swgldev_create(ord[i], width, height);
+		if (!members[i]) { for (int j = 0; j < i; j++) swgldev_destroy(members[j]); return nullptr; }
+	}
+	/* NVLink between the replicas: the all-gather of a sharded upload copies device to device */
+	for (int i = 0; i < count; i++)
+	{
+		cudaSetDevice(ord[i]);
+		for (int j = 0; j < count; j++)
+			if (ord[j] != ord[i])
+			{
+				int can = 0;
+				if (cudaDeviceCanAccessPeer(&can, ord[i], ord[j]) == cudaSuccess && can)
+				{
+					const cudaError_t e = cudaDeviceEnablePeerAccess(ord[j], 0);
+					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fprintf(stderr, "swgl_b200: no peer access %d -> %d (%s): uploads fall back to staged copies\n", ord[i], ord[j], cudaGetErrorString(e));
+				}
+				cudaGetLastError();
+			}
+	}
+	swgldev_ctx* c = members[0];
+	const uint32_t tiles_y32 = (height + 31u) / 32u;
+	uint32_t band = tiles_y32 / ((uint32_t)count * 16u);
+	if (band == 0) band = 1;
+	for (int i = 0; i < count; i++)
+	{
+		swgldev_ctx* m = members[i];
+		c->group[i] = m;
+		m->rank = (uint32_t)i; m->n_ranks = (uint32_t)count; m->band_rows = band;
+		/* the leader's pinned mirror is every member's write-through target (page-locked, portable, mapped) */
+		m->shared_mirror = c->h_mirror[0]; m->shared_mirror_dev = c->h_mirror[0];
+		m->shared_mirror_bytes = (size_t)width * height * 4; m->mirror_borrowed = 1; m->mirror_synced = 0;
+	}
+	c->n_group = count;
+	cudaSetDevice(c->device);
+	return c;
+}
+
 void swgldev_destroy(swgldev_ctx* c)
 {
 	if (!c) return;
+	if (c->n_group > 1)
+	{
+		/* every member drains before the leader's pinned mirror (which they write into) goes */
+		for (int i = 0; i < c->n_group; i++) if (c->group[i] && c->group[i]->stream) { cudaSetDevice(c->group[i]->device); cudaStreamSynchronize(c->group[i]->stream); cudaStreamSynchronize(c->group[i]->upload); }
+		for (int i = 1; i < c->n_group; i++) { swgldev_destroy(c->group[i]); c->group[i] = nullptr; }
+		c->n_group = 1;
+	}
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	if (c->shared_mirror) { cudaHostUnregister(c->shared_mirror); c->shared_mirror = nullptr; }
+	if (c->shared_mirror && !c->mirror_borrowed) cudaHostUnregister(c->shared_mirror);
+	c->shared_mirror = nullptr;
 	for (void* p : c->allocations) cudaFree(p);
 	for (auto& kv : c->code_cache) cudaFree(kv.second);
 	if (c->upload) { cudaStreamSynchronize(c->upload); cudaStreamDestroy(c->upload); }
@@ -1183,6 +1273,8 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->bands) cudaFree(c->bands);
 	if (c->pairs) cudaFree(c->pairs);
 	if (c->ctr_event) cudaEventDestroy(c->ctr_event);
+	if (c->slice_ev) cudaEventDestroy(c->slice_ev);
+	if (c->gather_ev) cudaEventDestroy(c->gather_ev);
 	for (int i = 0; i < 8; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	cudaGetLastError();
@@ -1192,6 +1284,17 @@ void swgldev_destroy(swgldev_ctx* c)
 const char* swgldev_last_error(swgldev_ctx* c)
 {
 	static char out[512];
+	out[0] = 0;
+	if (IS_GROUP(c))
+	{   /* the first member that has something to say; all are cleared */
+		for (int i = 0; i < c->n_group; i++)
+		{
+			swgldev_ctx* m = c->group[i];
+			if (!out[0] && m->error[0]) { if (i) snprintf(out, sizeof(out), "device %d: %.480s", m->device, m->error); else snprintf(out, sizeof(out), "%s", m->error); }
+			m->error[0] = 0;
+		}
+		return out;
+	}
 	snprintf(out, sizeof(out), "%s", c->error);
 	c->error[0] = 0;
 	return out;
@@ -1199,8 +1302,30 @@ const char* swgldev_last_error(swgldev_ctx* c)
 
 void* swgldev_stream(swgldev_ctx* c) { return (void*)c->stream; }
 
+/* the replica of a leader allocation on member i (the leader's own pointer for i = 0 or an address it does not know) */
+static swgldev_ptr member_ptr(swgldev_ctx* leader, int i, swgldev_ptr p)
+{
+	if (!p) return 0;
+	auto it = leader->replicas.find((uintptr_t)p);
+	if (it == leader->replicas.end()) return i == 0 ? p : 0;
+	return it->second[(size_t)i];
+}
+
 swgldev_ptr swgldev_alloc(swgldev_ctx* c, uint64_t bytes)
 {
+	if (IS_GROUP(c))
+	{
+		std::vector<swgldev_ptr> reps;
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); reps.push_back(swgldev_alloc(c->group[i], bytes)); }
+		for (int i = 0; i < c->n_group; i++)
+			if (!reps[(size_t)i])
+			{
+				for (int j = 0; j < c->n_group; j++) if (reps[(size_t)j]) { Solo s(c->group[j]); swgldev_free(c->group[j], reps[(size_t)j]); }
+				return 0;
+			}
+		c->replicas[(uintptr_t)reps[0]] = reps;
+		return reps[0];
+	}
 	void* p = nullptr;
 	cudaSetDevice(c->device);
 	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
@@ -1214,6 +1339,15 @@ static int settle_last_draw(swgldev_ctx* c);
 
 void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 {
+	if (IS_GROUP(c))
+	{
+		auto it = c->replicas.find((uintptr_t)p);
+		if (it == c->replicas.end()) return;
+		const std::vector<swgldev_ptr> reps = it->second;
+		c->replicas.erase(it);
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_free(c->group[i], reps[(size_t)i]); }
+		return;
+	}
 	void* q = (void*)(uintptr_t)p;
 	/* an overflowed draw is re-issued from the raw pointers it was launched with: resolve it while
 	 * the memory it reads is still there */
@@ -1231,8 +1365,94 @@ void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 		}
 }
 
+static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const void* src, uint64_t bytes, uint32_t* max_index);
+
+static void queue_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
+
+/* Device group: `bytes` of host memory into every member's replica of `dst` (+ offset).  Member i copies
+ * slice i over ITS PCIe link, then pulls the other slices from the members that hold them over NVLink
+ * (cudaMemcpyPeerAsync); the call returns when the host memory has been read (the caller may free it,
+ * swgl.c:3142), the device-to-device part only holds back the members' own draw streams.  With `max_index`
+ * each member also reduces the largest u32 of its slice (element data). */
+static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const void* src, uint64_t bytes, uint32_t* max_index)
+{
+	const int n = c->n_group;
+	if (max_index) *max_index = 0;
+	if (bytes == 0) return 0;
+	uint64_t slice = (bytes + (uint64_t)n - 1) / (uint64_t)n;
+	slice = (slice + 255u) & ~(uint64_t)255u;
+	int rc = 0;
+	/* 1. hazards: a replica may still be read by its member's queued draws, or by another member's pull of the
+	 * previous upload */
+	for (int i = 0; i < n; i++)
+	{
+		swgldev_ctx* m = c->group[i];
+		cudaSetDevice(m->device);
+		if (settle_last_draw(m)) rc = -1;
+		auto it = m->last_use.find((uintptr_t)member_ptr(c, i, dst));
+		if (it != m->last_use.end() && it->second)
+		{
+			const uint64_t sr = (m->draw_serial - it->second < 8u) ? it->second : m->draw_serial;
+			if (cudaStreamWaitEvent(m->upload, m->draw_ev[sr & 7u], 0) != cudaSuccess) rc = -1;
+		}
+		for (int j = 0; j < n; j++) if (c->group[j]->gather_pending) cudaStreamWaitEvent(m->upload, c->group[j]->gather_ev, 0);
+	}
+	/* 2. every member's own slice from the host */
+	for (int i = 0; i < n; i++)
+	{
+		swgldev_ctx* m = c->group[i];
+		const uint64_t lo = (uint64_t)i * slice, hi = lo + slice < bytes ? lo + slice : bytes;
+		cudaSetDevice(m->device);
+		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
+		if (!rep) { set_err(c, "upload: not a buffer of this device group", cudaSuccess); return -1; }
+		if (lo < hi)
+		{
+			if (cudaMemcpyAsync(rep + offset + lo, (const char*)src + lo, hi - lo, cudaMemcpyHostToDevice, m->upload) != cudaSuccess) rc = -1;
+			if (max_index) queue_max_index(m, (swgldev_ptr)(uintptr_t)(rep + offset + lo), hi - lo);
+		}
+		else if (max_index) *m->h_maxidx = 0;
+		if (cudaEventRecord(m->slice_ev, m->upload) != cudaSuccess) rc = -1;
+	}
+	/* 3. the other slices, device to device */
+	for (int i = 0; i < n; i++)
+	{
+		swgldev_ctx* m = c->group[i];
+		cudaSetDevice(m->device);
+		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
+		for (int k = 1; k < n; k++)
+		{
+			const int j = (i + k) % n;                 /* staggered: at any time every member is pulled from once */
+			const uint64_t lo = (uint64_t)j * slice, hi = lo + slice < bytes ? lo + slice : bytes;
+			if (lo >= hi) continue;
+			swgldev_ctx* o = c->group[j];
+			const char* from = (const char*)(uintptr_t)member_ptr(c, j, dst);
+			if (cudaStreamWaitEvent(m->upload, o->slice_ev, 0) != cudaSuccess) rc = -1;
+			if (cudaMemcpyPeerAsync(rep + offset + lo, m->device, from + offset + lo, o->device, hi - lo, m->upload) != cudaSuccess) rc = -1;
+		}
+		if (cudaEventRecord(m->gather_ev, m->upload) != cudaSuccess) rc = -1;
+		m->gather_pending = 1;
+		if (cudaStreamWaitEvent(m->stream, m->gather_ev, 0) != cudaSuccess) rc = -1;      /* the member's draws read the whole replica */
+	}
+	/* 4. the host memory has been read once every slice has landed */
+	for (int i = 0; i < n; i++)
+	{
+		swgldev_ctx* m = c->group[i];
+		if (cudaEventSynchronize(m->slice_ev) != cudaSuccess) rc = -1;
+		if (max_index && *m->h_maxidx > *max_index) *max_index = *m->h_maxidx;
+	}
+	cudaSetDevice(c->device);
+	if (rc) set_err(c, "upload to the device group failed", cudaGetLastError());
+	return rc;
+}
+
 int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes)
 {
+	if (IS_GROUP(c))
+	{
+		int rc = 0;
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_upload(c->group[i], member_ptr(c, i, dst), src, bytes); }
+		return rc;
+	}
 	/* ... and before the contents it reads are replaced */
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
@@ -1247,6 +1467,7 @@ int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t by
  * allocation: it overlaps whatever else is queued (the frame being rasterised, for instance). */
 int swgldev_upload_overlapped(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes)
 {
+	if (IS_GROUP(c)) return group_upload(c, dst, 0, src, bytes, nullptr);
 	cudaSetDevice(c->device);
 	/* an overflowed draw is re-issued from its buffers: resolve it before they may change */
 	if (settle_last_draw(c)) return -1;
@@ -1287,6 +1508,7 @@ void swgldev_host_free(void* p) { cudaFreeHost(p); }
 
 uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 {
+	if (IS_GROUP(c)) { Solo s(c); return swgldev_max_index(c, indices, bytes); }   /* the replicas hold the same data */
 	cudaSetDevice(c->device);
 	if (bytes < 4u) return 0;
 	/* on the upload stream: the buffer was just written there and nothing later has been queued */
@@ -1298,6 +1520,7 @@ uint32_t swgldev_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 /* Part of an allocation: `base` names it (for the read hazards), the copy goes to base + offset. */
 int swgldev_upload_range(swgldev_ctx* c, swgldev_ptr base, uint64_t offset, const void* src, uint64_t bytes)
 {
+	if (IS_GROUP(c)) return group_upload(c, base, offset, src, bytes, nullptr);
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
 	auto it = c->last_use.find((uintptr_t)base);
@@ -1317,6 +1540,7 @@ int swgldev_upload_range(swgldev_ctx* c, swgldev_ptr base, uint64_t offset, cons
  * application's, say) has just written: the reduction runs behind that work. */
 uint32_t swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes)
 {
+	if (IS_GROUP(c)) { Solo s(c); return swgldev_max_index_after_stream(c, indices, bytes); }
 	cudaSetDevice(c->device);
 	if (bytes < 4u) return 0;
 	if (cudaEventRecord(c->app_event, c->stream) != cudaSuccess) return 0;
@@ -1329,6 +1553,7 @@ uint32_t swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices, uin
 /* swgldev_upload_overlapped of element data plus the largest index in it, with one wait for both */
 int swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index)
 {
+	if (IS_GROUP(c)) return group_upload(c, dst, 0, src, bytes, max_index);
 	cudaSetDevice(c->device);
 	*max_index = 0;
 	if (settle_last_draw(c)) return -1;
@@ -1448,6 +1673,13 @@ static int flush_owned_bands(swgldev_ctx* c);
 
 int swgldev_sync(swgldev_ctx* c)
 {
+	if (IS_GROUP(c))
+	{
+		int rc = 0;
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_sync(c->group[i]); }
+		cudaSetDevice(c->device);
+		return rc;
+	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
 	if (flush_clear(c)) return -1;
@@ -1465,6 +1697,27 @@ int swgldev_sync(swgldev_ctx* c)
 
 swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, int32_t* n_levels)
 {
+	if (IS_GROUP(c))
+	{
+		std::vector<swgldev_ptr> reps;
+		bool ok = true;
+		for (int i = 0; i < c->n_group; i++)
+		{
+			Solo s(c->group[i]);
+			swgldev_texture b = *base;
+			b.data = member_ptr(c, i, base->data);
+			reps.push_back(swgldev_build_mipmaps(c->group[i], &b, n_levels));
+			ok = ok && reps.back();
+		}
+		if (!ok)
+		{
+			for (int i = 0; i < c->n_group; i++) if (reps[(size_t)i]) { Solo s(c->group[i]); swgldev_free(c->group[i], reps[(size_t)i]); }
+			*n_levels = 0;
+			return 0;
+		}
+		c->replicas[(uintptr_t)reps[0]] = reps;
+		return reps[0];
+	}
 	cudaSetDevice(c->device);
 	*n_levels = 0;
 	if (!base->data || base->fpp < 1 || base->fpp > 4) return 0;
@@ -1516,6 +1769,12 @@ swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, i
 
 int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
 {
+	if (IS_GROUP(c))
+	{
+		int rc = 0;
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_clear(c->group[i], flags, color_word, x0, y0, x1, y1); }
+		return rc;
+	}
 	cudaSetDevice(c->device);
 	if (!flags) return 0;
 	if (settle_last_draw(c)) return -1;
@@ -1537,6 +1796,11 @@ int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word, int32_t x
 
 void swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth)
 {
+	if (IS_GROUP(c))
+	{
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_fill(c->group[i], color_word, depth); }
+		return;
+	}
 	cudaSetDevice(c->device);
 	settle_last_draw(c);
 	c->pending_clear.flags = 0;
@@ -1715,6 +1979,19 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 {
+	if (IS_GROUP(c))
+	{
+		int rc = 0;
+		for (int i = 0; i < c->n_group; i++)
+		{
+			Solo s(c->group[i]);
+			swgldev_draw di = *d;
+			di.vbo = member_ptr(c, i, d->vbo); di.ibo = member_ptr(c, i, d->ibo);
+			for (int u = 0; u < SWGL_MAX_TEX_UNITS; u++) { di.tex[u].data = member_ptr(c, i, d->tex[u].data); di.tex[u].mips = member_ptr(c, i, d->tex[u].mips); }
+			rc |= swgldev_draw_triangles(c->group[i], &di);
+		}
+		return rc;
+	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
 	c->last_draw_valid = 0;
@@ -1815,6 +2092,19 @@ int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t 
 
 int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 {
+	if (IS_GROUP(c))
+	{
+		int rc = 0;
+		for (int i = 0; i < c->n_group; i++)
+		{
+			Solo s(c->group[i]);
+			swgldev_draw di = *d;
+			di.vbo = member_ptr(c, i, d->vbo); di.ibo = member_ptr(c, i, d->ibo);
+			for (int u = 0; u < SWGL_MAX_TEX_UNITS; u++) { di.tex[u].data = member_ptr(c, i, d->tex[u].data); di.tex[u].mips = member_ptr(c, i, d->tex[u].mips); }
+			rc |= swgldev_draw_points(c->group[i], &di);
+		}
+		return rc;
+	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
 	c->last_draw_valid = 0;
@@ -1870,6 +2160,14 @@ static int flush_owned_bands(swgldev_ctx* c)
 
 uint32_t* swgldev_map_color(swgldev_ctx* c)
 {
+	if (IS_GROUP(c))
+	{
+		/* every member brings its bands of the leader's pinned mirror up to date (written through by its raster
+		 * kernels, or copied by its swgldev_sync) */
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_map_color(c->group[i]); }
+		cudaSetDevice(c->device);
+		return c->h_mirror[0];
+	}
 	if (c->shared_mirror)
 	{
 		/* swgldev_sync has brought this rank's bands up to date; the other ranks' are theirs to finish
@@ -1894,6 +2192,7 @@ uint32_t* swgldev_map_color(swgldev_ctx* c)
 /* ---- frame pipelining ---- */
 uint64_t swgldev_frame_submit(swgldev_ctx* c)
 {
+	if (IS_GROUP(c)) { set_err(c, "swglFrameSubmit: not available with several devices (swglSetDeviceCount)", cudaSuccess); return 0; }
 	cudaSetDevice(c->device);
 	if (c->shared_mirror) { set_err(c, "swglFrameSubmit: not available with a shared frame mirror", cudaSuccess); return 0; }
 	if (settle_last_draw(c) || flush_clear(c)) return 0;
@@ -1943,6 +2242,13 @@ const uint32_t* swgldev_frame_wait(swgldev_ctx* c, uint64_t ticket)
 /* glGetFramePtr consumers that want bytes in R, G, B, A order: swizzled on the device, then copied */
 int swgldev_read_rgba8(swgldev_ctx* c, void* dst)
 {
+	if (IS_GROUP(c))
+	{   /* the assembled frame only exists in host memory: swizzle it there */
+		const uint32_t* src = swgldev_map_color(c);
+		uint8_t* o = (uint8_t*)dst;
+		for (size_t i = 0, n = (size_t)c->W * c->H; i < n; i++) { const uint32_t w = src[i]; o[4 * i] = (uint8_t)(w >> 24); o[4 * i + 1] = (uint8_t)(w >> 16); o[4 * i + 2] = (uint8_t)(w >> 8); o[4 * i + 3] = (uint8_t)w; }
+		return 0;
+	}
 	if (swgldev_sync(c)) return -1;
 	const size_t n = (size_t)c->W * c->H;
 	if (!n) return 0;
@@ -1954,8 +2260,29 @@ int swgldev_read_rgba8(swgldev_ctx* c, void* dst)
 	return 0;
 }
 
+/* rows of the depth attachment this member owns, into `dst` (the leader's pinned depth mirror) */
+static int copy_owned_depth_bands(swgldev_ctx* m, float* dst)
+{
+	const uint32_t band_px = 32u * (m->band_rows ? m->band_rows : 1u);
+	cudaSetDevice(m->device);
+	for (uint32_t b = 0; (size_t)b * band_px < m->H; b++)
+	{
+		if (m->n_ranks > 1 && b % m->n_ranks != m->rank) continue;
+		const size_t r0 = (size_t)b * band_px, r1 = (r0 + band_px < m->H) ? r0 + band_px : m->H;
+		if (cudaMemcpyAsync(dst + r0 * m->W, m->depth + r0 * m->W, (r1 - r0) * m->W * 4, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess) return -1;
+	}
+	return cudaStreamSynchronize(m->stream) == cudaSuccess ? 0 : -1;
+}
+
 float* swgldev_map_depth(swgldev_ctx* c)
 {
+	if (IS_GROUP(c))
+	{
+		swgldev_sync(c);
+		for (int i = 0; i < c->n_group; i++) if (copy_owned_depth_bands(c->group[i], c->h_depth)) set_err(c, "depth read-back of a device group member failed", cudaGetLastError());
+		cudaSetDevice(c->device);
+		return c->h_depth;
+	}
 	if (swgldev_sync(c)) return c->h_depth;
 	cudaMemcpyAsync(c->h_depth, c->depth, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream);
 	cudaStreamSynchronize(c->stream);
@@ -1972,6 +2299,24 @@ swgldev_ptr swgldev_depth_devptr(swgldev_ctx* c) { return (swgldev_ptr)(uintptr_
 
 void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out)
 {
+	if (IS_GROUP(c))
+	{
+		/* fragments and list entries add up over the members (a pixel belongs to one of them); a primitive
+		 * that spans bands of several members is counted by each */
+		swgldev_stats sum;
+		memset(&sum, 0, sizeof(sum));
+		for (int i = 0; i < c->n_group; i++)
+		{
+			Solo s(c->group[i]);
+			swgldev_stats one;
+			swgldev_get_stats(c->group[i], &one);
+			sum.draws = one.draws; sum.triangles_in = one.triangles_in;
+			sum.prims_out += one.prims_out; sum.tested += one.tested; sum.shaded += one.shaded; sum.tile_pairs += one.tile_pairs; sum.bands += one.bands;
+		}
+		cudaSetDevice(c->device);
+		*out = sum;
+		return;
+	}
 	swgldev_sync(c);
 	Counters h;
 	if (cudaMemcpy(&h, c->ctr, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -1986,6 +2331,7 @@ void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out)
 
 void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_t band_tile_rows)
 {
+	if (IS_GROUP(c)) { set_err(c, "swglSetStripe: the device group shards the frame itself (swglSetDeviceCount)", cudaSuccess); return; }
 	swgldev_sync(c);
 	c->rank = rank; c->n_ranks = n_ranks ? n_ranks : 1; c->band_rows = band_tile_rows ? band_tile_rows : 1;
 	if (c->shared_mirror) c->mirror_synced = 0;     /* other bands are this rank's now */
@@ -1993,12 +2339,14 @@ void swgldev_set_stripe(swgldev_ctx* c, uint32_t rank, uint32_t n_ranks, uint32_
 
 void swgldev_set_peer_color(swgldev_ctx* c, swgldev_ptr peer_color)
 {
+	if (IS_GROUP(c)) { set_err(c, "swglSetPeerColorTarget: not available with several devices (swglSetDeviceCount)", cudaSuccess); return; }
 	swgldev_sync(c);
 	c->peer_color = (uint32_t*)(uintptr_t)peer_color;
 }
 
 int swgldev_set_shared_mirror(swgldev_ctx* c, void* host_ptr, uint64_t bytes)
 {
+	if (c->n_group > 1 || c->mirror_borrowed) { set_err(c, "swglSetSharedFrameMirror: the device group assembles the frame in its own mirror (swglSetDeviceCount)", cudaSuccess); return -1; }
 	cudaSetDevice(c->device);
 	swgldev_sync(c);
 	if (c->shared_mirror)
@@ -2046,6 +2394,12 @@ void swgldev_ipc_close(swgldev_ctx* c, swgldev_ptr p)
 
 void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 {
+	if (IS_GROUP(c))
+	{
+		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_set_option(c->group[i], name, value); }
+		cudaSetDevice(c->device);
+		return;
+	}
 	swgldev_sync(c);
 	if (!strcmp(name, "fuse_clear")) c->opt_fuse_clear = (int)value;
 	else if (!strcmp(name, "count_fragments")) c->opt_count_fragments = (int)value;
@@ -2116,6 +2470,13 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "bin_cap")) return c->bin_cap;
 	if (!strcmp(name, "selftest_division_mismatches")) return c->selftest_mismatches;
 	if (!strcmp(name, "device")) return c->device;
+	if (!strcmp(name, "device_count")) return c->n_group;
+	if (!strcmp(name, "kernel_launches_all_devices"))
+	{
+		int64_t n = 0;
+		for (int i = 0; i < c->n_group; i++) n += (int64_t)(c->n_group > 1 ? c->group[i] : c)->n_launches;
+		return n;
+	}
 	if (!strcmp(name, "sizeof_draw_params")) return (int64_t)sizeof(DrawParams);
 	return -1;
 }

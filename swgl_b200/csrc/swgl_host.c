@@ -86,6 +86,7 @@ static struct
 {
 	swgldev_ctx* dev;
 	int device_ordinal;          /* -1: default */
+	int device_count;            /* devices the next glInit drives (swglSetDeviceCount), 0/1 = one */
 	uint32_t width, height;
 
 	VEC(gl_shader) shaders;
@@ -164,7 +165,8 @@ void glInit(GLsizei width, GLsizei height)
 		const char* lr = getenv("LOCAL_RANK");
 		ordinal = lr ? atoi(lr) : -1;
 	}
-	G.dev = swgldev_create(ordinal, width, height);
+	G.dev = G.device_count > 1 ? swgldev_create_group(ordinal < 0 ? 0 : ordinal, G.device_count, width, height)
+	                           : swgldev_create(ordinal, width, height);
 	if (!G.dev)
 	{
 		/* no CPU fallback: every later hot-path call is a no-op and the error is sticky */
@@ -251,6 +253,7 @@ void swglGetStats(swglStats* out)
 }
 
 void swglSetDevice(int ordinal) { G.device_ordinal = ordinal; }
+void swglSetDeviceCount(int count) { G.device_count = count; }
 void* swglGetStream(void) { return G.dev ? swgldev_stream(G.dev) : NULL; }
 uint64_t swglGetColorDevicePtr(void) { return G.dev ? swgldev_color_devptr(G.dev) : 0; }
 uint64_t swglGetDepthDevicePtr(void) { return G.dev ? swgldev_depth_devptr(G.dev) : 0; }
