@@ -33,13 +33,84 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "swgl_dev_common.cuh"
 #include "swgl_jit.h"
 
 #define SWGL_MAX_GROUP 16
+
+/* ========================================================================================
+ * device group workers
+ * ====================================================================================== */
+/* A device group is driven by the application's one thread, but a frame is a few dozen CUDA API calls PER
+ * DEVICE (uploads, event plumbing, three launches, a counter snapshot) and those calls cost microseconds
+ * each: issued one device after the other they -- not the GPUs -- set the frame time at eight devices.
+ * Member i > 0 therefore has a worker thread that issues member i's calls; run(f) executes f(i) for every
+ * member (f(0) on the caller) and returns when all are done.  Workers spin briefly between the fan-outs of
+ * a frame and sleep on a condition variable otherwise. */
+struct GroupPool
+{
+	int n = 0;
+	std::vector<std::thread> threads;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::atomic<uint64_t> epoch{0};
+	std::atomic<int> pending{0};
+	const std::function<void(int)>* fn = nullptr;
+	std::atomic<bool> quit{false};
+
+	void start(int count, const int* devices)
+	{
+		n = count;
+		for (int i = 1; i < count; i++) threads.emplace_back([this, i, d = devices[i]] { worker(i, d); });
+	}
+	void worker(int i, int device)
+	{
+		cudaSetDevice(device);
+		uint64_t seen = 0;
+		for (;;)
+		{
+			int spins = 0;
+			while (epoch.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_acquire))
+			{
+				if (++spins < 20000) { __builtin_ia32_pause(); continue; }
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait_for(lk, std::chrono::milliseconds(50), [&] { return epoch.load(std::memory_order_acquire) != seen || quit.load(std::memory_order_acquire); });
+			}
+			if (quit.load(std::memory_order_acquire)) return;
+			seen = epoch.load(std::memory_order_acquire);
+			(*fn)(i);
+			pending.fetch_sub(1, std::memory_order_acq_rel);
+		}
+	}
+	void run(const std::function<void(int)>& f)
+	{
+		fn = &f;
+		pending.store(n - 1, std::memory_order_release);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			epoch.fetch_add(1, std::memory_order_acq_rel);
+		}
+		cv.notify_all();
+		f(0);
+		while (pending.load(std::memory_order_acquire) > 0) __builtin_ia32_pause();
+	}
+	void stop()
+	{
+		quit.store(true, std::memory_order_release);
+		{ std::lock_guard<std::mutex> lk(mu); }
+		cv.notify_all();
+		for (auto& t : threads) t.join();
+		threads.clear();
+	}
+};
 
 /* ========================================================================================
  * context
@@ -133,6 +204,8 @@ struct swgldev_ctx
 	 * frame mirror over its own PCIe link).  `solo` > 0: the call is the fan-out itself. */
 	swgldev_ctx* group[SWGL_MAX_GROUP];
 	int n_group, solo;
+	GroupPool* pool;                     /* leader: one worker thread per further member */
+	int group_peer_ok;                   /* every member can load from every other member's memory */
 	std::map<uintptr_t, std::vector<swgldev_ptr>> replicas;
 	int mirror_borrowed;                 /* shared_mirror is the leader's pinned mirror: nothing to unregister */
 	cudaEvent_t slice_ev, gather_ev;     /* group uploads: this member's slice has arrived / its replica is complete */
@@ -141,6 +214,18 @@ struct swgldev_ctx
 
 #define IS_GROUP(c) ((c)->n_group > 1 && !(c)->solo)
 struct Solo { swgldev_ctx* m; explicit Solo(swgldev_ctx* m_) : m(m_) { m->solo++; } ~Solo() { m->solo--; } };
+
+/* f(i, member i) for every member of the leader's group, each on the thread that drives that member; the
+ * member is marked solo for the duration (its entry points then act on it alone).  Returns the OR of the results. */
+static int group_each(swgldev_ctx* c, const std::function<int(int, swgldev_ctx*)>& f)
+{
+	std::atomic<int> rc{0};
+	const std::function<void(int)> body = [&](int i) { swgldev_ctx* m = c->group[i]; Solo s(m); cudaSetDevice(m->device); if (f(i, m)) rc.fetch_or(1); };
+	if (c->pool) c->pool->run(body);
+	else for (int i = 0; i < c->n_group; i++) body(i);
+	cudaSetDevice(c->device);
+	return rc.load() ? -1 : 0;
+}
 
 static void set_err(swgldev_ctx* c, const char* what, cudaError_t e)
 {
@@ -196,6 +281,36 @@ __global__ void k_fill_fb(uint32_t* __restrict__ color, float* __restrict__ dept
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (; i < n; i += stride) { color[i] = word; depth[i] = d; }
+}
+
+/* ---- device group: the all-gather of a sharded upload.  Every member holds its own slice of the data in its
+ * replica; this kernel, run by member `self`, pulls the other members' slices out of THEIR replicas (peer
+ * loads over NVLink) into its own.  Slices are multiples of 256 bytes, replicas 16-byte aligned. ---- */
+struct GatherArgs
+{
+	const char* src[SWGL_MAX_GROUP];
+	char* dst;
+	unsigned long long slice, bytes;
+	int n, self;
+};
+
+__global__ void __launch_bounds__(256) k_group_gather(const __grid_constant__ GatherArgs a)
+{
+	const unsigned long long words = a.bytes >> 4, stride = (unsigned long long)gridDim.x * blockDim.x;
+	const unsigned long long lo = (unsigned long long)a.self * a.slice, hi = lo + a.slice;
+	for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride)
+	{
+		const unsigned long long at = w << 4;
+		if (at >= lo && at < hi) continue;
+		const unsigned long long j = at / a.slice;
+		*(uint4*)(a.dst + at) = *(const uint4*)(a.src[j] + at);
+	}
+	/* tail shorter than 16 bytes */
+	if (blockIdx.x == 0 && threadIdx.x < (a.bytes & 15ull))
+	{
+		const unsigned long long at = (words << 4) + threadIdx.x;
+		if (!(at >= lo && at < hi)) a.dst[at] = a.src[at / a.slice][at];
+	}
 }
 
 /* ---- glGenerateMipmap (swgl.c:2129-2171): one level of the 2x2 box chain, a thread per texel.  The
@@ -1115,7 +1230,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->n_draws = 0; c->error[0] = 0;
 	for (int i = 0; i < SWGL_MAX_GROUP; i++) c->group[i] = nullptr;
-	c->n_group = 1; c->solo = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0;
+	c->n_group = 1; c->solo = 0; c->pool = nullptr; c->group_peer_ok = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0;
 
 	const size_t npx = (size_t)width * height;
 	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
@@ -1201,6 +1316,7 @@ swgldev_ctx* swgldev_create_group(int device, int count, uint32_t width, uint32_
 		if (!members[i]) { for (int j = 0; j < i; j++) swgldev_destroy(members[j]); return nullptr; }
 	}
 	/* NVLink between the replicas: the all-gather of a sharded upload copies device to device */
+	int peer_ok = 1;
 	for (int i = 0; i < count; i++)
 	{
 		cudaSetDevice(ord[i]);
@@ -1208,14 +1324,18 @@ swgldev_ctx* swgldev_create_group(int device, int count, uint32_t width, uint32_
 			if (ord[j] != ord[i])
 			{
 				int can = 0;
-				if (cudaDeviceCanAccessPeer(&can, ord[i], ord[j]) == cudaSuccess && can)
+				cudaError_t e = cudaDeviceCanAccessPeer(&can, ord[i], ord[j]);
+				if (e == cudaSuccess && can)
 				{
-					const cudaError_t e = cudaDeviceEnablePeerAccess(ord[j], 0);
-					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fprintf(stderr, "swgl_b200: no peer access %d -> %d (%s): uploads fall back to staged copies\n", ord[i], ord[j], cudaGetErrorString(e));
+					e = cudaDeviceEnablePeerAccess(ord[j], 0);
+					if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
 				}
+				else can = 0;
+				if (!can) peer_ok = 0;      /* uploads fall back to cudaMemcpyPeerAsync (staged through the host if need be) */
 				cudaGetLastError();
 			}
 	}
+	members[0]->group_peer_ok = peer_ok;
 	swgldev_ctx* c = members[0];
 	const uint32_t tiles_y32 = (height + 31u) / 32u;
 	uint32_t band = tiles_y32 / ((uint32_t)count * 16u);
@@ -1230,6 +1350,8 @@ swgldev_ctx* swgldev_create_group(int device, int count, uint32_t width, uint32_
 		m->shared_mirror_bytes = (size_t)width * height * 4; m->mirror_borrowed = 1; m->mirror_synced = 0;
 	}
 	c->n_group = count;
+	c->pool = new GroupPool();
+	c->pool->start(count, ord);
 	cudaSetDevice(c->device);
 	return c;
 }
@@ -1241,6 +1363,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	{
 		/* every member drains before the leader's pinned mirror (which they write into) goes */
 		for (int i = 0; i < c->n_group; i++) if (c->group[i] && c->group[i]->stream) { cudaSetDevice(c->group[i]->device); cudaStreamSynchronize(c->group[i]->stream); cudaStreamSynchronize(c->group[i]->upload); }
+		if (c->pool) { c->pool->stop(); delete c->pool; c->pool = nullptr; }
 		for (int i = 1; i < c->n_group; i++) { swgldev_destroy(c->group[i]); c->group[i] = nullptr; }
 		c->n_group = 1;
 	}
@@ -1315,12 +1438,12 @@ swgldev_ptr swgldev_alloc(swgldev_ctx* c, uint64_t bytes)
 {
 	if (IS_GROUP(c))
 	{
-		std::vector<swgldev_ptr> reps;
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); reps.push_back(swgldev_alloc(c->group[i], bytes)); }
+		std::vector<swgldev_ptr> reps((size_t)c->n_group, 0);
+		group_each(c, [&](int i, swgldev_ctx* m) { reps[(size_t)i] = swgldev_alloc(m, bytes); return 0; });
 		for (int i = 0; i < c->n_group; i++)
 			if (!reps[(size_t)i])
 			{
-				for (int j = 0; j < c->n_group; j++) if (reps[(size_t)j]) { Solo s(c->group[j]); swgldev_free(c->group[j], reps[(size_t)j]); }
+				group_each(c, [&](int j, swgldev_ctx* m) { if (reps[(size_t)j]) swgldev_free(m, reps[(size_t)j]); return 0; });
 				return 0;
 			}
 		c->replicas[(uintptr_t)reps[0]] = reps;
@@ -1345,7 +1468,7 @@ void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 		if (it == c->replicas.end()) return;
 		const std::vector<swgldev_ptr> reps = it->second;
 		c->replicas.erase(it);
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_free(c->group[i], reps[(size_t)i]); }
+		group_each(c, [&](int i, swgldev_ctx* m) { swgldev_free(m, reps[(size_t)i]); return 0; });
 		return;
 	}
 	void* q = (void*)(uintptr_t)p;
@@ -1370,10 +1493,11 @@ static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const 
 static void queue_max_index(swgldev_ctx* c, swgldev_ptr indices, uint64_t bytes);
 
 /* Device group: `bytes` of host memory into every member's replica of `dst` (+ offset).  Member i copies
- * slice i over ITS PCIe link, then pulls the other slices from the members that hold them over NVLink
- * (cudaMemcpyPeerAsync); the call returns when the host memory has been read (the caller may free it,
- * swgl.c:3142), the device-to-device part only holds back the members' own draw streams.  With `max_index`
- * each member also reduces the largest u32 of its slice (element data). */
+ * slice i over ITS PCIe link, then one kernel per member pulls the other slices straight out of the peers'
+ * replicas over NVLink (k_group_gather, peer loads; cudaMemcpyPeerAsync per slice where peer access is
+ * missing).  The call returns when the host memory has been read (the caller may free it, swgl.c:3142); the
+ * device-to-device part only holds back the members' own draw streams.  With `max_index` each member also
+ * reduces the largest u32 of its slice (element data). */
 static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const void* src, uint64_t bytes, uint32_t* max_index)
 {
 	const int n = c->n_group;
@@ -1381,66 +1505,76 @@ static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const 
 	if (bytes == 0) return 0;
 	uint64_t slice = (bytes + (uint64_t)n - 1) / (uint64_t)n;
 	slice = (slice + 255u) & ~(uint64_t)255u;
-	int rc = 0;
-	/* 1. hazards: a replica may still be read by its member's queued draws, or by another member's pull of the
-	 * previous upload */
-	for (int i = 0; i < n; i++)
+	for (int i = 0; i < n; i++) if (!member_ptr(c, i, dst)) { set_err(c, "upload: not a buffer of this device group", cudaSuccess); return -1; }
+	/* 1. hazards (a replica may still be read by its member's queued draws, or by another member's pull of the
+	 * previous upload), then every member's own slice from the host */
+	int rc = group_each(c, [&](int i, swgldev_ctx* m)
 	{
-		swgldev_ctx* m = c->group[i];
-		cudaSetDevice(m->device);
-		if (settle_last_draw(m)) rc = -1;
-		auto it = m->last_use.find((uintptr_t)member_ptr(c, i, dst));
+		int r = 0;
+		if (settle_last_draw(m)) r = -1;
+		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
+		auto it = m->last_use.find((uintptr_t)rep);
 		if (it != m->last_use.end() && it->second)
 		{
 			const uint64_t sr = (m->draw_serial - it->second < 8u) ? it->second : m->draw_serial;
-			if (cudaStreamWaitEvent(m->upload, m->draw_ev[sr & 7u], 0) != cudaSuccess) rc = -1;
+			if (cudaStreamWaitEvent(m->upload, m->draw_ev[sr & 7u], 0) != cudaSuccess) r = -1;
 		}
-		for (int j = 0; j < n; j++) if (c->group[j]->gather_pending) cudaStreamWaitEvent(m->upload, c->group[j]->gather_ev, 0);
-	}
-	/* 2. every member's own slice from the host */
-	for (int i = 0; i < n; i++)
-	{
-		swgldev_ctx* m = c->group[i];
+		for (int j = 0; j < n; j++) if (j != i && c->group[j]->gather_pending) cudaStreamWaitEvent(m->upload, c->group[j]->gather_ev, 0);
 		const uint64_t lo = (uint64_t)i * slice, hi = lo + slice < bytes ? lo + slice : bytes;
-		cudaSetDevice(m->device);
-		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
-		if (!rep) { set_err(c, "upload: not a buffer of this device group", cudaSuccess); return -1; }
 		if (lo < hi)
 		{
-			if (cudaMemcpyAsync(rep + offset + lo, (const char*)src + lo, hi - lo, cudaMemcpyHostToDevice, m->upload) != cudaSuccess) rc = -1;
+			if (cudaMemcpyAsync(rep + offset + lo, (const char*)src + lo, hi - lo, cudaMemcpyHostToDevice, m->upload) != cudaSuccess) r = -1;
 			if (max_index) queue_max_index(m, (swgldev_ptr)(uintptr_t)(rep + offset + lo), hi - lo);
 		}
 		else if (max_index) *m->h_maxidx = 0;
-		if (cudaEventRecord(m->slice_ev, m->upload) != cudaSuccess) rc = -1;
-	}
-	/* 3. the other slices, device to device */
-	for (int i = 0; i < n; i++)
+		if (cudaEventRecord(m->slice_ev, m->upload) != cudaSuccess) r = -1;
+		return r;
+	});
+	/* 2. (every slice event has been recorded) the other slices, device to device; then the host waits for the
+	 * member's own slice only */
+	GatherArgs ga;
+	memset(&ga, 0, sizeof(ga));
+	for (int j = 0; j < n; j++) ga.src[j] = (const char*)(uintptr_t)member_ptr(c, j, dst) + offset;
+	ga.slice = slice; ga.bytes = bytes; ga.n = n;
+	const bool by_kernel = c->group_peer_ok && ((offset & 15u) == 0);
+	std::atomic<uint32_t> mx{0};
+	rc |= group_each(c, [&](int i, swgldev_ctx* m)
 	{
-		swgldev_ctx* m = c->group[i];
-		cudaSetDevice(m->device);
+		int r = 0;
 		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
 		for (int k = 1; k < n; k++)
 		{
-			const int j = (i + k) % n;                 /* staggered: at any time every member is pulled from once */
-			const uint64_t lo = (uint64_t)j * slice, hi = lo + slice < bytes ? lo + slice : bytes;
-			if (lo >= hi) continue;
-			swgldev_ctx* o = c->group[j];
-			const char* from = (const char*)(uintptr_t)member_ptr(c, j, dst);
-			if (cudaStreamWaitEvent(m->upload, o->slice_ev, 0) != cudaSuccess) rc = -1;
-			if (cudaMemcpyPeerAsync(rep + offset + lo, m->device, from + offset + lo, o->device, hi - lo, m->upload) != cudaSuccess) rc = -1;
+			const int j = (i + k) % n;
+			if ((uint64_t)j * slice < bytes && cudaStreamWaitEvent(m->upload, c->group[j]->slice_ev, 0) != cudaSuccess) r = -1;
 		}
-		if (cudaEventRecord(m->gather_ev, m->upload) != cudaSuccess) rc = -1;
+		if (by_kernel)
+		{
+			GatherArgs a = ga;
+			a.dst = rep + offset; a.self = i;
+			k_group_gather<<<148 * 2, 256, 0, m->upload>>>(a);
+			m->n_launches++;
+		}
+		else
+			for (int k = 1; k < n; k++)
+			{
+				const int j = (i + k) % n;                 /* staggered: at any time every member is pulled from once */
+				const uint64_t lo = (uint64_t)j * slice, hi = lo + slice < bytes ? lo + slice : bytes;
+				if (lo >= hi) continue;
+				if (cudaMemcpyPeerAsync(rep + offset + lo, m->device, ga.src[j] + lo, c->group[j]->device, hi - lo, m->upload) != cudaSuccess) r = -1;
+			}
+		if (cudaEventRecord(m->gather_ev, m->upload) != cudaSuccess) r = -1;
 		m->gather_pending = 1;
-		if (cudaStreamWaitEvent(m->stream, m->gather_ev, 0) != cudaSuccess) rc = -1;      /* the member's draws read the whole replica */
-	}
-	/* 4. the host memory has been read once every slice has landed */
-	for (int i = 0; i < n; i++)
-	{
-		swgldev_ctx* m = c->group[i];
-		if (cudaEventSynchronize(m->slice_ev) != cudaSuccess) rc = -1;
-		if (max_index && *m->h_maxidx > *max_index) *max_index = *m->h_maxidx;
-	}
-	cudaSetDevice(c->device);
+		if (cudaStreamWaitEvent(m->stream, m->gather_ev, 0) != cudaSuccess) r = -1;      /* the member's draws read the whole replica */
+		if (cudaEventSynchronize(m->slice_ev) != cudaSuccess) r = -1;                      /* the host memory has been read */
+		if (max_index)
+		{
+			uint32_t cur = mx.load();
+			const uint32_t v = *m->h_maxidx;
+			while (v > cur && !mx.compare_exchange_weak(cur, v)) { }
+		}
+		return r;
+	});
+	if (max_index) *max_index = mx.load();
 	if (rc) set_err(c, "upload to the device group failed", cudaGetLastError());
 	return rc;
 }
@@ -1449,9 +1583,7 @@ int swgldev_upload(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t by
 {
 	if (IS_GROUP(c))
 	{
-		int rc = 0;
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_upload(c->group[i], member_ptr(c, i, dst), src, bytes); }
-		return rc;
+		return group_each(c, [&](int i, swgldev_ctx* m) { return swgldev_upload(m, member_ptr(c, i, dst), src, bytes); });
 	}
 	/* ... and before the contents it reads are replaced */
 	cudaSetDevice(c->device);
@@ -1675,15 +1807,13 @@ int swgldev_sync(swgldev_ctx* c)
 {
 	if (IS_GROUP(c))
 	{
-		int rc = 0;
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_sync(c->group[i]); }
-		cudaSetDevice(c->device);
-		return rc;
+		return group_each(c, [&](int, swgldev_ctx* m) { return swgldev_sync(m); });
 	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
 	if (flush_clear(c)) return -1;
 	CK(cudaStreamSynchronize(c->stream));
+	c->gather_pending = 0;               /* the stream waited for the member's last group upload */
 	if (c->copy_inflight) CK(cudaStreamSynchronize(c->copy));
 	if (c->shared_mirror && !c->mirror_synced)
 	{
@@ -1699,19 +1829,21 @@ swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, i
 {
 	if (IS_GROUP(c))
 	{
-		std::vector<swgldev_ptr> reps;
-		bool ok = true;
-		for (int i = 0; i < c->n_group; i++)
+		std::vector<swgldev_ptr> reps((size_t)c->n_group, 0);
+		std::vector<int32_t> levels((size_t)c->n_group, 0);
+		group_each(c, [&](int i, swgldev_ctx* m)
 		{
-			Solo s(c->group[i]);
 			swgldev_texture b = *base;
 			b.data = member_ptr(c, i, base->data);
-			reps.push_back(swgldev_build_mipmaps(c->group[i], &b, n_levels));
-			ok = ok && reps.back();
-		}
+			reps[(size_t)i] = swgldev_build_mipmaps(m, &b, &levels[(size_t)i]);
+			return 0;
+		});
+		bool ok = true;
+		for (int i = 0; i < c->n_group; i++) ok = ok && reps[(size_t)i];
+		*n_levels = levels[0];
 		if (!ok)
 		{
-			for (int i = 0; i < c->n_group; i++) if (reps[(size_t)i]) { Solo s(c->group[i]); swgldev_free(c->group[i], reps[(size_t)i]); }
+			group_each(c, [&](int i, swgldev_ctx* m) { if (reps[(size_t)i]) swgldev_free(m, reps[(size_t)i]); return 0; });
 			*n_levels = 0;
 			return 0;
 		}
@@ -1771,9 +1903,7 @@ int swgldev_clear(swgldev_ctx* c, uint32_t flags, uint32_t color_word, int32_t x
 {
 	if (IS_GROUP(c))
 	{
-		int rc = 0;
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); rc |= swgldev_clear(c->group[i], flags, color_word, x0, y0, x1, y1); }
-		return rc;
+		return group_each(c, [&](int, swgldev_ctx* m) { return swgldev_clear(m, flags, color_word, x0, y0, x1, y1); });
 	}
 	cudaSetDevice(c->device);
 	if (!flags) return 0;
@@ -1798,7 +1928,7 @@ void swgldev_fill(swgldev_ctx* c, uint32_t color_word, float depth)
 {
 	if (IS_GROUP(c))
 	{
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_fill(c->group[i], color_word, depth); }
+		group_each(c, [&](int, swgldev_ctx* m) { swgldev_fill(m, color_word, depth); return 0; });
 		return;
 	}
 	cudaSetDevice(c->device);
@@ -1981,16 +2111,13 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 {
 	if (IS_GROUP(c))
 	{
-		int rc = 0;
-		for (int i = 0; i < c->n_group; i++)
+		return group_each(c, [&](int i, swgldev_ctx* m)
 		{
-			Solo s(c->group[i]);
 			swgldev_draw di = *d;
 			di.vbo = member_ptr(c, i, d->vbo); di.ibo = member_ptr(c, i, d->ibo);
 			for (int u = 0; u < SWGL_MAX_TEX_UNITS; u++) { di.tex[u].data = member_ptr(c, i, d->tex[u].data); di.tex[u].mips = member_ptr(c, i, d->tex[u].mips); }
-			rc |= swgldev_draw_triangles(c->group[i], &di);
-		}
-		return rc;
+			return swgldev_draw_triangles(m, &di);
+		});
 	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
@@ -2094,16 +2221,13 @@ int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d)
 {
 	if (IS_GROUP(c))
 	{
-		int rc = 0;
-		for (int i = 0; i < c->n_group; i++)
+		return group_each(c, [&](int i, swgldev_ctx* m)
 		{
-			Solo s(c->group[i]);
 			swgldev_draw di = *d;
 			di.vbo = member_ptr(c, i, d->vbo); di.ibo = member_ptr(c, i, d->ibo);
 			for (int u = 0; u < SWGL_MAX_TEX_UNITS; u++) { di.tex[u].data = member_ptr(c, i, d->tex[u].data); di.tex[u].mips = member_ptr(c, i, d->tex[u].mips); }
-			rc |= swgldev_draw_points(c->group[i], &di);
-		}
-		return rc;
+			return swgldev_draw_points(m, &di);
+		});
 	}
 	cudaSetDevice(c->device);
 	if (settle_last_draw(c)) return -1;
@@ -2164,8 +2288,7 @@ uint32_t* swgldev_map_color(swgldev_ctx* c)
 	{
 		/* every member brings its bands of the leader's pinned mirror up to date (written through by its raster
 		 * kernels, or copied by its swgldev_sync) */
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_map_color(c->group[i]); }
-		cudaSetDevice(c->device);
+		group_each(c, [&](int, swgldev_ctx* m) { swgldev_map_color(m); return 0; });
 		return c->h_mirror[0];
 	}
 	if (c->shared_mirror)
@@ -2279,8 +2402,8 @@ float* swgldev_map_depth(swgldev_ctx* c)
 	if (IS_GROUP(c))
 	{
 		swgldev_sync(c);
-		for (int i = 0; i < c->n_group; i++) if (copy_owned_depth_bands(c->group[i], c->h_depth)) set_err(c, "depth read-back of a device group member failed", cudaGetLastError());
-		cudaSetDevice(c->device);
+		if (group_each(c, [&](int, swgldev_ctx* m) { return copy_owned_depth_bands(m, c->h_depth); }))
+			set_err(c, "depth read-back of a device group member failed", cudaGetLastError());
 		return c->h_depth;
 	}
 	if (swgldev_sync(c)) return c->h_depth;
@@ -2303,17 +2426,15 @@ void swgldev_get_stats(swgldev_ctx* c, swgldev_stats* out)
 	{
 		/* fragments and list entries add up over the members (a pixel belongs to one of them); a primitive
 		 * that spans bands of several members is counted by each */
-		swgldev_stats sum;
+		swgldev_stats sum, each[SWGL_MAX_GROUP];
 		memset(&sum, 0, sizeof(sum));
+		group_each(c, [&](int i, swgldev_ctx* m) { swgldev_get_stats(m, &each[i]); return 0; });
 		for (int i = 0; i < c->n_group; i++)
 		{
-			Solo s(c->group[i]);
-			swgldev_stats one;
-			swgldev_get_stats(c->group[i], &one);
+			const swgldev_stats& one = each[i];
 			sum.draws = one.draws; sum.triangles_in = one.triangles_in;
 			sum.prims_out += one.prims_out; sum.tested += one.tested; sum.shaded += one.shaded; sum.tile_pairs += one.tile_pairs; sum.bands += one.bands;
 		}
-		cudaSetDevice(c->device);
 		*out = sum;
 		return;
 	}
@@ -2396,8 +2517,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 {
 	if (IS_GROUP(c))
 	{
-		for (int i = 0; i < c->n_group; i++) { Solo s(c->group[i]); swgldev_set_option(c->group[i], name, value); }
-		cudaSetDevice(c->device);
+		group_each(c, [&](int, swgldev_ctx* m) { swgldev_set_option(m, name, value); return 0; });
 		return;
 	}
 	swgldev_sync(c);
