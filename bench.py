@@ -251,6 +251,128 @@ def dist_setup(n_gpus: int):
     return dist, rank, world, local
 
 
+def e2e_record(n_tris, e2e_s, verts_bytes, idx_bytes, scene):
+    return {"value": n_tris / e2e_s, "unit": METRIC, "ms_per_step": e2e_s * 1e3,
+            "h2d_bytes_per_step": int(verts_bytes + idx_bytes),
+            "host_buffers": "page-locked, write-combined (swglHostAlloc)",
+            "d2h_bytes_per_step": scene.width * scene.height * 4}
+
+
+def group_e2e(api, sw, G, scene, args, world, local):
+    """Rank 0, N > 1: the end-to-end step through the library's device group (swglSetDeviceCount)."""
+    from swgl_b200 import multigpu
+
+    api.swglSetDevice(0)
+    api.swglSetDeviceCount(world)
+    api.glInit(scene.width, scene.height)
+    err = api.swglGetLastError().decode()
+    if err or api.swglGetOption(b"device_count") != world:
+        raise RuntimeError(f"device group of {world} could not be created: {err}")
+    st = G.setup_scene(api, scene, indexed=True, init=False)
+    verts = multigpu.HostArray(api, scene.vertices)
+    idx = multigpu.HostArray(api, scene.indices)
+
+    def step():
+        api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
+        api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
+        api.glClear(G.GL_COLOR_BUFFER_BIT | G.GL_DEPTH_BUFFER_BIT)
+        api.glDrawElements(G.GL_TRIANGLES, st["n_draw"], G.GL_UNSIGNED_INT, None)
+        api.glGetFramePtr()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    api.swglFinish()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    out = e2e_record(scene.n_triangles, e2e_s, verts.nbytes, idx.nbytes, scene)
+    out["driver"] = (f"rank 0 drives all {world} GPUs from one host thread: swglSetDeviceCount({world}) + the reference's calls; "
+                     "uploads cross PCIe once (1/N per device) and are completed over NVLink, every device writes its bands "
+                     "of the frame into one pinned host mirror")
+    stats = sw.swglStats()
+    api.swglGetStats(C.byref(stats))
+    out["parity"] = parity_block(api, scene, args.config, stats.as_dict())
+    out["kernel_launches_per_step"] = None
+    verts.free()
+    idx.free()
+    err = api.swglGetLastError().decode()
+    if err:
+        out["error"] = err
+    return out
+
+
+def ranks_e2e(api, G, multigpu, dist, torch, scene, args, rank, world, local, frame, barrier, assembled_equals_single, peer):
+    """The end-to-end step with one process per GPU (N = 1, or --e2e-mode ranks): at N > 1 every rank uploads 1/N
+    of the arrays over its own PCIe link, an NCCL all-gather over NVLink on the library's stream replicates them,
+    and every rank writes its bands of the frame into one shared host segment."""
+    n_tris = scene.n_triangles
+    shared = None
+    if world > 1:
+        if peer is not None:
+            peer.close()
+        try:
+            shared = multigpu.SharedFrameMirror(api, dist, rank, world, scene.width, scene.height)
+        except (RuntimeError, OSError):
+            shared = None
+            peer = multigpu.PeerColorTarget(api, dist, rank, world)
+    verts = multigpu.HostArray(api, scene.vertices)
+    idx = multigpu.HostArray(api, scene.indices)
+    sharded = None
+    if world > 1 and multigpu.ShardedUpload.divisible(verts.nbytes, world) and multigpu.ShardedUpload.divisible(idx.nbytes, world):
+        sharded = multigpu.ShardedUpload(api, dist, rank, world, torch.device("cuda", local))
+
+    def e2e_step():
+        nonlocal sharded
+        if sharded is not None:
+            try:
+                sharded.upload(G.GL_ARRAY_BUFFER, verts)
+                sharded.upload(G.GL_ELEMENT_ARRAY_BUFFER, idx)
+            except Exception as exc:      # the same call fails the same way on every rank: all fall back together
+                print(f"bench: sharded upload unavailable ({exc!r}); every rank uploads the whole arrays", file=sys.stderr)
+                sharded = None
+        if sharded is None:
+            api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
+            api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
+        frame()
+        if dist is not None:
+            api.swglFinish()
+            dist.barrier()
+        if rank == 0:
+            api.glGetFramePtr()   # N = 1: wait for the written-through mirror; N > 1: the shared segment (or sync + D2H)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = e2e_record(n_tris, e2e_s, verts.nbytes * (1 if sharded is not None or world == 1 else world),
+                     idx.nbytes * (1 if sharded is not None or world == 1 else world), scene)
+    if world > 1:
+        e2e["driver"] = "one process per GPU (torch.distributed)"
+        e2e["upload"] = ("1/N of the arrays per rank over its own PCIe link + NCCL all-gather over NVLink" if sharded is not None
+                         else "every rank uploads the whole arrays")
+        if sharded is not None:
+            e2e["nvlink_bytes_per_step_per_rank"] = int(verts.nbytes + idx.nbytes) * (world - 1) // world
+        e2e["assembly"] = ("shared host frame mirror: every rank writes its bands over its own PCIe link" if shared is not None
+                           else "peer stores into rank 0's HBM, then one D2H copy on rank 0")
+        if shared is not None:
+            e2e["host_mirror_check"] = assembled_equals_single()
+            shared.close()
+    verts.free()
+    idx.free()
+    if peer is not None:
+        peer.close()
+    return e2e
+
+
 # ---------------------------------------------------------------------------------------------
 def run_own(args):
     import torch
@@ -381,75 +503,36 @@ def run_own(args):
 
     mg_check = assembled_equals_single() if world > 1 else None
 
-    # For the end-to-end step the frame is wanted in HOST memory: the ranks switch from the NVLink target
-    # (rank 0's HBM) to one shared host segment that every rank writes its bands into over its own PCIe link.
-    shared = None
-    if world > 1:
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    # N > 1 (default --e2e-mode group): what a C application does -- ONE host thread, swglSetDeviceCount(N) before
+    # glInit, then the reference's own calls.  Rank 0 drives all N GPUs of the box through the library's device
+    # group (uploads split over the N PCIe links and completed over NVLink, frame assembled in one pinned mirror);
+    # the other ranks wait on the rendezvous store without touching their GPUs.
+    e2e = None
+    if world > 1 and args.e2e_mode == "group":
         peer.close()
         peer = None
-        try:
-            shared = multigpu.SharedFrameMirror(api, dist, rank, world, scene.width, scene.height)
-        except (RuntimeError, OSError):
-            shared = None
-            peer = multigpu.PeerColorTarget(api, dist, rank, world)
-
-    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
-    # the application's vertex / index arrays in page-locked, write-combined host memory (swglHostAlloc):
-    # written once by the CPU, read by the copy engine every step without snooping the CPU caches
-    verts = multigpu.HostArray(api, scene.vertices)
-    idx = multigpu.HostArray(api, scene.indices)
-    # N > 1: every rank uploads 1/N of the arrays over its own PCIe link, an NCCL all-gather over NVLink on the
-    # library's stream replicates them (falls back to N full uploads when the sizes do not divide)
-    sharded = None
-    if world > 1 and multigpu.ShardedUpload.divisible(verts.nbytes, world) and multigpu.ShardedUpload.divisible(idx.nbytes, world):
-        sharded = multigpu.ShardedUpload(api, dist, rank, world, torch.device("cuda", local))
-
-    def e2e_step():
-        nonlocal sharded
-        if sharded is not None:
-            try:
-                sharded.upload(G.GL_ARRAY_BUFFER, verts)
-                sharded.upload(G.GL_ELEMENT_ARRAY_BUFFER, idx)
-            except Exception as exc:      # the same call fails the same way on every rank: all fall back together
-                print(f"bench: sharded upload unavailable ({exc!r}); every rank uploads the whole arrays", file=sys.stderr)
-                sharded = None
-        if sharded is None:
-            api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, C.c_void_p(verts.ptr))
-            api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, C.c_void_p(idx.ptr))
-        frame()
-        if dist is not None:
-            api.swglFinish()
-            dist.barrier()
+        barrier()
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
-            api.glGetFramePtr()   # N = 1: wait for the written-through mirror; N > 1: the shared segment (or sync + D2H)
-
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": n_tris / e2e_s, "unit": METRIC, "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes) * (1 if sharded is not None else world),
-           "host_buffers": "page-locked, write-combined (swglHostAlloc)",
-           "d2h_bytes_per_step": scene.width * scene.height * 4}
-    if world > 1:
-        e2e["upload"] = ("1/N of the arrays per rank over its own PCIe link + NCCL all-gather over NVLink" if sharded is not None
-                         else "every rank uploads the whole arrays")
-        if sharded is not None:
-            e2e["nvlink_bytes_per_step_per_rank"] = int(verts.nbytes + idx.nbytes) * (world - 1) // world
-        e2e["assembly"] = ("shared host frame mirror: every rank writes its bands over its own PCIe link" if shared is not None
-                           else "peer stores into rank 0's HBM, then one D2H copy on rank 0")
-        if shared is not None:
-            e2e["host_mirror_check"] = assembled_equals_single()
-            shared.close()
-            shared = None
+            try:
+                e2e = group_e2e(api, sw, G, scene, args, world, local)
+            except Exception as exc:          # report, do not hang the other ranks
+                e2e = {"error": repr(exc)}
+            store.set("swgl_b200_e2e_done", "1")
+        else:
+            store.wait(["swgl_b200_e2e_done"])
+        barrier()
+        if rank == 0:
+            api.swglSetDeviceCount(1)         # nothing below renders at N > 1
+            api.swglSetDevice(local)
+    if e2e is None:
+        e2e = ranks_e2e(api, G, multigpu, dist, torch, scene, args, rank, world, local, frame, barrier, assembled_equals_single, peer)
+        peer = None
+    verts = idx = None
+    if world == 1:
+        verts = multigpu.HostArray(api, scene.vertices)
+        idx = multigpu.HostArray(api, scene.indices)
 
     # ---- the same step pipelined: two geometry sets and two frame mirrors; step N's
     # upload overlaps frame N-1 on the device, its frame is collected during step N+1 ----
@@ -505,8 +588,9 @@ def run_own(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(scene, target_seconds=12.0)
 
-    verts.free()
-    idx.free()
+    if verts is not None:
+        verts.free()
+        idx.free()
     if peer is not None:
         peer.close()
     err = api.swglGetLastError().decode()
@@ -671,6 +755,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", type=int, default=4, help="BASELINE.json config 1..5 (default 4: 4K, 1M triangles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-mode", default="group", choices=["group", "ranks"],
+                    help="N > 1 end-to-end step: rank 0 drives all GPUs through swglSetDeviceCount (group), or one process per GPU (ranks)")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1, C2, C3, C5) of the N=1 line")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,6 +8,7 @@
  *     ./c4_multi_gpu <devices> [grid width height frames]
  *
  * prints:  <devices> <colour FNV-1a64> <covered pixels> <ms per end-to-end frame>
+ *          and on stderr where the host thread spent that time (vertex upload, index upload, clear + draw, glGetFramePtr)
  *
  * The scene is swgl_b200/scenes.py's grid_mesh() restated in C (32-bit LCG s = s*1664525 + 1013904223,
  * rnd = (s >> 8) / 2^24, seed 12345; per vertex: w, jx, jy, z, r, g, b), so the colour hash of the default
@@ -108,17 +109,25 @@ int main(int argc, char** argv)
 	glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
 
 	const uint32_t* frame = NULL;
-	double t0 = 0.0;
+	double t0 = 0.0, phase[4] = { 0.0, 0.0, 0.0, 0.0 };
 	for (int f = 0; f < frames + 3; f++)
 	{
-		if (f == 3) t0 = now_ms();               /* three warm-up frames */
+		if (f == 3) { t0 = now_ms(); phase[0] = phase[1] = phase[2] = phase[3] = 0.0; }   /* three warm-up frames */
+		const double a = now_ms();
 		swglBufferRespecify(GL_ARRAY_BUFFER, (GLsizei)vbytes, verts);
+		const double b = now_ms();
 		swglBufferRespecify(GL_ELEMENT_ARRAY_BUFFER, (GLsizei)ibytes, idx);
+		const double c = now_ms();
 		glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
 		glDrawElements(GL_TRIANGLES, (GLsizei)ni, GL_UNSIGNED_INT, (const void*)0);
+		const double d = now_ms();
 		frame = glGetFramePtr();
+		const double e = now_ms();
+		phase[0] += b - a; phase[1] += c - b; phase[2] += d - c; phase[3] += e - d;
 	}
 	const double ms = (now_ms() - t0) / (double)(frames > 0 ? frames : 1);
+	fprintf(stderr, "devices %d: vertex upload %.3f ms, index upload %.3f ms, clear + draw calls %.3f ms, glGetFramePtr %.3f ms\n", devices,
+	        phase[0] / (frames > 0 ? frames : 1), phase[1] / (frames > 0 ? frames : 1), phase[2] / (frames > 0 ? frames : 1), phase[3] / (frames > 0 ? frames : 1));
 	const char* err = swglGetLastError();
 	if (err[0]) { fprintf(stderr, "error: %s\n", err); return 3; }
 

@@ -209,7 +209,13 @@ struct swgldev_ctx
 	std::map<uintptr_t, std::vector<swgldev_ptr>> replicas;
 	int mirror_borrowed;                 /* shared_mirror is the leader's pinned mirror: nothing to unregister */
 	cudaEvent_t slice_ev, gather_ev;     /* group uploads: this member's slice has arrived / its replica is complete */
-	int gather_pending;
+	cudaStream_t gather;                 /* the device-to-device part runs here, so the next upload's host copy does not queue behind it */
+	/* gathers in flight on `gather`, newest last used: (event, the leader's allocation it completes).  An upload
+	 * into an allocation waits for the earlier gathers of the same allocation on every member; an entry that is
+	 * recycled while it may still be pending makes later checks wait for the newest event (same stream: it covers all) */
+	cudaEvent_t gather_ring_ev[4];
+	swgldev_ptr gather_ring_dst[4];
+	int gather_ring_pos, gather_pending, gather_evicted;
 };
 
 #define IS_GROUP(c) ((c)->n_group > 1 && !(c)->solo)
@@ -1230,7 +1236,8 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->n_draws = 0; c->error[0] = 0;
 	for (int i = 0; i < SWGL_MAX_GROUP; i++) c->group[i] = nullptr;
-	c->n_group = 1; c->solo = 0; c->pool = nullptr; c->group_peer_ok = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0;
+	c->n_group = 1; c->solo = 0; c->pool = nullptr; c->group_peer_ok = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0; c->gather = nullptr; c->gather_ring_pos = 0; c->gather_evicted = 0;
+	for (int i = 0; i < 4; i++) { c->gather_ring_ev[i] = nullptr; c->gather_ring_dst[i] = 0; }
 
 	const size_t npx = (size_t)width * height;
 	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
@@ -1259,6 +1266,11 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaEventCreateWithFlags(&c->ctr_event, cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->slice_ev, cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->gather_ev, cudaEventDisableTiming) == cudaSuccess
+	       && cudaStreamCreateWithPriority(&c->gather, cudaStreamNonBlocking, prio_hi) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->gather_ring_ev[0], cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->gather_ring_ev[1], cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->gather_ring_ev[2], cudaEventDisableTiming) == cudaSuccess
+	       && cudaEventCreateWithFlags(&c->gather_ring_ev[3], cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[0]) == cudaSuccess && cudaEventCreate(&c->stage_ev[1]) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[2]) == cudaSuccess && cudaEventCreate(&c->stage_ev[3]) == cudaSuccess
 	       && cudaEventCreate(&c->stage_ev[4]) == cudaSuccess && cudaEventCreate(&c->stage_ev[5]) == cudaSuccess
@@ -1398,6 +1410,8 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->ctr_event) cudaEventDestroy(c->ctr_event);
 	if (c->slice_ev) cudaEventDestroy(c->slice_ev);
 	if (c->gather_ev) cudaEventDestroy(c->gather_ev);
+	if (c->gather) { cudaStreamSynchronize(c->gather); cudaStreamDestroy(c->gather); }
+	for (int i = 0; i < 4; i++) if (c->gather_ring_ev[i]) cudaEventDestroy(c->gather_ring_ev[i]);
 	for (int i = 0; i < 8; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	cudaGetLastError();
@@ -1468,6 +1482,7 @@ void swgldev_free(swgldev_ctx* c, swgldev_ptr p)
 		if (it == c->replicas.end()) return;
 		const std::vector<swgldev_ptr> reps = it->second;
 		c->replicas.erase(it);
+		swgldev_sync(c);      /* every member: a gather on another member may still be reading this member's replica */
 		group_each(c, [&](int i, swgldev_ctx* m) { swgldev_free(m, reps[(size_t)i]); return 0; });
 		return;
 	}
@@ -1519,7 +1534,14 @@ static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const 
 			const uint64_t sr = (m->draw_serial - it->second < 8u) ? it->second : m->draw_serial;
 			if (cudaStreamWaitEvent(m->upload, m->draw_ev[sr & 7u], 0) != cudaSuccess) r = -1;
 		}
-		for (int j = 0; j < n; j++) if (j != i && c->group[j]->gather_pending) cudaStreamWaitEvent(m->upload, c->group[j]->gather_ev, 0);
+		/* the previous upload INTO THIS BUFFER may still be pulled from (or into) the replicas */
+		for (int j = 0; j < n; j++)
+		{
+			const swgldev_ctx* o = c->group[j];
+			if (!o->gather_pending) continue;
+			if (o->gather_evicted) { cudaStreamWaitEvent(m->upload, o->gather_ev, 0); continue; }
+			for (int q = 0; q < 4; q++) if (o->gather_ring_dst[q] == dst) cudaStreamWaitEvent(m->upload, o->gather_ring_ev[q], 0);
+		}
 		const uint64_t lo = (uint64_t)i * slice, hi = lo + slice < bytes ? lo + slice : bytes;
 		if (lo < hi)
 		{
@@ -1542,16 +1564,16 @@ static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const 
 	{
 		int r = 0;
 		char* rep = (char*)(uintptr_t)member_ptr(c, i, dst);
-		for (int k = 1; k < n; k++)
+		for (int k = 0; k < n; k++)
 		{
-			const int j = (i + k) % n;
-			if ((uint64_t)j * slice < bytes && cudaStreamWaitEvent(m->upload, c->group[j]->slice_ev, 0) != cudaSuccess) r = -1;
+			const int j = (i + k) % n;                 /* k = 0: the member's own slice and whatever the upload stream held before it */
+			if (((uint64_t)j * slice < bytes || k == 0) && cudaStreamWaitEvent(m->gather, c->group[j]->slice_ev, 0) != cudaSuccess) r = -1;
 		}
 		if (by_kernel)
 		{
 			GatherArgs a = ga;
 			a.dst = rep + offset; a.self = i;
-			k_group_gather<<<148 * 2, 256, 0, m->upload>>>(a);
+			k_group_gather<<<148 * 2, 256, 0, m->gather>>>(a);
 			m->n_launches++;
 		}
 		else
@@ -1560,9 +1582,20 @@ static int group_upload(swgldev_ctx* c, swgldev_ptr dst, uint64_t offset, const 
 				const int j = (i + k) % n;                 /* staggered: at any time every member is pulled from once */
 				const uint64_t lo = (uint64_t)j * slice, hi = lo + slice < bytes ? lo + slice : bytes;
 				if (lo >= hi) continue;
-				if (cudaMemcpyPeerAsync(rep + offset + lo, m->device, ga.src[j] + lo, c->group[j]->device, hi - lo, m->upload) != cudaSuccess) r = -1;
+				if (cudaMemcpyPeerAsync(rep + offset + lo, m->device, ga.src[j] + lo, c->group[j]->device, hi - lo, m->gather) != cudaSuccess) r = -1;
 			}
-		if (cudaEventRecord(m->gather_ev, m->upload) != cudaSuccess) r = -1;
+		if (cudaEventRecord(m->gather_ev, m->gather) != cudaSuccess) r = -1;       /* the newest gather of this member */
+		{
+			int q = -1;
+			for (int t = 0; t < 4; t++) if (m->gather_ring_dst[t] == dst) q = t;   /* the same allocation again: its entry moves forward */
+			if (q < 0)
+			{
+				q = m->gather_ring_pos; m->gather_ring_pos = (q + 1) & 3;
+				if (m->gather_pending && m->gather_ring_dst[q]) m->gather_evicted = 1;
+			}
+			m->gather_ring_dst[q] = dst;
+			if (cudaEventRecord(m->gather_ring_ev[q], m->gather) != cudaSuccess) r = -1;
+		}
 		m->gather_pending = 1;
 		if (cudaStreamWaitEvent(m->stream, m->gather_ev, 0) != cudaSuccess) r = -1;      /* the member's draws read the whole replica */
 		if (cudaEventSynchronize(m->slice_ev) != cudaSuccess) r = -1;                      /* the host memory has been read */
@@ -1813,7 +1846,11 @@ int swgldev_sync(swgldev_ctx* c)
 	if (settle_last_draw(c)) return -1;
 	if (flush_clear(c)) return -1;
 	CK(cudaStreamSynchronize(c->stream));
-	c->gather_pending = 0;               /* the stream waited for the member's last group upload */
+	if (c->gather_pending)
+	{   /* the stream waited for the member's last group upload: no gather is in flight any more */
+		c->gather_pending = 0; c->gather_evicted = 0;
+		for (int i = 0; i < 4; i++) c->gather_ring_dst[i] = 0;
+	}
 	if (c->copy_inflight) CK(cudaStreamSynchronize(c->copy));
 	if (c->shared_mirror && !c->mirror_synced)
 	{
