@@ -23,6 +23,12 @@
 #ifndef SWGL_RASTER_WARP_CUH
 #define SWGL_RASTER_WARP_CUH
 
+#ifndef WT_FIRST_TURN_FAST
+#define WT_FIRST_TURN_FAST 1
+#endif
+#ifndef WT_MAGIC_I2F
+#define WT_MAGIC_I2F 1
+#endif
 #define WT_H        8        /* tile rows */
 #define WT_H_SHIFT  3
 #define WT_PIX      (SWGL_TILE * WT_H)
@@ -476,7 +482,14 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				if (active)
 				{
 					float u, v, w;
+#if WT_MAGIC_I2F
+					/* pixel coordinates are below 2^23 here (tiles_x <= 2047, |y| < 2^22 is checked by the host): the
+					 * int -> float conversion is an OR into the mantissa of 2^23 and one exact subtraction */
+					const float px = __int_as_float(0x4b000000 | (tile_x0 + (int)lx)) - 8388608.0f;
+					const float py = (float)(band_last_y - (int)r);
+#else
 					const float px = (float)(tile_x0 + (int)lx), py = (float)(band_last_y - (int)r);
+#endif
 					if (!(frag_weights_fast(pc, px, py, u, v, w, z) && ((e >> 26) & 1u)))
 					{
 						const float4 s4 = weights_slow_entry(P, __float_as_uint(pc[5].w), px, py);
@@ -537,7 +550,25 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				/* ---- ordered commit ---- */
 				const uint32_t my_turn = (uint32_t)__popc(peers & ((1u << lane) - 1u));
 				const uint32_t turns = __reduce_max_sync(0xffffffffu, my_turn);
+#if WT_FIRST_TURN_FAST
+				/* the first fragment of each pixel group sees the depth it was tested against above (nothing has
+				 * written the pixel since): its test is decided, no reload, no late shading */
+				if (pending && my_turn == 0u)
+				{
+					if (shaded_early)
+					{
+						T.depth[pix] = z;
+						n_shaded++;
+						T.color[pix] = blend_pack_lut(col.x, col.y, col.z, col.w, T.color[pix], S.lut);
+						dirty = true;
+					}
+					pending = false;
+				}
+				__syncwarp();
+				for (uint32_t turn = 1; turn <= turns; turn++)
+#else
 				for (uint32_t turn = 0; turn <= turns; turn++)
+#endif
 				{
 					if (pending && my_turn == turn)
 					{

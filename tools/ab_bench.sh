@@ -3,5 +3,5 @@
 for rnd in 1 2; do
 for lib in "$@"; do
   if [ "$lib" = cur ]; then unset SWGL_B200_LIB; else export SWGL_B200_LIB=$PWD/$lib; fi
-  timeout 120 python bench.py --no-cpu-baseline --steps 20 --warmup 3 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$lib', round(d['ms_per_step']*1e3,1), {k: round(v,1) for k,v in d['roofline']['stage_us'].items()}, 'e2e', round(d['e2e']['ms_per_step'],3))"
+  timeout 120 python bench.py --no-cpu-baseline --no-configs --steps 20 --warmup 3 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$lib', round(d['ms_per_step']*1e3,1), {k: round(v,1) for k,v in d['roofline']['stage_us'].items()}, 'e2e', round(d['e2e']['ms_per_step'],3))"
 done; done
