@@ -27,7 +27,7 @@
 #define WT_FIRST_TURN_FAST 1
 #endif
 #ifndef WT_MAGIC_I2F
-#define WT_MAGIC_I2F 1
+#define WT_MAGIC_I2F 0   /* measured: no gain (tools/ab_bench.sh, r02) */
 #endif
 #define WT_H        8        /* tile rows */
 #define WT_H_SHIFT  3
