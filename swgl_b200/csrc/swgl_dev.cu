@@ -639,19 +639,15 @@ __device__ __noinline__ uint32_t setup_clipped(const DrawParams& P, uint32_t t, 
 	return 0u;
 }
 
-__global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ DrawParams P)
+/* One group of 32 x warps triangles: triangle t of this thread with its vertices already loaded. */
+__device__ __forceinline__ void setup_group(const DrawParams& P, float4 (*stage)[32][4], uint32_t t, uint32_t lane, uint32_t wid,
+                                            float4 p0, float4 p1, float4 p2, uint32_t s0, uint32_t s1, uint32_t s2)
 {
-	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	uint32_t live = 0, tr_top = 0, pk[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu };
 	uint32_t rec_band = 0xffffffffu;
 	bool rec_pending = false;
-	float4 p0, p1, p2;
-	uint32_t s0 = 0, s1 = 0, s2 = 0;
 	if (t < P.ntri)
 	{
-		tri_vertices<true>(P, t, p0, p1, p2, s0, s1, s2);
 		if (P.diag & 4u) { if (p0.x + p1.x + p2.x == 12345.678f) P.ctr->prims_out = 1; return; }
 		if (P.diag & 16u) { if (s0 + s1 + s2 == 0x12345678u) P.ctr->prims_out = 1; return; }
 		/* ClipTriangleAgainstNearPlane (swgl.c:532-561): inside iff z >= -w */
@@ -749,6 +745,78 @@ __global__ void __launch_bounds__(128, 8) k_setup_bin(const __grid_constant__ Dr
 	/* primitives that reached the rasteriser: one atomic per warp */
 	for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
 	if (lane == 0 && live) atomicAdd(&P.ctr->prims_out, live);
+}
+
+/* the element indices of triangle t (stream positions 3t .. 3t+2 for glDrawArrays) */
+__device__ __forceinline__ void tri_indices(const DrawParams& P, uint32_t t, uint32_t& s0, uint32_t& s1, uint32_t& s2)
+{
+	s0 = 3u * t; s1 = s0 + 1u; s2 = s0 + 2u;
+	if (P.ibo && t < P.ntri)
+	{
+		const unsigned long long at = (unsigned long long)(long long)P.first + s0;
+		s0 = (at < P.ibo_count) ? __ldg(P.ibo + at) : 0xffffffffu;
+		s1 = (at + 1 < P.ibo_count) ? __ldg(P.ibo + at + 1) : 0xffffffffu;
+		s2 = (at + 2 < P.ibo_count) ? __ldg(P.ibo + at + 2) : 0xffffffffu;
+	}
+}
+
+__device__ __forceinline__ void tri_clip(const DrawParams& P, uint32_t t, uint32_t s0, uint32_t s1, uint32_t s2, float4& p0, float4& p1, float4& p2)
+{
+	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	p0 = p1 = p2 = zero;
+	if (t >= P.ntri) return;
+	p0 = (s0 < P.n_shade) ? P.clip[s0] : to_screen(zero, P);
+	p1 = (s1 < P.n_shade) ? P.clip[s1] : to_screen(zero, P);
+	p2 = (s2 < P.n_shade) ? P.clip[s2] : to_screen(zero, P);
+}
+
+/* The set-up kernel is a chain of three dependent global round trips per triangle (indices -> gathered
+ * vertices -> list cursors) and was latency-bound at 45 % issue with one triangle per thread.  It is now a
+ * resident grid whose threads walk the triangle stream in groups of (grid x 128) with a two-deep software
+ * pipeline: while group g is set up and binned, the vertices of group g+1 and the indices of group g+2 are in
+ * flight.  Launched with programmatic stream serialisation behind k_vertex: the first indices are requested
+ * before the wait, clip[] is only read after it. */
+#ifndef SETUP_PIPELINED
+#define SETUP_PIPELINED 1
+#endif
+#ifndef SETUP_CTAS_PER_SM
+#define SETUP_CTAS_PER_SM 5
+#endif
+__global__ void __launch_bounds__(128, SETUP_PIPELINED ? SETUP_CTAS_PER_SM : 8) k_setup_bin(const __grid_constant__ DrawParams P)
+{
+	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
+	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#if SETUP_PIPELINED
+	const uint32_t stride = gridDim.x * blockDim.x;
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	/* whole warps leave together: every shuffle / vote below is warp-wide */
+	const uint32_t t_end = (P.ntri + 31u) & ~31u;
+	uint32_t a0, a1, a2, b0, b1, b2;        /* indices of the group being processed next / the one after */
+	float4 p0, p1, p2;
+	tri_indices(P, t, a0, a1, a2);
+	tri_indices(P, t + stride, b0, b1, b2);
+	pdl_wait();                              /* everything below reads the vertex kernel's output */
+	tri_clip(P, t, a0, a1, a2, p0, p1, p2);
+	for (; (t & ~31u) < t_end; t += stride)
+	{
+		/* requests for the next two groups go out before this group's dependent work */
+		float4 q0, q1, q2;
+		tri_clip(P, t + stride, b0, b1, b2, q0, q1, q2);
+		uint32_t c0, c1, c2;
+		tri_indices(P, t + 2u * stride, c0, c1, c2);
+		setup_group(P, stage, t, lane, wid, p0, p1, p2, a0, a1, a2);
+		__syncwarp();                        /* the stage rows of this warp are reused by the next group */
+		p0 = q0; p1 = q1; p2 = q2;
+		a0 = b0; a1 = b1; a2 = b2;
+		b0 = c0; b1 = c1; b2 = c2;
+	}
+#else
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	float4 p0, p1, p2;
+	uint32_t s0 = 0, s1 = 0, s2 = 0;
+	if (t < P.ntri) tri_vertices<true>(P, t, p0, p1, p2, s0, s1, s2);
+	setup_group(P, stage, t, lane, wid, p0, p1, p2, s0, s1, s2);
+#endif
 }
 
 /* The tile's list length; the cursor is re-armed (zeroed) for the next draw.  Whole CTA calls it. */
@@ -2040,7 +2108,11 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		 * wave runs and wait (cudaGridDependencySynchronize) only before they read its output */
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
-		cfg.gridDim = dim3((P.ntri + 127u) / 128u); cfg.blockDim = dim3(128); cfg.stream = c->stream;
+		uint32_t groups = (P.ntri + 127u) / 128u;
+#if SETUP_PIPELINED
+		if (groups > 148u * SETUP_CTAS_PER_SM) groups = 148u * SETUP_CTAS_PER_SM;     /* one resident wave, the threads stride over the stream */
+#endif
+		cfg.gridDim = dim3(groups ? groups : 1u); cfg.blockDim = dim3(128); cfg.stream = c->stream;
 		cudaLaunchAttribute at[1];
 		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		at[0].val.programmaticStreamSerializationAllowed = timing ? 0 : 1;
