@@ -182,6 +182,8 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_tile_rows;                   /* warp rasteriser: 8, 4 or 2 rows per tile; 0 = chosen per draw (th_shift_of) */
+	uint32_t cur_th_shift;               /* of the draw being issued (list capacity is per tile of that size) */
 	int opt_jit;                         /* compile generic shaders to kernels at run time (default 1; 0: on-device interpreter) */
 	int jit_failed;                      /* a compilation failed: reported once, the interpreter draws */
 	int last_vs_kind, last_fs_kind;      /* of the last triangle draw, as launched */
@@ -777,7 +779,7 @@ __device__ __forceinline__ void tri_clip(const DrawParams& P, uint32_t t, uint32
  * flight.  Launched with programmatic stream serialisation behind k_vertex: the first indices are requested
  * before the wait, clip[] is only read after it. */
 #ifndef SETUP_PIPELINED
-#define SETUP_PIPELINED 1
+#define SETUP_PIPELINED 0   /* measured (r02, C4): 36.7 us against 33.6 us for one triangle per thread -- the kernel is not bound by the load chain alone */
 #endif
 #ifndef SETUP_CTAS_PER_SM
 #define SETUP_CTAS_PER_SM 5
@@ -1257,17 +1259,40 @@ static bool small_triangle_draw(const swgldev_ctx* c, uint32_t ntri)
 {
 	return (double)c->W * (double)c->H / (double)(ntri ? ntri : 1u) <= 64.0;
 }
-static uint32_t th_shift_of(int path) { return path == 3 ? WT_H_SHIFT : SWGL_TILE_SHIFT; }
+/* Tile height of a draw.  The CTA kernels use 32 rows.  The warp kernel uses 8 when the tiles this context owns
+ * fill at least one resident wave of warps (148 SMs x 32), else 4, else 2 (a tile is one warp's serial work: with
+ * few tiles the slowest warp sets the kernel's time); the "tile_rows" option pins it.  Tile rows must stay below
+ * 1024 (band-entry packing). */
+static uint32_t th_shift_of(const swgldev_ctx* c, int path)
+{
+	if (path != 3) return SWGL_TILE_SHIFT;
+	if (c->opt_tile_rows == 8 || c->opt_tile_rows == 4 || c->opt_tile_rows == 2)
+	{
+		const uint32_t sh = c->opt_tile_rows == 8 ? 3u : c->opt_tile_rows == 4 ? 2u : 1u;
+		if (((c->H + (1u << sh) - 1u) >> sh) <= 1023u) return sh;
+	}
+	const uint32_t ranks = c->n_ranks ? c->n_ranks : 1u;
+	for (uint32_t sh = WT_H_SHIFT; sh > WT_H_SHIFT_MIN; sh--)
+	{
+		const size_t tiles = (size_t)c->tiles_x * ((c->H + (1u << sh) - 1u) >> sh) / ranks;
+		const bool finer_fits = ((c->H + (1u << (sh - 1u)) - 1u) >> (sh - 1u)) <= 1023u;
+		if (tiles >= 148u * 32u || !finer_fits) return sh;
+	}
+	return WT_H_SHIFT_MIN;
+}
 
 template <int FS>
 static void launch_raster(swgldev_ctx* c, const DrawParams& P)
 {
-	const int path = P.th_shift == WT_H_SHIFT ? 3 : (c->opt_raster_path == 1 ? 1 : 2);
+	const int path = P.th_shift < SWGL_TILE_SHIFT ? 3 : (c->opt_raster_path == 1 ? 1 : 2);
 	c->last_raster_path = path;
 	dim3 grid(P.tiles_x, P.tiles_y);
+	const dim3 wgrid((P.tiles_x + WT_WARPS - 1) / WT_WARPS, P.owned_tile_rows ? P.owned_tile_rows : 1);
 	if (path == 1) k_raster<FS><<<grid, SWGL_RASTER_THREADS, sizeof(RasterShared), c->stream>>>(P);
 	else if (path == 2) k_raster_frag<FS><<<grid, FRAG_THREADS, sizeof(FragShared), c->stream>>>(P);
-	else k_raster_warp<FS><<<dim3((P.tiles_x + WT_WARPS - 1) / WT_WARPS, P.owned_tile_rows ? P.owned_tile_rows : 1), WT_WARPS * 32, 0, c->stream>>>(P);
+	else if (P.th_shift == 3) k_raster_warp<FS, 3><<<wgrid, WT_WARPS * 32, 0, c->stream>>>(P);
+	else if (P.th_shift == 2) k_raster_warp<FS, 2><<<wgrid, WT_WARPS * 32, 0, c->stream>>>(P);
+	else k_raster_warp<FS, 1><<<wgrid, WT_WARPS * 32, 0, c->stream>>>(P);
 }
 
 extern "C" {
@@ -1294,7 +1319,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -1308,7 +1333,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	for (int i = 0; i < 4; i++) { c->gather_ring_ev[i] = nullptr; c->gather_ring_dst[i] = 0; }
 
 	const size_t npx = (size_t)width * height;
-	const size_t ntiles = (size_t)c->tiles_x * ((height + WT_H - 1) / WT_H);   /* finest tiling */
+	const size_t ntiles = (size_t)c->tiles_x * ((height + (1u << WT_H_SHIFT_MIN) - 1) >> WT_H_SHIFT_MIN);   /* finest tiling */
 	/* the upload stream's small reduction kernel must not queue behind a whole raster grid */
 	int prio_lo = 0, prio_hi = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -1856,7 +1881,7 @@ static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 		if (grow(c, &c->bands, &c->cap_bands, (size_t)h.band_cursor + (size_t)h.band_cursor / 4 + 1024)) return -1;
 	if (h.overflow & 1u)
 	{
-		const size_t ntiles = (size_t)c->tiles_x * ((c->H + WT_H - 1) / WT_H);   /* finest tiling */
+		const size_t ntiles = (size_t)c->tiles_x * ((c->H + (1u << P.th_shift) - 1) >> P.th_shift);   /* tiles of this draw */
 		size_t want = (size_t)h.max_list + (size_t)h.max_list / 4 + 64;
 		if (want < 2 * (size_t)c->bin_cap) want = 2 * (size_t)c->bin_cap;
 		if (want * ntiles * 4 > c->opt_bin_limit)
@@ -2236,7 +2261,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
 	 * several raster rows onto row Height-1, swgl.c:3386). */
 	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
-	    || c->tiles_x > 2047u || (c->H + WT_H - 1) / WT_H > 1023u)
+	    || c->tiles_x > 2047u || (c->H + (1u << WT_H_SHIFT) - 1) / (1u << WT_H_SHIFT) > 1023u)
 	{
 		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
 		return flush_clear(c);
@@ -2252,20 +2277,24 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	DrawParams P;
 	if (fill_common_params(c, d, P)) return flush_clear(c);
 	P.ntri = ntri;
-	P.th_shift = th_shift_of(raster_path_for(c, ntri));
+	const int rpath = raster_path_for(c, ntri);
+	P.th_shift = th_shift_of(c, rpath);
+	/* a fragment shader outside the built-in shapes has its kernel compiled for 8-row tiles only */
+	if (rpath == 3 && P.fs_kind == SWFS_GENERIC && c->opt_jit && !c->jit_failed) P.th_shift = WT_H_SHIFT;
+	c->cur_th_shift = P.th_shift;
 	P.tiles_x = c->tiles_x; P.tiles_y = (c->H + (1u << P.th_shift) - 1u) >> P.th_shift;
 	P.owned_tile_rows = P.tiles_y;
-	if (P.n_ranks > 1 && P.th_shift == WT_H_SHIFT)
+	if (P.n_ranks > 1 && rpath == 3)
 	{
-		const uint32_t per = P.band_rows << (5u - WT_H_SHIFT), cycle = per * P.n_ranks;
+		const uint32_t per = P.band_rows << (5u - P.th_shift), cycle = per * P.n_ranks;
 		/* whole ownership cycles, plus what the last partial cycle leaves to this rank */
 		const uint32_t full = P.tiles_y / cycle, rest = P.tiles_y % cycle;
 		const uint32_t lo = P.rank * per;
 		P.owned_tile_rows = full * per + (rest > lo ? (rest - lo < per ? rest - lo : per) : 0u);
 	}
-	apply_jit(c, d, P, P.th_shift == WT_H_SHIFT);
-	P.lean_prims = (c->opt_lean_prims && P.th_shift == WT_H_SHIFT) ? 1u : 0u;
-	P.inline_tall = (P.th_shift == WT_H_SHIFT && small_triangle_draw(c, ntri)) ? 1u : 0u;
+	apply_jit(c, d, P, rpath == 3 && P.th_shift == WT_H_SHIFT);
+	P.lean_prims = (c->opt_lean_prims && rpath == 3) ? 1u : 0u;
+	P.inline_tall = (rpath == 3 && small_triangle_draw(c, ntri)) ? 1u : 0u;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;
 
@@ -2278,7 +2307,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	if (grow(c, &c->bands, &c->cap_bands, (size_t)1 << 16)) return -1;
 	{
 		/* per-tile lists: K entries each, K grows (never shrinks) when a draw overflows it */
-		const size_t ntiles = (size_t)c->tiles_x * ((c->H + WT_H - 1) / WT_H);   /* finest tiling */
+		const size_t ntiles = (size_t)c->tiles_x * ((c->H + (1u << c->cur_th_shift) - 1) >> c->cur_th_shift);   /* tiles of the current draw */
 		if (c->bin_cap == 0) c->bin_cap = 256;
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
 	}
@@ -2637,6 +2666,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "lean_prims")) c->opt_lean_prims = (int)value;
 	else if (!strcmp(name, "mip_lod")) c->opt_mip_lod = value ? 1 : 0;
 	else if (!strcmp(name, "jit")) c->opt_jit = value ? 1 : 0;
+	else if (!strcmp(name, "tile_rows")) c->opt_tile_rows = (int)value;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
@@ -2687,6 +2717,8 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "host_mirror")) return c->opt_host_mirror;
 	if (!strcmp(name, "mip_lod")) return c->opt_mip_lod;
 	if (!strcmp(name, "jit")) return c->opt_jit;
+	if (!strcmp(name, "tile_rows")) return c->opt_tile_rows;
+	if (!strcmp(name, "last_tile_rows")) return 1 << c->cur_th_shift;
 	if (!strcmp(name, "last_vs_kind")) return c->last_vs_kind;
 	if (!strcmp(name, "last_fs_kind")) return c->last_fs_kind;
 	if (!strcmp(name, "mirror_synced")) return c->mirror_synced;

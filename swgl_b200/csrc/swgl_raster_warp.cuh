@@ -29,37 +29,41 @@
 #ifndef WT_MAGIC_I2F
 #define WT_MAGIC_I2F 0   /* measured: no gain (tools/ab_bench.sh, r02) */
 #endif
-#define WT_H        8        /* tile rows */
-#define WT_H_SHIFT  3
-#define WT_PIX      (SWGL_TILE * WT_H)
+/* Tiles are 32 pixels wide and TH = 8, 4 or 2 rows tall (template parameter THS = log2 TH).  8 rows is the
+ * choice whenever the framebuffer has at least one resident wave of such tiles (148 SMs x 32 warps); smaller
+ * framebuffers -- or the share of one rank of a sort-first group -- get shorter tiles, i.e. more and shorter
+ * warps, because a tile is one warp's serial work and the slowest warp sets the kernel's time. */
+#define WT_H_SHIFT  3        /* the default tile height (and the only one of run-time compiled kernels) */
+#define WT_H_SHIFT_MIN 1
 #define WT_WARPS    4        /* tiles per CTA */
 #define WT_SORT_CAP 256      /* list entries a warp sorts in shared memory */
-#define WT_MAX_SPANS (32 * WT_H)             /* (primitive, row) spans of one batch */
 #define WT_MAX_FRAGS 2048                     /* fragments of one batch: a batch that would produce more is cut short */
 
 /* span entry: (tile pixel of the first fragment - its fragment index) mod 2^13 | primitive lane << 21
  * | primitive passed prim_fast_ok() << 26 */
 #define WT_PC_WORDS (4 * PC_VEC4)             /* per-primitive constants of phase B, see prim_consts() */
+template <int TH>
 struct WarpTile
 {
-	uint32_t color[WT_PIX];
-	float    depth[WT_PIX];
+	uint32_t color[SWGL_TILE * TH];
+	float    depth[SWGL_TILE * TH];
 	union
 	{
 		uint32_t ids[WT_SORT_CAP];               /* scratch of the list sort (before the first batch) */
 		struct
 		{
-			uint32_t span[WT_MAX_SPANS];         /* this batch's non-empty spans in fragment order */
+			uint32_t span[32 * TH];              /* this batch's non-empty (primitive, row) spans in fragment order */
 			uint32_t start_bits[WT_MAX_FRAGS / 32];  /* bit f: fragment f is the first of a span */
 		} b;
 	} u;
 	float4   pc[32 * WT_PC_WORDS / 4];       /* [primitive lane][6]: constants staged by phase A */
 };
 
+template <int TH>
 struct WarpShared
 {
 	float    lut[256];             /* byte / 255.0f (swgl.c:3434-3437) */
-	WarpTile w[WT_WARPS];
+	WarpTile<TH> w[WT_WARPS];
 };
 
 /* ascending sort of one value per lane (padding 0xffffffff sinks to the top lanes) */
@@ -124,41 +128,50 @@ __device__ __noinline__ void warp_sort_mem(uint32_t* ids, uint32_t n, uint32_t l
 	}
 }
 
-/* 8 consecutive pixels of one tile row: load (or take the pending clear value) */
-__device__ __forceinline__ void wt_load8(const DrawParams& P, const ClearParams& cp, int row, int px0,
-                                         uint32_t* c8, float* d8, bool& touched)
+/* N (8, 4 or 2) consecutive pixels of one tile row: load (or take the pending clear value) */
+template <int N>
+__device__ __forceinline__ void wt_load(const DrawParams& P, const ClearParams& cp, int row, int px0,
+                                        uint32_t* c8, float* d8, bool& touched)
 {
-	for (int k = 0; k < 8; k++) { c8[k] = 0u; d8[k] = 0.0f; }
+#pragma unroll
+	for (int k = 0; k < N; k++) { c8[k] = 0u; d8[k] = 0.0f; }
 	if (row >= (int)P.H) return;
 	const size_t pix = (size_t)row * P.W + (size_t)px0;
 	const bool in_row = cp.flags && row >= cp.y0 && row < cp.y1;
-	const bool all_in = in_row && px0 >= cp.x0 && px0 + 8 <= cp.x1;
-	const bool none_in = !in_row || px0 + 8 <= cp.x0 || px0 >= cp.x1;
+	const bool all_in = in_row && px0 >= cp.x0 && px0 + N <= cp.x1;
+	const bool none_in = !in_row || px0 + N <= cp.x0 || px0 >= cp.x1;
 	const bool need_c = !(all_in && (cp.flags & 1u)), need_d = !(all_in && (cp.flags & 2u));
-	if (px0 + 7 < (int)P.W && ((pix & 3u) == 0))
+	if (N >= 4 && px0 + N - 1 < (int)P.W && ((pix & 3u) == 0))
 	{
-		if (need_c)
+#pragma unroll
+		for (int q = 0; q < N / 4; q++)
 		{
-			const uint4 a = *(const uint4*)(P.color + pix), b = *(const uint4*)(P.color + pix + 4);
-			c8[0] = a.x; c8[1] = a.y; c8[2] = a.z; c8[3] = a.w; c8[4] = b.x; c8[5] = b.y; c8[6] = b.z; c8[7] = b.w;
-		}
-		if (need_d)
-		{
-			const float4 a = *(const float4*)(P.depth + pix), b = *(const float4*)(P.depth + pix + 4);
-			d8[0] = a.x; d8[1] = a.y; d8[2] = a.z; d8[3] = a.w; d8[4] = b.x; d8[5] = b.y; d8[6] = b.z; d8[7] = b.w;
+			if (need_c) { const uint4 a = *(const uint4*)(P.color + pix + 4 * q); c8[4 * q] = a.x; c8[4 * q + 1] = a.y; c8[4 * q + 2] = a.z; c8[4 * q + 3] = a.w; }
+			if (need_d) { const float4 a = *(const float4*)(P.depth + pix + 4 * q); d8[4 * q] = a.x; d8[4 * q + 1] = a.y; d8[4 * q + 2] = a.z; d8[4 * q + 3] = a.w; }
 		}
 	}
+	else if (N == 2 && px0 + 1 < (int)P.W && ((pix & 1u) == 0))
+	{
+		if (need_c) { const uint2 a = *(const uint2*)(P.color + pix); c8[0] = a.x; c8[1] = a.y; }
+		if (need_d) { const float2 a = *(const float2*)(P.depth + pix); d8[0] = a.x; d8[1] = a.y; }
+	}
 	else
-		for (int k = 0; k < 8; k++)
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++)
 			if (px0 + k < (int)P.W) { if (need_c) c8[k] = P.color[pix + k]; if (need_d) d8[k] = P.depth[pix + k]; }
+	}
 	if (!none_in)
-		for (int k = 0; k < 8; k++)
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++)
 		{
 			const bool inside = (px0 + k) >= cp.x0 && (px0 + k) < cp.x1;
 			if (inside && (cp.flags & 1u)) c8[k] = cp.word;
 			if (inside && (cp.flags & 2u)) d8[k] = 0.0f;
 			touched |= inside;
 		}
+	}
 }
 
 /* frag_weights() for a fragment outside the fast domain, from the list entry: out of line, the hot loop
@@ -194,10 +207,11 @@ __device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, flo
 	return clamp_color(run_fragment<FS>(P, fi));
 }
 
-template <int FS>
+template <int FS, int THS>
 __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_constant__ DrawParams P)
 {
-	__shared__ WarpShared S;
+	constexpr int TH = 1 << THS;                 /* tile rows */
+	__shared__ WarpShared<TH> S;
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
 	__syncthreads();            /* the only block-level barrier */
@@ -209,12 +223,12 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	uint32_t ty = blockIdx.y;
 	if (P.n_ranks > 1)
 	{
-		const uint32_t per = P.band_rows << (5u - WT_H_SHIFT);      /* tile rows per ownership group */
+		const uint32_t per = P.band_rows << (5u - THS);      /* tile rows per ownership group */
 		ty = ((ty / per) * P.n_ranks + P.rank) * per + ty % per;
 		if (ty >= P.tiles_y || !owns_tile_row(P, ty)) return;
 	}
 	const uint32_t tile = ty * P.tiles_x + tx;
-	WarpTile& T = S.w[wid];
+	WarpTile<TH>& T = S.w[wid];
 
 	/* list length; the cursor is re-armed for the next draw */
 	uint32_t n_raw = 0;
@@ -231,35 +245,41 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	const ClearParams cp = P.clear;
 	if (n_list == 0 && !cp.flags) return;
 
-	const int tile_x0 = (int)(tx << SWGL_TILE_SHIFT), tile_r0 = (int)(ty << WT_H_SHIFT);
+	const int tile_x0 = (int)(tx << SWGL_TILE_SHIFT), tile_r0 = (int)(ty << THS);
 	const int band_last_y = P.ytop - tile_r0;                /* raster y of tile row 0 */
-	const int band_first_y = band_last_y - (WT_H - 1);
+	const int band_first_y = band_last_y - (TH - 1);
 
-	/* ---- stage the tile: lane -> row lane/4, 8 pixels from column 8*(lane%4) ---- */
+	/* ---- stage the tile: every lane TH consecutive pixels (32 / TH lanes per row) ---- */
 	bool dirty = false;
 	{
-		const int r = (int)(lane >> 2), px0 = tile_x0 + (int)((lane & 3u) << 3);
-		const uint32_t s = (uint32_t)r * SWGL_TILE + ((lane & 3u) << 3);
+		const int r = (int)(lane >> (5 - THS)), seg = (int)(lane & ((32u >> THS) - 1u));
+		const int px0 = tile_x0 + (seg << THS);
+		const uint32_t s = (uint32_t)r * SWGL_TILE + (uint32_t)(seg << THS);
 		/* the usual frame: a pending clear of both attachments covers the whole tile, nothing is read */
 		const bool whole = (cp.flags & 3u) == 3u && cp.x0 <= tile_x0 && cp.x1 >= tile_x0 + SWGL_TILE
-		                   && cp.y0 <= tile_r0 && cp.y1 >= tile_r0 + WT_H
-		                   && tile_x0 + SWGL_TILE <= (int)P.W && tile_r0 + WT_H <= (int)P.H;
+		                   && cp.y0 <= tile_r0 && cp.y1 >= tile_r0 + TH
+		                   && tile_x0 + SWGL_TILE <= (int)P.W && tile_r0 + TH <= (int)P.H;
+		uint32_t c8[TH]; float d8[TH];
 		if (whole)
 		{
-			const uint4 cw = make_uint4(cp.word, cp.word, cp.word, cp.word);
-			const float4 dz = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			*(uint4*)&T.color[s] = cw; *(uint4*)&T.color[s + 4] = cw;
-			*(float4*)&T.depth[s] = dz; *(float4*)&T.depth[s + 4] = dz;
+#pragma unroll
+			for (int k = 0; k < TH; k++) { c8[k] = cp.word; d8[k] = 0.0f; }
 			dirty = true;
+		}
+		else wt_load<TH>(P, cp, tile_r0 + r, px0, c8, d8, dirty);
+		if (TH >= 4)
+		{
+#pragma unroll
+			for (int q = 0; q < TH / 4; q++)
+			{
+				*(uint4*)&T.color[s + 4 * q] = make_uint4(c8[4 * q], c8[4 * q + 1], c8[4 * q + 2], c8[4 * q + 3]);
+				*(float4*)&T.depth[s + 4 * q] = make_float4(d8[4 * q], d8[4 * q + 1], d8[4 * q + 2], d8[4 * q + 3]);
+			}
 		}
 		else
 		{
-			uint32_t c8[8]; float d8[8];
-			wt_load8(P, cp, tile_r0 + r, px0, c8, d8, dirty);
-			*(uint4*)&T.color[s] = make_uint4(c8[0], c8[1], c8[2], c8[3]);
-			*(uint4*)&T.color[s + 4] = make_uint4(c8[4], c8[5], c8[6], c8[7]);
-			*(float4*)&T.depth[s] = make_float4(d8[0], d8[1], d8[2], d8[3]);
-			*(float4*)&T.depth[s + 4] = make_float4(d8[4], d8[5], d8[6], d8[7]);
+			*(uint2*)&T.color[s] = make_uint2(c8[0], c8[1]);
+			*(float2*)&T.depth[s] = make_float2(d8[0], d8[1]);
 		}
 	}
 	__syncwarp();
@@ -332,9 +352,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 			}
 			uint32_t cnt = 0, nsp = 0, fast = 0;
 			uint32_t row0 = 0;                   /* tile row of the primitive's first walked row; sp[k] is the span k rows above it */
-			uint32_t sp[WT_H];
+			uint32_t sp[TH];
 #pragma unroll
-			for (int r = 0; r < WT_H; r++) sp[r] = 0u;
+			for (int r = 0; r < TH; r++) sp[r] = 0u;
 			if (lane < nb)
 			{
 				const PrimRef q = prim_ref(P, pid);
@@ -359,7 +379,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 						 * the viewport (swgl.c:3358-3361) -- and the edge switch is an integer compare. */
 						const int c1yi = (int)w.c1y;
 #pragma unroll
-						for (int k = 0; k < WT_H; k++)
+						for (int k = 0; k < TH; k++)
 						{
 							const int y = y_in + k;
 							if (y <= y_out)
@@ -380,7 +400,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					else
 					{
 #pragma unroll
-						for (int k = 0; k < WT_H; k++)
+						for (int k = 0; k < TH; k++)
 						{
 							const int y = y_in + k;
 							if (y <= y_out)
@@ -420,7 +440,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				if (lane >= take)
 				{
 #pragma unroll
-					for (int r = 0; r < WT_H; r++) sp[r] = 0u;
+					for (int r = 0; r < TH; r++) sp[r] = 0u;
 				}
 			}
 			n_tested += (lane == 0) ? total : 0u;
@@ -431,7 +451,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				uint32_t run = excl_k & 0xffffu, k = excl_k >> 16;
 				const uint32_t tag = (lane << 21) | (fast << 26);
 #pragma unroll
-				for (int j = 0; j < WT_H; j++)
+				for (int j = 0; j < TH; j++)
 				{
 					const uint32_t len = sp[j] >> 8;
 					if (len)
@@ -597,10 +617,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	{
 		const int px0 = tile_x0 + (int)((lane & 7u) << 2);
 #pragma unroll
-		for (int i = 0; i < WT_H / 4; i++)
+		for (int i = 0; i < (TH + 3) / 4; i++)
 		{
 			const int r = (int)(lane >> 3) + 4 * i, row = tile_r0 + r;
-			if (row >= (int)P.H) continue;
+			if (r >= TH || row >= (int)P.H) continue;
 			const size_t pixg = (size_t)row * P.W + (size_t)px0;
 			const uint32_t s = (uint32_t)r * SWGL_TILE + ((lane & 7u) << 2);
 			const uint4 c4 = *(const uint4*)&T.color[s];

@@ -47,9 +47,9 @@ def test_random_scene_matches_restatement(gpu_api, restatement, seed):
     rc, rd, rstats = restatement.render(sc, clear=clear, fill=fill)
     n = len(sc.indices) if sc.indices is not None else len(sc.vertices)
     cut = 3 * int(rng.integers(0, n // 3 + 1))
-    for path in (1, 2, 3):
+    for path, rows in ((1, 0), (2, 0), (3, 0), (3, 8), (3, 4)):       # warp rasteriser: its own choice of tile height (2 here), 8 and 4 rows
         draws = None if path == 1 else [(0, cut), (cut, n - cut)]       # also split the draw in two
         col, dep, stats, err = gpu_render(gpu_api, sc, indexed=sc.indices is not None, clear=clear, fill=fill,
-                                          options={"raster_path": path, "fuse_clear": int(rng.integers(0, 2))}, draws=draws)
+                                          options={"raster_path": path, "tile_rows": rows, "fuse_clear": int(rng.integers(0, 2))}, draws=draws)
         assert err == "", err
         assert_bit_exact(O.compare(col, dep, rc, rd), f"{sc.name} path {path}")

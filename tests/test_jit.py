@@ -53,7 +53,7 @@ def test_every_generic_shader_compiles_to_register_resident_kernels(name, tmp_pa
     kernels = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", usage)
     assert kernels, usage
     for fn, reg, stack, shared, local in kernels:
-        assert "ILi3EE" in fn                                  # k_vertex<SWVS_JIT> / k_raster_warp<SWFS_JIT>
+        assert "ILi3E" in fn                                   # k_vertex<SWVS_JIT> / k_raster_warp<SWFS_JIT, 3>
         assert int(local) == 0 and int(stack) <= 128, (fn, stack, local)   # interpreter: STACK 1536 / 2096
         if "k_raster_warp" in fn:
             assert int(reg) <= 64                              # 8 CTAs of 128 threads per SM, like the built-in shapes

@@ -32,14 +32,20 @@ def _small_scenes():
     return out
 
 
-PATHS = {1: "pixel_owner", 2: "fragment_parallel", 3: "warp_tile"}
+# 3: the warp rasteriser with the tile height it picks itself (2 rows for framebuffers this small); 38 / 34: pinned
+# to 8 and 4 rows (the heights of large framebuffers and of sort-first ranks)
+PATHS = {1: "pixel_owner", 2: "fragment_parallel", 3: "warp_tile", 38: "warp_tile_8_rows", 34: "warp_tile_4_rows"}
+
+
+def _opts(path):
+    return {"raster_path": 3, "tile_rows": path % 10} if path > 3 else {"raster_path": path}
 
 
 @pytest.mark.parametrize("path", sorted(PATHS), ids=lambda p: PATHS[p])
 @pytest.mark.parametrize("scene", _small_scenes(), ids=lambda s: s.name)
 def test_matches_reference_and_restatement(gpu_api, restatement, reference, scene, path):
     col, dep, stats, err = gpu_render(gpu_api, scene, indexed=scene.indices is not None,
-                                      options={"raster_path": path})
+                                      options=_opts(path))
     assert err == "", err
     rc, rd, rstats = restatement.render(scene)
     assert_bit_exact(O.compare(col, dep, rc, rd), "vs restatement")
@@ -88,8 +94,8 @@ def test_long_tile_lists_and_span_pool_cuts(gpu_api, restatement):
     the per-batch pool, and lists beyond the shared-memory sort capacity (2048)."""
     scene = S.random_triangles(6000, 256, 192, seed=77, extent=0.9, alpha=0.5)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2, 3):
-        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+    for path in (1, 2, 3, 38, 34):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options=_opts(path))
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
@@ -103,8 +109,8 @@ def test_depth_zero_reopens_pixels(gpu_api, restatement):
     v[::3, :, 2] = 0.0          # every third triangle lies exactly on z = 0
     v[1::7, :, 2] = -0.25       # some negative depths too
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2, 3):
-        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+    for path in (1, 2, 3, 38, 34):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options=_opts(path))
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["shaded"] == rstats["shaded"]
@@ -116,15 +122,15 @@ def test_bin_overflow_grows_and_splits(gpu_api, restatement):
     consecutive sub-draws (which keep the submission order).  Result must not change."""
     scene = S.random_triangles(1200, 256, 192, seed=5, extent=0.6, alpha=0.5)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2, 3):
+    for path in (1, 2, 3, 38, 34):
         # K = 4: grows until the longest list fits
-        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path, "bin_cap": 4})
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={**_opts(path), "bin_cap": 4})
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), "grow " + PATHS[path])
         assert gpu_api.swglGetOption(b"bin_cap") > 4
         # K = 8 and lists limited to 16 entries per tile: the draw has to be split recursively
         ntiles = ((scene.width + 31) // 32) * ((scene.height + 31) // 32)
-        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path, "bin_cap": 8,
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={**_opts(path), "bin_cap": 8,
                                                                    "bin_limit_bytes": ntiles * 16 * 4})
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), "split " + PATHS[path])
@@ -134,8 +140,8 @@ def test_tall_triangles_use_band_entries(gpu_api, restatement):
     """Triangles taller than SWGL_SHORT_ROWS keep per-band walk states; shorter ones are re-walked."""
     scene = S.random_triangles(300, 512, 768, seed=8, extent=0.95, alpha=0.7, centre_range=0.8)
     rc, rd, rstats = restatement.render(scene)
-    for path in (1, 2, 3):
-        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": path})
+    for path in (1, 2, 3, 38, 34):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options=_opts(path))
         assert err == "" and stats["bands"] > 0
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
 
@@ -167,8 +173,8 @@ def test_wide_and_tall_primitives_inside_a_fine_mesh(gpu_api, restatement):
         [idx[:half], np.arange(base, base + len(extra), dtype=np.uint32), idx[half:]]))
     mesh.name += "_mixed"
     rc, rd, rstats = restatement.render(mesh)
-    for path in (3, 2):
-        col, dep, stats, err = gpu_render(gpu_api, mesh, options={"raster_path": path})
+    for path in (3, 38, 34, 2):
+        col, dep, stats, err = gpu_render(gpu_api, mesh, options=_opts(path))
         assert err == ""
         assert_bit_exact(O.compare(col, dep, rc, rd), PATHS[path])
         assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
