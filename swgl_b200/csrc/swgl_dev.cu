@@ -1271,14 +1271,14 @@ static uint32_t th_shift_of(const swgldev_ctx* c, int path)
 		const uint32_t sh = c->opt_tile_rows == 8 ? 3u : c->opt_tile_rows == 4 ? 2u : 1u;
 		if (((c->H + (1u << sh) - 1u) >> sh) <= 1023u) return sh;
 	}
+	/* measured (tools/tile_rows_probe.py, r02): C1 (640x480, 1 200 tiles of 8 rows) 79.6 us with 8 rows, 73.5 with 4,
+	 * 85.3 with 2 (band entries and list insertions of its tall triangles grow faster than the raster kernel
+	 * shrinks); C2 (8 100 tiles) 51.8 / 56.7 / 141.7.  So: 4 rows below one resident wave of 8-row tiles, never 2
+	 * unless asked for. */
 	const uint32_t ranks = c->n_ranks ? c->n_ranks : 1u;
-	for (uint32_t sh = WT_H_SHIFT; sh > WT_H_SHIFT_MIN; sh--)
-	{
-		const size_t tiles = (size_t)c->tiles_x * ((c->H + (1u << sh) - 1u) >> sh) / ranks;
-		const bool finer_fits = ((c->H + (1u << (sh - 1u)) - 1u) >> (sh - 1u)) <= 1023u;
-		if (tiles >= 148u * 32u || !finer_fits) return sh;
-	}
-	return WT_H_SHIFT_MIN;
+	const size_t tiles8 = (size_t)c->tiles_x * ((c->H + 7u) >> 3) / ranks;
+	if (tiles8 < 148u * 32u && ((c->H + 3u) >> 2) <= 1023u) return 2u;
+	return WT_H_SHIFT;
 }
 
 template <int FS>
