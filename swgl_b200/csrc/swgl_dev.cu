@@ -197,6 +197,7 @@ struct swgldev_ctx
 
 	swgldev_stats stats;
 	uint64_t n_draws;
+	uint64_t draws_refused;              /* draws skipped because the viewport leaves the framebuffer rows (error string set) */
 	char error[512];
 
 	/* Device group (swgldev_create_group): one host thread drives several GPUs.  The leader (member 0, the
@@ -262,22 +263,27 @@ static int grow(swgldev_ctx* c, T** p, size_t* cap, size_t need)
  * ====================================================================================== */
 
 /* ---- glClear (swgl.c:3183-3214) ---- */
-__global__ void k_clear(uint32_t* __restrict__ color, float* __restrict__ depth, uint32_t W,
-                        ClearParams cp)
+/* Sort-first ranks clear the rows of the bands they own only (the other rows of the local attachment are
+ * nobody's, and in the assembled frame they belong to ranks that may be storing into them right now); `mirror`
+ * is the assembled colour target of those rows (a peer's attachment or a shared host mirror), if any. */
+__global__ void k_clear(uint32_t* __restrict__ color, float* __restrict__ depth, uint32_t* __restrict__ mirror, uint32_t W,
+                        ClearParams cp, uint32_t rank, uint32_t n_ranks, uint32_t band_rows)
 {
 	int y = cp.y0 + (int)blockIdx.y;
 	int x = cp.x0 + (int)(blockIdx.x * blockDim.x + threadIdx.x) * 4;
 	if (y >= cp.y1) return;
+	if (n_ranks > 1 && (((uint32_t)y >> 5) / band_rows) % n_ranks != rank) return;
 	size_t base = (size_t)y * W;
 	if (x + 3 < cp.x1 && (((base + (size_t)x) & 3u) == 0))
 	{
-		if (cp.flags & 1u) *(uint4*)(color + base + x) = make_uint4(cp.word, cp.word, cp.word, cp.word);
+		const uint4 w4 = make_uint4(cp.word, cp.word, cp.word, cp.word);
+		if (cp.flags & 1u) { *(uint4*)(color + base + x) = w4; if (mirror) *(uint4*)(mirror + base + x) = w4; }
 		if (cp.flags & 2u) *(float4*)(depth + base + x) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		return;
 	}
 	for (int k = 0; k < 4 && x + k < cp.x1; k++)
 	{
-		if (cp.flags & 1u) color[base + x + k] = cp.word;
+		if (cp.flags & 1u) { color[base + x + k] = cp.word; if (mirror) mirror[base + x + k] = cp.word; }
 		if (cp.flags & 2u) depth[base + x + k] = 0.0f;
 	}
 }
@@ -564,7 +570,23 @@ __device__ __forceinline__ uint32_t setup_one_prim(const DrawParams& P, uint32_t
 	if (ts.ye - ts.ys > (2 << P.th_shift) || (!INLINE_INSERT && !narrow))
 	{
 		const uint32_t nb = tr_hi - tr_lo + 1u;
-		band = atomicAdd(&P.ctr->band_cursor, nb);
+		/* one cursor round trip for the lanes of the warp that are here together (a draw of big triangles sends
+		 * every lane through this: a thousand same-address atomics that return a value take microseconds) */
+		{
+			const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u;
+			uint32_t before = 0, total = 0;
+			for (uint32_t m = act; m; m &= m - 1u)
+			{
+				const uint32_t j = (uint32_t)__ffs(m) - 1u;
+				const uint32_t v = __shfl_sync(act, nb, j);
+				total += v;
+				if (j < lane_id) before += v;
+			}
+			const uint32_t leader = (uint32_t)__ffs(act) - 1u;
+			uint32_t base = 0;
+			if (lane_id == leader) base = atomicAdd(&P.ctr->band_cursor, total);
+			band = __shfl_sync(act, base, leader) + before;
+		}
 		if ((unsigned long long)band + nb > (unsigned long long)P.cap_bands) { atomicOr(&P.ctr->overflow, 2u); return 0u; }
 	}
 	/* list entry; the record is written unless the consumer can gather the primitive itself */
@@ -1327,7 +1349,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
-	c->n_draws = 0; c->error[0] = 0;
+	c->n_draws = 0; c->draws_refused = 0; c->error[0] = 0;
 	for (int i = 0; i < SWGL_MAX_GROUP; i++) c->group[i] = nullptr;
 	c->n_group = 1; c->solo = 0; c->pool = nullptr; c->group_peer_ok = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0; c->gather = nullptr; c->gather_ring_pos = 0; c->gather_evicted = 0;
 	for (int i = 0; i < 4; i++) { c->gather_ring_ev[i] = nullptr; c->gather_ring_dst[i] = 0; }
@@ -1920,7 +1942,10 @@ static int flush_clear(swgldev_ctx* c)
 	if (cp.x1 <= cp.x0 || cp.y1 <= cp.y0) return 0;
 	dim3 block(128), grid(((uint32_t)(cp.x1 - cp.x0) + 511u) / 512u, (uint32_t)(cp.y1 - cp.y0));
 	if (guard_color_write(c)) return -1;
-	k_clear<<<grid, block, 0, c->stream>>>(c->color, c->depth, c->W, cp);
+	/* the assembled frame of a sort-first group lives in a peer's attachment (peer_color): the clear of this
+	 * rank's rows goes there too.  A host mirror (shared or own) is brought up to date by the next read-back. */
+	k_clear<<<grid, block, 0, c->stream>>>(c->color, c->depth, c->n_ranks > 1 ? c->peer_color : nullptr, c->W, cp,
+	                                       c->rank, c->n_ranks, c->band_rows ? c->band_rows : 1u);
 	c->mirror_synced = 0;
 	c->n_launches++;
 	CK(cudaGetLastError());
@@ -2264,6 +2289,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	    || c->tiles_x > 2047u || (c->H + (1u << WT_H_SHIFT) - 1) / (1u << WT_H_SHIFT) > 1023u)
 	{
 		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
+		c->draws_refused++;
 		return flush_clear(c);
 	}
 	const uint32_t ntri = (d->count + 2u) / 3u;
@@ -2732,6 +2758,7 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "selftest_division_mismatches")) return c->selftest_mismatches;
 	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "device_count")) return c->n_group;
+	if (!strcmp(name, "draws_refused")) return (int64_t)c->draws_refused;
 	if (!strcmp(name, "kernel_launches_all_devices"))
 	{
 		int64_t n = 0;

@@ -463,10 +463,30 @@ void swglBufferRespecify(GLenum target, GLsizei size, const void* data)
 	if (!b || !G.dev || !data || size == 0) return;
 	if (size > b->capacity)
 	{
-		if (b->data) swgldev_free(G.dev, b->data);
+		/* The storage moves.  glBindBuffer snapshots a named buffer into the vertex array's own struct
+		 * (swgl.c:3116-3122), so other vertex arrays -- and the named buffer -- may hold the old address: every
+		 * struct that shares it follows the move (or is emptied when the allocation fails). */
+		const swgldev_ptr old = b->data;
+		if (old) swgldev_free(G.dev, old);
 		b->data = swgldev_alloc(G.dev, size);
-		if (!b->data) { b->size = b->capacity = 0; return; }
-		b->capacity = size;
+		b->capacity = b->data ? size : 0;
+		if (!b->data) b->size = 0;
+		if (old)
+		{
+			for (int i = 0; i < G.vaos.n; i++)
+			{
+				gl_vao* v = G.vaos.items[i];
+				gl_buffer* both[2] = { &v->vertex, &v->element };
+				for (int k = 0; k < 2; k++)
+					if (both[k] != b && both[k]->data == old) { both[k]->data = b->data; both[k]->capacity = b->capacity; if (!b->data) both[k]->size = 0; }
+			}
+			for (int i = 0; i < G.buffers.n; i++)
+			{
+				gl_buffer* o = G.buffers.items[i];
+				if (o != b && o->data == old) { o->data = b->data; o->capacity = b->capacity; if (!b->data) o->size = 0; }
+			}
+		}
+		if (!b->data) return;
 	}
 	b->size = size;
 	if (target == GL_ELEMENT_ARRAY_BUFFER) swgldev_upload_indices(G.dev, b->data, data, size, &b->max_index);

@@ -295,3 +295,43 @@ def test_texture_respecified_right_after_a_draw_that_overflowed(gpu_api, referen
     a, b = _both(gpu_api, reference, script)
     assert gpu_api.swglGetOption(b"bin_cap") > 4
     _assert_same(a, b, 100)
+
+
+def test_respecify_that_moves_the_storage_reaches_every_vertex_array_sharing_it(gpu_api, restatement):
+    """glBindBuffer snapshots the named buffer into the vertex array's own struct (swgl.c:3116-3122); two vertex
+    arrays that bound the same name share its storage.  When swglBufferRespecify through one of them has to
+    grow (move) the storage, the other one must follow instead of reading freed memory."""
+    small, big = S.random_triangles(60, W, H, seed=11), S.random_triangles(200, W, H, seed=12)
+    api = gpu_api
+    api.glInit(W, H)
+    api.swglFillFramebuffer(0, C.c_float(0.0))
+    p, _, _ = _program(api, S.VS_PASSTHROUGH, S.FS_COLOR)
+    api.glUseProgram(p)
+    api.glViewport(0, 0, W, H)
+    api.glClearColor(0.0, 0.0, 0.0, 1.0)
+    v0 = np.ascontiguousarray(small.vertices, np.float32)
+    vbo = C.c_uint32(0)
+    api.glGenBuffers(1, C.byref(vbo))
+    api.glBindVertexArray(0)
+    api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)             # no vertex array bound: the name owns the data
+    api.glBufferData(G.GL_ARRAY_BUFFER, v0.nbytes, _ptr(v0), G.GL_STATIC_DRAW)
+    vaos = []
+    for _ in range(2):
+        vao = C.c_uint32(0)
+        api.glGenVertexArrays(1, C.byref(vao))
+        api.glBindVertexArray(vao.value)
+        api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)         # snapshot (alias) of the named buffer
+        api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
+        api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
+        vaos.append(vao.value)
+    v1 = np.ascontiguousarray(big.vertices, np.float32)
+    api.glBindVertexArray(vaos[0])
+    api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+    api.swglBufferRespecify(G.GL_ARRAY_BUFFER, v1.nbytes, _ptr(v1))     # larger: the storage moves
+    api.glBindVertexArray(vaos[1])                             # the other array still knows the old size only
+    api.glClear(3)
+    api.glDrawArrays(G.GL_TRIANGLES, 0, len(v0))
+    col = G.frame_color(api, W, H)
+    assert api.swglGetLastError().decode() == ""
+    want = restatement.render(big, count=len(v0))[0]
+    assert np.array_equal(col, want)

@@ -41,16 +41,20 @@ def test_c4_matches_restatement_at_full_size(gpu_api, restatement, c4):
     # these scenes -- colour hashes, coverage and fragment counts are -- so they are not pinned)
 
 
-@pytest.mark.parametrize("n_ranks,band", [(2, 1), (4, 2), (8, 1)])
-def test_stripe_emulation_equals_single_gpu(gpu_api, n_ranks, band):
+@pytest.mark.parametrize("n_ranks,band,fuse", [(2, 1, 1), (4, 2, 1), (8, 1, 1), (4, 1, 0)])
+def test_stripe_emulation_equals_single_gpu(gpu_api, n_ranks, band, fuse):
     """Sort-first sharding is a pure function of (tile row, N): rendering the N stripes one after
-    the other on one GPU and assembling them must equal the unsharded frame bit for bit."""
+    the other on one GPU and assembling them must equal the unsharded frame bit for bit.  fuse = 0: the
+    clear runs as its own kernel and touches the rank's rows only (the others belong to other ranks)."""
     scene = S.config(2)
     full = gpu_render(gpu_api, scene)
     stripes = []
     total_shaded = 0
     for r in range(n_ranks):
-        col, dep, stats, err = gpu_render(gpu_api, scene, stripe=(r, n_ranks, band), fill=(0xDEADBEEF, 0.0))
+        col, dep, stats, err = gpu_render(gpu_api, scene, stripe=(r, n_ranks, band), fill=(0xDEADBEEF, 0.0), options={"fuse_clear": fuse})
+        if not fuse:       # rows of other ranks keep what was there: the clear is not this rank's business
+            foreign = [r0 for rr in range(n_ranks) if rr != r for r0, _ in multigpu.rows_of_rank(scene.height, rr, n_ranks, band)]
+            assert (col[foreign[0]] == 0xDEADBEEF).all()
         assert err == ""
         stripes.append(col)
         total_shaded += stats["shaded"]
