@@ -45,6 +45,7 @@
 #include "swgl_jit.h"
 
 #define SWGL_MAX_GROUP 16
+#define SWGL_MAX_HOT_TILES 64       /* tiles whose list may exceed K and continue in the overflow pool */
 
 /* ========================================================================================
  * device group workers
@@ -161,6 +162,8 @@ struct swgldev_ctx
 	Prim* prims; size_t cap_prims;
 	BandEntry* bands; size_t cap_bands;
 	uint32_t* pairs; size_t cap_pairs;   /* tiles * bin_cap entries */
+	uint2* ov_pool; size_t cap_ov;       /* overflow pool of the deep tiles: (tile, entry) */
+	uint32_t* hot_store; size_t cap_hot; /* where the raster warps of deep tiles assemble their lists */
 	uint32_t bin_cap;                    /* K */
 	uint32_t* tile_count;
 	uint32_t* winner;                    /* GL_POINTS arbitration, W*H words, kept zeroed between draws */
@@ -182,6 +185,7 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_overflow_pool;               /* 1 (default): lists longer than K continue in the overflow pool; 0: K grows for every tile */
 	int opt_tile_rows;                   /* warp rasteriser: 8, 4 or 2 rows per tile; 0 = chosen per draw (th_shift_of) */
 	uint32_t cur_th_shift;               /* of the draw being issued (list capacity is per tile of that size) */
 	int opt_jit;                         /* compile generic shaders to kernels at run time (default 1; 0: on-device interpreter) */
@@ -444,12 +448,23 @@ __device__ __forceinline__ void lerp_vary(const DrawParams& P, uint32_t dst, uin
 }
 
 
+/* An entry beyond the tile's K inline slots: into the overflow pool (a few deep tiles must not size every
+ * list).  The draw is dropped and re-issued with larger scratch only when the pool itself is full or too many
+ * tiles are deep; both are known when the set-up kernels have finished, before any pixel is touched. */
+__device__ __noinline__ void bin_overflow(const DrawParams& P, uint32_t tile, uint32_t entry, uint32_t slot)
+{
+	if (slot == P.bin_cap && atomicAdd(&P.ctr->hot_tiles, 1u) >= P.max_hot) atomicOr(&P.ctr->overflow, 1u);
+	const uint32_t o = atomicAdd(&P.ctr->ov_cursor, 1u);
+	if (o < P.ov_cap) P.ov_pool[o] = make_uint2(tile, entry);
+	else atomicOr(&P.ctr->overflow, 1u);
+}
+
 /* list slot for primitive `pid` in `tile`, from the tile's atomic cursor */
 __device__ __forceinline__ void bin_insert(const DrawParams& P, uint32_t tile, uint32_t entry)
 {
 	const uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
 	if (slot < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot] = entry;
-	else atomicOr(&P.ctr->overflow, 1u);
+	else bin_overflow(P, tile, entry, slot);
 }
 
 /* The walk of a primitive that is not binned by its vertex extent (swgl.c:3356-3361, 3466-3471): tall,
@@ -738,7 +753,7 @@ __device__ __forceinline__ void setup_group(const DrawParams& P, float4 (*stage)
 		{
 			const uint32_t slot = b0 + (uint32_t)__popc(peers[k] & ((1u << lane) - 1u));
 			if (slot < P.bin_cap) P.pairs[(size_t)tile[k] * P.bin_cap + slot] = short_entry;
-			else atomicOr(&P.ctr->overflow, 1u);
+			else bin_overflow(P, tile[k], short_entry, slot);
 		}
 	}
 #pragma unroll
@@ -760,7 +775,7 @@ __device__ __forceinline__ void setup_group(const DrawParams& P, float4 (*stage)
 			{
 				const uint32_t slot = bs + (uint32_t)__popc(pr & ((1u << lane) - 1u));
 				if (slot < P.bin_cap) P.pairs[(size_t)tl * P.bin_cap + slot] = short_entry;
-				else atomicOr(&P.ctr->overflow, 1u);
+				else bin_overflow(P, tl, short_entry, slot);
 			}
 			cx++;
 		}
@@ -1338,10 +1353,11 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->clip = nullptr; c->cap_clip = 0; c->clip_xy = nullptr; c->cap_clip_xy = 0; c->vary = nullptr; c->cap_vary = 0;
 	c->prims = nullptr; c->cap_prims = 0; c->bin_cap = 0; c->side = nullptr; c->setup_event = nullptr; c->app_event = nullptr;
 	c->bands = nullptr; c->cap_bands = 0; c->pairs = nullptr; c->cap_pairs = 0;
+	c->ov_pool = nullptr; c->cap_ov = 0; c->hot_store = nullptr; c->cap_hot = 0;
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -1522,6 +1538,8 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->prims) cudaFree(c->prims);
 	if (c->bands) cudaFree(c->bands);
 	if (c->pairs) cudaFree(c->pairs);
+	if (c->ov_pool) cudaFree(c->ov_pool);
+	if (c->hot_store) cudaFree(c->hot_store);
 	if (c->ctr_event) cudaEventDestroy(c->ctr_event);
 	if (c->slice_ev) cudaEventDestroy(c->slice_ev);
 	if (c->gather_ev) cudaEventDestroy(c->gather_ev);
@@ -1892,6 +1910,29 @@ static int issue_sync(swgldev_ctx* c, DrawParams P, int depth)
 	return resolve_and_reissue(c, P, depth + 1);
 }
 
+/* pool of `entries` (tile, entry) pairs + room for SWGL_MAX_HOT_TILES whole lists in hot_store */
+static int ensure_overflow_pool(swgldev_ctx* c, size_t entries)
+{
+	if (entries > 0xfffffff0ull) entries = 0xfffffff0ull;
+	if (entries > c->cap_ov)
+	{
+		uint2* np = nullptr;
+		CK(cudaMallocAsync((void**)&np, entries * sizeof(uint2), c->stream));
+		if (c->ov_pool) CK(cudaFreeAsync(c->ov_pool, c->stream));
+		c->ov_pool = np; c->cap_ov = entries;
+	}
+	size_t hot = c->cap_ov + (size_t)SWGL_MAX_HOT_TILES * c->bin_cap;
+	if (hot > 0xfffffff0ull) hot = 0xfffffff0ull;
+	if (hot > c->cap_hot)
+	{
+		uint32_t* np = nullptr;
+		CK(cudaMallocAsync((void**)&np, hot * sizeof(uint32_t), c->stream));
+		if (c->hot_store) CK(cudaFreeAsync(c->hot_store, c->stream));
+		c->hot_store = np; c->cap_hot = hot;
+	}
+	return 0;
+}
+
 /* Precondition: the last attempt at `P` was dropped by the device (overflow flag set). */
 static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 {
@@ -1901,7 +1942,12 @@ static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 	CK(cudaMemcpy(&h, c->ctr, sizeof(h), cudaMemcpyDeviceToHost));
 	if (h.overflow & 2u)
 		if (grow(c, &c->bands, &c->cap_bands, (size_t)h.band_cursor + (size_t)h.band_cursor / 4 + 1024)) return -1;
-	if (h.overflow & 1u)
+	if ((h.overflow & 1u) && P.ov_cap && h.hot_tiles <= SWGL_MAX_HOT_TILES && (size_t)h.ov_cursor * 12u <= c->opt_bin_limit)
+	{
+		/* a few deep tiles: the pool was too small, every other list is fine */
+		if (ensure_overflow_pool(c, (size_t)h.ov_cursor + (size_t)h.ov_cursor / 4 + 1024)) return -1;
+	}
+	else if (h.overflow & 1u)
 	{
 		const size_t ntiles = (size_t)c->tiles_x * ((c->H + (1u << P.th_shift) - 1) >> P.th_shift);   /* tiles of this draw */
 		size_t want = (size_t)h.max_list + (size_t)h.max_list / 4 + 64;
@@ -1920,6 +1966,7 @@ static int resolve_and_reissue(swgldev_ctx* c, const DrawParams& P, int depth)
 		}
 		if (grow(c, &c->pairs, &c->cap_pairs, want * ntiles)) return -1;
 		c->bin_cap = (uint32_t)(c->cap_pairs / ntiles);
+		if (ensure_overflow_pool(c, c->cap_ov)) return -1;      /* hot_store holds SWGL_MAX_HOT_TILES lists of the new K */
 	}
 	return issue_sync(c, P, depth);
 }
@@ -2145,6 +2192,10 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	P.cap_bands = (uint32_t)(c->cap_bands > 0xffffffffull ? 0xffffffffull : c->cap_bands);
 	P.bin_cap = c->bin_cap;
 	P.bands = c->bands; P.pairs = c->pairs;
+	/* overflow pool of deep tiles: warp rasteriser only (the CTA cross-check kernels have no gather step) */
+	P.max_hot = SWGL_MAX_HOT_TILES;
+	P.ov_pool = c->ov_pool; P.ov_cap = (P.th_shift < SWGL_TILE_SHIFT && c->opt_overflow_pool) ? (uint32_t)c->cap_ov : 0u;
+	P.hot_store = c->hot_store; P.hot_cap = (uint32_t)c->cap_hot;
 	c->last_draw = P; c->last_draw_valid = 1;
 
 	const bool timing = c->opt_stage_timing != 0;
@@ -2336,6 +2387,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		const size_t ntiles = (size_t)c->tiles_x * ((c->H + (1u << c->cur_th_shift) - 1) >> c->cur_th_shift);   /* tiles of the current draw */
 		if (c->bin_cap == 0) c->bin_cap = 256;
 		if (grow(c, &c->pairs, &c->cap_pairs, ntiles * c->bin_cap)) return -1;
+		if (ensure_overflow_pool(c, c->cap_ov ? c->cap_ov : ((size_t)1 << 18))) return -1;
 	}
 	P.clip = c->clip; P.clip_xy = c->clip_xy; P.vary = c->vary; P.prims = c->prims; P.prims2 = c->prims + ntri;
 
@@ -2693,6 +2745,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "mip_lod")) c->opt_mip_lod = value ? 1 : 0;
 	else if (!strcmp(name, "jit")) c->opt_jit = value ? 1 : 0;
 	else if (!strcmp(name, "tile_rows")) c->opt_tile_rows = (int)value;
+	else if (!strcmp(name, "overflow_pool")) c->opt_overflow_pool = value ? 1 : 0;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
@@ -2755,6 +2808,8 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "stage_draws")) return (int64_t)c->stage_draws;
 	if (!strncmp(name, "stage_ns_", 9)) { int i = atoi(name + 9); return (i >= 0 && i < 3) ? (int64_t)(c->stage_us[i] * 1000.0) : -1; }
 	if (!strcmp(name, "bin_cap")) return c->bin_cap;
+	if (!strcmp(name, "overflow_pool_entries")) return (int64_t)c->cap_ov;
+	if (!strcmp(name, "pairs_bytes")) return (int64_t)(c->cap_pairs * 4);
 	if (!strcmp(name, "selftest_division_mismatches")) return c->selftest_mismatches;
 	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "device_count")) return c->n_group;

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ DrawPara
 	{
 		/* per-draw counters: this kernel is the first of the draw */
 		P.ctr->band_cursor = 0; P.ctr->max_list = 0; P.ctr->overflow = 0; P.ctr->prims_out = 0; P.ctr->pair_total = 0ull;
+		P.ctr->ov_cursor = 0; P.ctr->hot_tiles = 0; P.ctr->hot_cursor = 0;
 	}
 	if (v < SWGL_CTR_SLOTS && blockIdx.x == 0) { P.ctr->tested[v] = 0ull; P.ctr->shaded[v] = 0ull; }
 	if (v >= P.n_shade) return;

@@ -63,6 +63,10 @@ struct Counters
 	uint32_t overflow;          /* bit0: a tile list exceeded K, bit1: band scratch too small; the draw
 	                               is dropped and re-issued by the host */
 	uint32_t prims_out;
+	uint32_t ov_cursor;         /* entries requested in the overflow pool (lists longer than K) */
+	uint32_t hot_tiles;         /* tiles whose list is longer than K */
+	uint32_t hot_cursor;        /* words handed out of hot_store to the raster warps of those tiles */
+	uint32_t _pad;
 	unsigned long long pair_total;   /* bin entries consumed by the raster CTAs */
 	unsigned long long tested[SWGL_CTR_SLOTS];
 	unsigned long long shaded[SWGL_CTR_SLOTS];
@@ -107,6 +111,11 @@ struct DrawParams
 	Prim* prims; Prim* prims2;  /* primitive 2t at prims[t], 2t+1 (second triangle of a near-clipped input) at prims2[t] */
 	BandEntry* bands; uint32_t cap_bands;
 	uint32_t* tile_count; uint32_t* pairs; uint32_t bin_cap;   /* K: list capacity per tile; entries are (id << 1) | has_record */
+	/* A few tiles may be much deeper than the rest (localised overdraw): entries beyond K go to one pool as
+	 * (tile, entry) pairs, and the raster warp of such a tile assembles its whole list in hot_store (K inline
+	 * entries + its pool entries) before sorting it.  ov_cap = 0: no pool (the CTA cross-check kernels). */
+	uint2* ov_pool; uint32_t ov_cap; uint32_t max_hot;
+	uint32_t* hot_store; uint32_t hot_cap;
 	uint32_t lean_prims;        /* short unclipped primitives have no record (warp rasteriser draws) */
 	uint32_t inline_tall;       /* tall primitives are inserted by the set-up kernel itself (no k_bin_tall launch) */
 	Counters* ctr;

@@ -237,11 +237,13 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 		n_raw = P.tile_count[tile];
 		if (n_raw) P.tile_count[tile] = 0u;
 		if (n_raw > P.bin_cap) atomicMax(&P.ctr->max_list, n_raw);
-		else if (n_raw && P.count_fragments) atomicAdd(&P.ctr->pair_total, (unsigned long long)n_raw);
+		if (n_raw && P.count_fragments && (n_raw <= P.bin_cap || P.ov_cap)) atomicAdd(&P.ctr->pair_total, (unsigned long long)n_raw);
 	}
 	n_raw = __shfl_sync(0xffffffffu, n_raw, 0);
 	if (P.ctr->overflow || P.diag) return;
-	const uint32_t n_list = min(n_raw, P.bin_cap);
+	/* n_raw > K: a deep tile, its list continues in the overflow pool (assembled below); without a pool the
+	 * draw has been flagged and never gets here */
+	uint32_t n_list = (n_raw > P.bin_cap && !P.ov_cap) ? P.bin_cap : n_raw;
 	const ClearParams cp = P.clear;
 	if (n_list == 0 && !cp.flags) return;
 
@@ -296,6 +298,31 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	{
 		/* ---- ascending primitive id = submission order ---- */
 		uint32_t* gl_ids = P.pairs + (size_t)tile * P.bin_cap;
+		if (n_list > P.bin_cap)
+		{
+			/* deep tile: K inline entries + this tile's entries of the pool, gathered into hot_store (the set-up
+			 * kernels have checked that the pool and hot_store are large enough) and sorted there */
+			uint32_t hb = 0;
+			if (lane == 0) hb = atomicAdd(&P.ctr->hot_cursor, n_raw);
+			hb = __shfl_sync(0xffffffffu, hb, 0);
+			uint32_t* dst = P.hot_store + hb;
+			for (uint32_t i = lane; i < P.bin_cap; i += 32) dst[i] = gl_ids[i];
+			uint32_t wr = P.bin_cap;
+			const uint32_t tot = min(P.ctr->ov_cursor, P.ov_cap);
+			for (uint32_t i0 = 0; i0 < tot; i0 += 32)
+			{
+				const uint32_t i = i0 + lane;
+				uint2 e = make_uint2(0xffffffffu, 0u);
+				if (i < tot) e = P.ov_pool[i];
+				const bool mine = e.x == tile;
+				const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+				if (mine) dst[wr + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = e.y;
+				wr += (uint32_t)__popc(bal);
+			}
+			__syncwarp();
+			n_list = min(wr, n_raw);
+			gl_ids = dst;
+		}
 		const uint32_t* sorted = gl_ids;
 		uint32_t xs0 = 0xffffffffu, xs1 = 0xffffffffu, xs2 = 0xffffffffu, xs3 = 0xffffffffu;
 		if (n_list <= 128)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from swgl_b200 import scenes as S
+from swgl_b200 import gl as G, scenes as S
 
 from util import assert_bit_exact, gpu_render
 
@@ -192,3 +192,43 @@ def test_wide_framebuffers_around_the_fast_division_domain(gpu_api, restatement,
     assert err == ""
     assert_bit_exact(O.compare(col, dep, rc, rd), scene.name)
     assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
+
+
+@pytest.mark.parametrize("deep", [3000, 100000])
+def test_one_deep_tile_goes_through_the_overflow_pool(gpu_api, restatement, deep):
+    """Localised overdraw: `deep` small blended triangles on one spot of an otherwise ordinary mesh.  The
+    lists of the few tiles under the spot continue in the overflow pool; K and the per-tile lists stay as
+    they are and the draw is not issued a second time (3 kernels), unless the pool itself has to grow once."""
+    import copy
+    mesh = S.grid_mesh(24, 320, 200, alpha=0.5)
+    rng = np.random.default_rng(3)
+    spot = np.empty((deep * 3, 8), np.float32)
+    c = np.array([0.31, -0.17], np.float32)
+    spot[:, 0:2] = c + rng.uniform(-0.02, 0.02, (deep * 3, 2)).astype(np.float32)
+    spot[:, 2] = rng.uniform(0.1, 0.9, deep * 3)
+    spot[:, 3] = 1.0
+    spot[:, 4:7] = rng.uniform(0, 1, (deep * 3, 3))
+    spot[:, 7] = 0.5
+    sc = copy.copy(mesh)
+    sc.vertices = np.concatenate([mesh.deindexed(), spot]).astype(np.float32)
+    sc.indices = None
+    sc.name = f"deep_tile_{deep}"
+    rc, rd, rstats = restatement.render(sc)
+    gpu_render(gpu_api, sc, indexed=False)                         # first frame: scratch reaches its steady size
+    api = gpu_api
+    pairs0, k0 = api.swglGetOption(b"pairs_bytes"), api.swglGetOption(b"bin_cap")
+    n0 = api.swglGetOption(b"kernel_launches")
+    api.glClear(3)
+    api.glDrawArrays(G.GL_TRIANGLES, 0, len(sc.vertices))
+    api.swglFinish()
+    assert api.swglGetOption(b"kernel_launches") - n0 == 3         # vertex, set-up, raster: no second issue
+    assert api.swglGetOption(b"bin_cap") == k0 == 256 and api.swglGetOption(b"pairs_bytes") == pairs0
+    col, dep, stats, err = gpu_render(gpu_api, sc, indexed=False)
+    assert err == "", err
+    assert_bit_exact(O.compare(col, dep, rc, rd), sc.name)
+    assert stats["tested"] == rstats["tested"] and stats["shaded"] == rstats["shaded"]
+    # the same scene with the pool switched off: K grows for every tile instead, same bits
+    col2, dep2, _, err2 = gpu_render(gpu_api, sc, indexed=False, options={"overflow_pool": 0})
+    assert err2 == "" and np.array_equal(col, col2) and np.array_equal(dep.view(np.uint32), dep2.view(np.uint32))
+    if deep >= 100000:
+        assert gpu_api.swglGetOption(b"bin_cap") > 256
