@@ -45,6 +45,9 @@
 #include "swgl_jit.h"
 
 #define SWGL_MAX_GROUP 16
+#ifndef SWGL_BIN_TALL_CTAS_PER_SM
+#define SWGL_BIN_TALL_CTAS_PER_SM 8   /* a warp handles its band entries one after the other, three dependent loads each: many warps, few entries per warp */
+#endif
 #define SWGL_MAX_HOT_TILES 64       /* tiles whose list may exceed K and continue in the overflow pool */
 
 /* ========================================================================================
@@ -2220,7 +2223,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		cfg.attrs = at; cfg.numAttrs = 1;
 		CK(cudaLaunchKernelEx(&cfg, k_setup_bin, P));
 	}
-	if (!P.inline_tall) k_bin_tall<<<148 * 2, 256, 0, c->stream>>>(P);
+	if (!P.inline_tall) k_bin_tall<<<148 * SWGL_BIN_TALL_CTAS_PER_SM, 256, 0, c->stream>>>(P);
 	STAGE(2);
 	/* overflow flags are final once set-up is done: snapshot them on the side stream so the next
 	 * draw can be queued while this one is still rasterising */
