@@ -140,8 +140,21 @@ void  swglHostFree(void* p);
  * primitives have no record, the rasteriser gathers them through the element buffer; 0 writes a record for every one),
  * "selftest_division" (value = number of operand pairs: runs the device self-test of the shared-reciprocal division
  * against `/`, mismatches in "selftest_division_mismatches");
+ * "jit" (1 default: shaders outside the built-in shapes are compiled to kernels at run time with NVRTC; 0: the
+ * on-device interpreter, kept as the cross-check);
+ * "mip_lod" (0 default: glGenerateMipmap builds the chain but the base level is sampled, which is what the compiled
+ * reference does -- its level of detail goes through an rsqrt() with undefined behaviour, swgl.c:3240-3246; 1: the
+ * chain is sampled with the per-triangle level the same code gives with a 32-bit pun, bit-identical to the reference
+ * built that way, oracle/ref_shim.c);
+ * "tile_rows" (0 default: 8 rows per tile, 4 when the context owns less than one resident wave of 8-row tiles; 8 / 4 /
+ * 2 pin it); "overflow_pool" (1 default: tile lists longer than bin_cap continue in a shared overflow pool; 0: bin_cap
+ * grows for every tile instead);
  * read-only: "wt_draws", "mirror_synced", "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
- * "stage_draws", "tile_size", "device". */
+ * "stage_draws", "tile_size", "last_tile_rows", "device", "device_count", "last_vs_kind" / "last_fs_kind" (shape of the last
+ * draw as launched: 0 interpreter, 1 / 2 built-in shapes, 3 run-time compiled), "jit_compiles", "jit_cache_hits",
+ * "jit_compile_us_total", "draws_refused" (draws skipped because the viewport leaves the framebuffer rows: the reference
+ * folds the rows outside onto row Height-1, swgl.c:3386, this library reports it through swglGetLastError and draws
+ * nothing), "overflow_pool_entries", "pairs_bytes", "bin_cap". */
 void swglSetOption(const char* name, int64_t value);
 int64_t swglGetOption(const char* name);
 
