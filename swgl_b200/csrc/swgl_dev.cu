@@ -204,6 +204,9 @@ struct swgldev_ctx
 
 	swgldev_stats stats;
 	uint64_t n_draws;
+	int in_fold;                         /* the draw being issued renders into the virtual framebuffer of draw_folded() */
+	int64_t fold_shift;                  /* virtual storage row = real storage row - fold_shift (<= 0) */
+	uint64_t draws_folded;
 	uint64_t draws_refused;              /* draws skipped because the viewport leaves the framebuffer rows (error string set) */
 	char error[512];
 
@@ -1265,6 +1268,117 @@ __global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ Dr
 #include "swgl_raster_frag.cuh"
 #include "swgl_raster_warp.cuh"
 
+/* ---- viewports that leave the framebuffer vertically (swgl.c:3386) ----
+ * The reference stores raster row y at row min(Height-1, (unsigned)(VH-1+2*VY-y)): every row whose storage row
+ * would be negative or beyond the framebuffer lands on row Height-1, where the fragments of several rows of a
+ * primitive -- and of all primitives -- then meet in (primitive, y) order.  The tile machinery needs one raster
+ * row per storage row, so such a draw is rendered in two parts (draw_folded): the rows that map inside
+ * [0, Height-2] through the ordinary kernels into a virtual framebuffer tall enough for the whole viewport, and
+ * row Height-1 by this kernel: one thread per pixel column walks every primitive in submission order and, for
+ * each, its aliased rows in ascending y, with the exact (slow-path) fragment arithmetic.  Correct, not fast:
+ * a client with an oversized or offset viewport gets the reference's frame instead of nothing. */
+__device__ __forceinline__ bool fold_aliased(const DrawParams& P, int y)
+{
+	const long long srow = (long long)P.ytop - (long long)y;
+	return srow < 0 || srow >= (long long)P.H - 1;
+}
+
+template <int FS>
+__device__ __forceinline__ void fold_prim(const DrawParams& P, int x, const float4& a, const float4& b, const float4& c,
+                                          uint32_t v0, uint32_t v1, uint32_t v2, uint32_t& col, float& dep,
+                                          uint32_t& n_tested, uint32_t& n_shaded)
+{
+	TriWalk w;
+	if (!tri_setup(a, b, c, P, w)) return;
+	/* aliased rows: y > ytop (negative storage row) or y <= ytop - (H - 1) */
+	const long long hi_from = (long long)P.ytop + 1, lo_to = (long long)P.ytop - ((long long)P.H - 1);
+	if (!((long long)w.ye - 1 >= hi_from || (long long)w.ys <= lo_to)) return;
+	BaryConst k;
+	bary_setup(a, b, c, k);
+	float x0 = w.c0x, x1 = w.c0x, s1 = w.s1;
+	bool switched = false;
+	for (int y = w.ys; y < w.ye; y++)
+	{
+		if (fold_aliased(P, y))
+		{
+			int xa, xb;
+			row_span(x0, x1, P, xa, xb);
+			if (x >= xa && x < xb)
+			{
+				n_tested++;
+				FragIn fi;
+				float z;
+				frag_weights(k, (float)x, (float)y, fi.u, fi.v, fi.w, z);
+				if (dep == 0.0f || dep >= z)     /* swgl.c:3387 */
+				{
+					dep = z;
+					n_shaded++;
+					fi.vid0 = v0; fi.vid1 = v1; fi.vid2 = v2;
+					fi.a = P.vary + (size_t)v0 * P.nvf + P.fs_slot;
+					fi.b = P.vary + (size_t)v1 * P.nvf + P.fs_slot;
+					fi.c = P.vary + (size_t)v2 * P.nvf + P.fs_slot;
+					fi.stride = 1;
+					fi.lod = (FS == SWFS_GENERIC && P.mip_lod) ? mip_level(a.x, a.y, b.x, b.y, c.x, c.y) : 0.0f;
+					const float4 o = run_fragment<FS>(P, fi);
+					col = blend_pack(o.x, o.y, o.z, o.w, col);
+				}
+			}
+		}
+		if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; s1 = w.s2; x1 = w.c1x; }
+		x0 += w.s0; x1 += s1;
+	}
+}
+
+template <int FS>
+__global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawParams P, int x_lo, int x_hi)
+{
+	const int x = x_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (x >= x_hi) return;
+	const size_t pix = (size_t)(P.H - 1u) * P.W + (size_t)x;
+	uint32_t col = P.color[pix];
+	float dep = P.depth[pix];
+	uint32_t n_tested = 0, n_shaded = 0;
+	for (uint32_t t = 0; t < P.ntri; t++)
+	{
+		float4 p0, p1, p2;
+		uint32_t s0, s1, s2;
+		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
+		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
+		if (in_mask == 7u) { fold_prim<FS>(P, x, p0, p1, p2, s0, s1, s2, col, dep, n_tested, n_shaded); continue; }
+		if (in_mask == 0u) continue;
+		/* near clip again (swgl.c:563-696); the varyings of the new vertices were written by the set-up kernel */
+		const float2 zz = make_float2(0.0f, 0.0f);
+		const float2 c0 = (s0 < P.n_shade) ? P.clip_xy[s0] : zz, c1 = (s1 < P.n_shade) ? P.clip_xy[s1] : zz, c2 = (s2 < P.n_shade) ? P.clip_xy[s2] : zz;
+		const float4 p[3] = { make_float4(c0.x, c0.y, p0.z, p0.w), make_float4(c1.x, c1.y, p1.z, p1.w), make_float4(c2.x, c2.y, p2.z, p2.w) };
+		const uint32_t sid[3] = { s0, s1, s2 };
+		int in_idx[3], out_idx[3], n_in = 0, n_out = 0;
+		for (int j = 0; j < 3; j++) { if ((in_mask >> j) & 1u) in_idx[n_in++] = j; else out_idx[n_out++] = j; }
+		const uint32_t new0 = P.clip_vid_base + 2u * t, new1 = new0 + 1u;
+		float t0, t1;
+		if (n_in == 1)
+		{
+			const int ia = in_idx[0];
+			const float4 q1 = near_intersect(p[ia], p[out_idx[0]], t0), q2 = near_intersect(p[ia], p[out_idx[1]], t1);
+			fold_prim<FS>(P, x, to_screen(p[ia], P), to_screen(q1, P), to_screen(q2, P), sid[ia], new0, new1, col, dep, n_tested, n_shaded);
+		}
+		else
+		{
+			const int ia = in_idx[0], ib = in_idx[1], io = out_idx[0];
+			const float4 q0 = near_intersect(p[ia], p[io], t0), q1 = near_intersect(p[ib], p[io], t1);
+			const float4 sq0 = to_screen(q0, P);
+			fold_prim<FS>(P, x, to_screen(p[ia], P), to_screen(p[ib], P), sq0, sid[ia], sid[ib], new0, col, dep, n_tested, n_shaded);
+			fold_prim<FS>(P, x, to_screen(p[ib], P), sq0, to_screen(q1, P), sid[ib], new0, new1, col, dep, n_tested, n_shaded);
+		}
+	}
+	P.color[pix] = col;
+	P.depth[pix] = canon_nan(dep);
+	if (P.count_fragments && (n_tested | n_shaded))
+	{
+		atomicAdd(&P.ctr->tested[x % SWGL_CTR_SLOTS], (unsigned long long)n_tested);
+		atomicAdd(&P.ctr->shaded[x % SWGL_CTR_SLOTS], (unsigned long long)n_shaded);
+	}
+}
+
 /* raster_path: 1 = pixel-owner CTA per 32x32 tile (k_raster), 2 = fragment-parallel CTA per 32x32
  * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = default = the warp kernel for
  * every draw.  All three produce identical bits. */
@@ -1368,7 +1482,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
 	memset(&c->stats, 0, sizeof(c->stats));
-	c->n_draws = 0; c->draws_refused = 0; c->error[0] = 0;
+	c->n_draws = 0; c->draws_refused = 0; c->draws_folded = 0; c->in_fold = 0; c->fold_shift = 0; c->error[0] = 0;
 	for (int i = 0; i < SWGL_MAX_GROUP; i++) c->group[i] = nullptr;
 	c->n_group = 1; c->solo = 0; c->pool = nullptr; c->group_peer_ok = 0; c->mirror_borrowed = 0; c->slice_ev = nullptr; c->gather_ev = nullptr; c->gather_pending = 0; c->gather = nullptr; c->gather_ring_pos = 0; c->gather_evicted = 0;
 	for (int i = 0; i < 4; i++) { c->gather_ring_ev[i] = nullptr; c->gather_ring_dst[i] = 0; }
@@ -2277,7 +2391,7 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 	P.fvx = (float)d->vx; P.fvy = (float)d->vy;
 	P.xlimit = (float)(uint32_t)((uint32_t)d->vx + d->vw);
 	P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
-	P.ytop = (int32_t)d->vh - 1 + 2 * d->vy;
+	P.ytop = (int32_t)((int64_t)d->vh - 1 + 2 * (int64_t)d->vy - c->fold_shift);
 	P.rank = c->rank; P.n_ranks = c->n_ranks; P.band_rows = c->band_rows ? c->band_rows : 1;
 	P.vbo = (const uint8_t*)(uintptr_t)d->vbo; P.vbo_bytes = d->vbo_bytes;
 	P.ibo = (const uint32_t*)(uintptr_t)d->ibo; P.ibo_count = d->ibo_bytes / 4u;
@@ -2320,6 +2434,8 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 	return 0;
 }
 
+static int draw_folded(swgldev_ctx* c, const swgldev_draw* d);
+
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 {
 	if (IS_GROUP(c))
@@ -2339,7 +2455,13 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	/* The tile mapping needs storage row = VH-1+2*VY-y to be a bijection on the viewport rows,
 	 * i.e. the viewport lies inside the framebuffer vertically (otherwise the reference clamps
 	 * several raster rows onto row Height-1, swgl.c:3386). */
-	if (d->vy < 0 || (uint64_t)d->vy + d->vh > c->H || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
+	const bool outside = d->vy < 0 || (uint64_t)d->vy + d->vh > c->H;
+	if (outside && !c->in_fold && d->vw <= 0x7fffffffu && d->vh <= 0x7fffffffu && c->tiles_x <= 2047u)
+	{
+		const int rc = draw_folded(c, d);
+		if (rc != 1) return rc;           /* 1: not possible here, refused below */
+	}
+	if ((outside && !c->in_fold) || d->vw > 0x7fffffffu || d->vh > 0x7fffffffu
 	    || c->tiles_x > 2047u || (c->H + (1u << WT_H_SHIFT) - 1) / (1u << WT_H_SHIFT) > 1023u)
 	{
 		set_err(c, "draw skipped: viewport must lie inside the framebuffer rows (0 <= y, y+height <= Height)", cudaSuccess);
@@ -2409,7 +2531,7 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 		if (!c->color_exposed && (c->mirror_synced || full_clear)) { c->mirror_synced = 1; P.peer_color = c->shared_mirror_dev; c->wt_draws++; }
 		else { c->mirror_synced = 0; P.peer_color = nullptr; }
 	}
-	else if (c->opt_host_mirror && !P.peer_color && c->n_ranks == 1 && !c->color_exposed && (c->mirror_synced || full_clear)
+	else if (c->opt_host_mirror && !c->in_fold && !P.peer_color && c->n_ranks == 1 && !c->color_exposed && (c->mirror_synced || full_clear)
 	    && (c->opt_host_mirror == 2 || (c->wt_predict && c->draws_since_map <= 2)))
 	{
 		c->mirror_synced = 1;
@@ -2424,6 +2546,77 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	c->stats.triangles_in = ntri;
 	if (launch_draw(c, P)) return -1;
 	return stamp_draw(c, d);
+}
+
+
+/* A draw whose viewport leaves the framebuffer rows (see k_fold_row).  Returns 0 / -1 when the draw has been
+ * handled, 1 when this configuration cannot do it (sort-first ranks, assembled targets, a virtual framebuffer
+ * beyond the tile-row limit): the caller then refuses the draw as before. */
+static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
+{
+	if (c->n_ranks > 1 || c->peer_color || c->shared_mirror || c->n_group > 1 || c->mirror_borrowed) return 1;
+	if (raster_path_for(c, 0) != 3) return 1;
+	const int64_t s_lo = d->vy < 0 ? (int64_t)d->vy : 0;
+	const int64_t s_hi = (int64_t)d->vy + (int64_t)d->vh > (int64_t)c->H ? (int64_t)d->vy + (int64_t)d->vh : (int64_t)c->H;
+	const int64_t Hv = s_hi - s_lo;
+	if (Hv <= 0 || (Hv + 7) / 8 > 1023 || d->vh == 0 || c->H < 1 || c->W == 0) return 1;
+	if (flush_clear(c)) return -1;
+	if (guard_color_write(c)) return -1;
+	const size_t npx = (size_t)c->W * (size_t)Hv;
+	const size_t ntiles = (size_t)c->tiles_x * (size_t)((Hv + (1 << WT_H_SHIFT_MIN) - 1) >> WT_H_SHIFT_MIN) + 1;
+	uint32_t* vcol = nullptr; float* vdep = nullptr; uint32_t* vcount = nullptr;
+	CK(cudaMallocAsync((void**)&vcol, npx * 4, c->stream));
+	CK(cudaMallocAsync((void**)&vdep, npx * 4, c->stream));
+	CK(cudaMallocAsync((void**)&vcount, ntiles * 4, c->stream));
+	CK(cudaMemsetAsync(vcol, 0, npx * 4, c->stream));
+	CK(cudaMemsetAsync(vdep, 0, npx * 4, c->stream));
+	CK(cudaMemsetAsync(vcount, 0, ntiles * 4, c->stream));
+	/* real rows 0 .. H-2 keep their place in the virtual framebuffer; row H-1 and the rows outside are the fold */
+	const size_t keep = (size_t)(c->H - 1u) * c->W * 4;
+	const size_t off = (size_t)(-s_lo) * c->W;
+	if (keep)
+	{
+		CK(cudaMemcpyAsync(vcol + off, c->color, keep, cudaMemcpyDeviceToDevice, c->stream));
+		CK(cudaMemcpyAsync(vdep + off, c->depth, keep, cudaMemcpyDeviceToDevice, c->stream));
+	}
+	uint32_t* const rcol = c->color; float* const rdep = c->depth; uint32_t* const rcount = c->tile_count;
+	const uint32_t rH = c->H, rty = c->tiles_y;
+	c->color = vcol; c->depth = vdep; c->tile_count = vcount; c->H = (uint32_t)Hv; c->tiles_y = (uint32_t)((Hv + SWGL_TILE - 1) / SWGL_TILE);
+	c->fold_shift = s_lo; c->in_fold = 1;
+	int rc = swgldev_draw_triangles(c, d);
+	if (!rc) rc = settle_last_draw(c);        /* a scratch overflow is resolved against the virtual target */
+	DrawParams P = c->last_draw;
+	const bool drew = c->last_draw_valid != 0;
+	c->color = rcol; c->depth = rdep; c->tile_count = rcount; c->H = rH; c->tiles_y = rty;
+	c->fold_shift = 0; c->in_fold = 0; c->last_draw_valid = 0; c->mirror_synced = 0;
+	if (!rc && keep)
+	{
+		CK(cudaMemcpyAsync(c->color, vcol + off, keep, cudaMemcpyDeviceToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->depth, vdep + off, keep, cudaMemcpyDeviceToDevice, c->stream));
+	}
+	if (!rc && drew)
+	{
+		/* row H-1: every aliased raster row of every primitive, in submission order */
+		P.color = c->color; P.depth = c->depth; P.peer_color = nullptr; P.H = c->H;
+		P.ytop = (int32_t)((int64_t)d->vh - 1 + 2 * (int64_t)d->vy);
+		P.clear.flags = 0;
+		if (P.fs_kind == SWFS_JIT) P.fs_kind = SWFS_GENERIC;      /* the interpreter: its op list is uploaded with every generic draw */
+		int x_lo = d->vx > 0 ? d->vx : 0;
+		int64_t xh = (int64_t)d->vx + (int64_t)d->vw;
+		int x_hi = xh < (int64_t)c->W ? (int)xh : (int)c->W;
+		if (x_hi > x_lo)
+		{
+			const dim3 grid(((uint32_t)(x_hi - x_lo) + 127u) / 128u);
+			if (P.fs_kind == SWFS_VARYING) k_fold_row<SWFS_VARYING><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
+			else if (P.fs_kind == SWFS_TEXTURE) k_fold_row<SWFS_TEXTURE><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
+			else k_fold_row<SWFS_GENERIC><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
+			c->n_launches++;
+		}
+		c->draws_folded++;
+	}
+	cudaFreeAsync(vcol, c->stream); cudaFreeAsync(vdep, c->stream); cudaFreeAsync(vcount, c->stream);
+	CK(cudaGetLastError());
+	return rc ? -1 : 0;
 }
 
 int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t msg_len)
@@ -2817,6 +3010,7 @@ int64_t swgldev_get_option(swgldev_ctx* c, const char* name)
 	if (!strcmp(name, "device")) return c->device;
 	if (!strcmp(name, "device_count")) return c->n_group;
 	if (!strcmp(name, "draws_refused")) return (int64_t)c->draws_refused;
+	if (!strcmp(name, "draws_folded")) return (int64_t)c->draws_folded;
 	if (!strcmp(name, "kernel_launches_all_devices"))
 	{
 		int64_t n = 0;

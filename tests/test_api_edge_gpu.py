@@ -335,3 +335,35 @@ def test_respecify_that_moves_the_storage_reaches_every_vertex_array_sharing_it(
     assert api.swglGetLastError().decode() == ""
     want = restatement.render(big, count=len(v0))[0]
     assert np.array_equal(col, want)
+
+
+@pytest.mark.parametrize("viewport", [(0, -40, W, H), (0, 30, W, H), (-10, -25, W + 20, H + 60), (13, -7, 150, 300)],
+                         ids=["below", "above", "both", "narrow_tall"])
+@pytest.mark.parametrize("kind", ["colour_alpha_nearclip", "textured_mesh", "generic_shader"])
+def test_viewport_that_leaves_the_framebuffer_rows_folds_onto_the_last_row(gpu_api, reference, viewport, kind):
+    """swgl.c:3386: raster rows whose storage row would fall outside the framebuffer all land on row Height-1,
+    in (primitive, y) order.  The library renders the rows inside through the ordinary kernels (into a virtual
+    framebuffer) and row Height-1 with k_fold_row; the frame must be the reference's, bit for bit."""
+    if kind == "colour_alpha_nearclip":
+        scene = S.random_triangles(400, W, H, seed=21, near_cross=True, alpha=None, centre_range=1.2)
+    elif kind == "textured_mesh":
+        scene = S.grid_mesh(20, W, H, textured=True)
+    else:
+        scene = S.random_triangles(300, W, H, seed=22, alpha=None)
+        scene.fs = ("in vec4 vCol;\nuniform vec4 tint;\nout vec4 FragColor;\nvoid main()\n{\n"
+                    "FragColor = vCol * tint + vec4(0.1, 0.0, 0.2, 0.0);\n}\n")
+        scene.uniforms = {"tint": ("4f", [0.9, 0.7, 0.8, 0.6])}
+
+    def script(api):
+        st = G.setup_scene(api, scene, indexed=False, init=False)
+        api.glViewport(0, 0, W, H)
+        api.glClear(3)
+        api.glViewport(*viewport)
+        api.glClear(G.GL_DEPTH_BUFFER_BIT)           # partial: viewport ∩ framebuffer, rows not flipped
+        api.glDrawArrays(G.GL_TRIANGLES, 0, st["n_draw"])
+        api.glDrawArrays(G.GL_TRIANGLES, 3, st["n_draw"] - 3)     # a second draw blends over the folded row again
+    a, b = _both(gpu_api, reference, script)
+    assert gpu_api.swglGetOption(b"draws_folded") == 2 and gpu_api.swglGetOption(b"draws_refused") == 0
+    _assert_same(a, b, 100)
+    # the last row really collects fragments of several raster rows
+    assert int((b[1][H - 1].view(np.uint32) != 0).sum()) > 0
