@@ -152,9 +152,11 @@ void  swglHostFree(void* p);
  * read-only: "wt_draws", "mirror_synced", "kernel_launches", "stage_ns_0".."stage_ns_2" (vertex, setup+bin, raster),
  * "stage_draws", "tile_size", "last_tile_rows", "device", "device_count", "last_vs_kind" / "last_fs_kind" (shape of the last
  * draw as launched: 0 interpreter, 1 / 2 built-in shapes, 3 run-time compiled), "jit_compiles", "jit_cache_hits",
- * "jit_compile_us_total", "draws_refused" (draws skipped because the viewport leaves the framebuffer rows: the reference
- * folds the rows outside onto row Height-1, swgl.c:3386, this library reports it through swglGetLastError and draws
- * nothing), "overflow_pool_entries", "pairs_bytes", "bin_cap". */
+ * "jit_compile_us_total", "draws_folded" (draws whose viewport leaves the framebuffer rows: the reference folds the raster
+ * rows outside onto row Height-1, swgl.c:3386; drawn identically here, through a slower two-part path), "draws_refused"
+ * (such draws in configurations that cannot fold -- sort-first ranks, device groups, assembled targets, a virtual
+ * framebuffer beyond 8184 rows: nothing is drawn and swglGetLastError says so), "overflow_pool_entries", "pairs_bytes",
+ * "bin_cap". */
 void swglSetOption(const char* name, int64_t value);
 int64_t swglGetOption(const char* name);
 
