@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 #if WT_FIRST_TURN_FAST
 				/* the first fragment of each pixel group sees the depth it was tested against above (nothing has
 				 * written the pixel since): its test is decided, no reload, no late shading */
+				__syncwarp();                /* the early depth reads of the later fragments of a group come first */
 				if (pending && my_turn == 0u)
 				{
 					if (shaded_early)
