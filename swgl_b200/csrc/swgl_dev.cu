@@ -48,6 +48,9 @@
 #ifndef SWGL_BIN_TALL_CTAS_PER_SM
 #define SWGL_BIN_TALL_CTAS_PER_SM 8   /* a warp handles its band entries one after the other, three dependent loads each: many warps, few entries per warp */
 #endif
+#ifndef SWGL_SETUP_PIPELINED_FROM_RANKS
+#define SWGL_SETUP_PIPELINED_FROM_RANKS 4
+#endif
 #define SWGL_MAX_HOT_TILES 64       /* tiles whose list may exceed K and continue in the overflow pool */
 
 /* ========================================================================================
@@ -188,6 +191,7 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_setup_pipelined;             /* -1 (default): by the number of sort-first ranks; 0 / 1 pin the set-up kernel's form */
 	int opt_overflow_pool;               /* 1 (default): lists longer than K continue in the overflow pool; 0: K grows for every tile */
 	int opt_tile_rows;                   /* warp rasteriser: 8, 4 or 2 rows per tile; 0 = chosen per draw (th_shift_of) */
 	uint32_t cur_th_shift;               /* of the draw being issued (list capacity is per tile of that size) */
@@ -821,17 +825,20 @@ __device__ __forceinline__ void tri_clip(const DrawParams& P, uint32_t t, uint32
  * pipeline: while group g is set up and binned, the vertices of group g+1 and the indices of group g+2 are in
  * flight.  Launched with programmatic stream serialisation behind k_vertex: the first indices are requested
  * before the wait, clip[] is only read after it. */
-#ifndef SETUP_PIPELINED
-#define SETUP_PIPELINED 0   /* measured (r02, C4): 36.7 us against 33.6 us for one triangle per thread -- the kernel is not bound by the load chain alone */
-#endif
 #ifndef SETUP_CTAS_PER_SM
 #define SETUP_CTAS_PER_SM 5
 #endif
-__global__ void __launch_bounds__(128, SETUP_PIPELINED ? SETUP_CTAS_PER_SM : 8) k_setup_bin(const __grid_constant__ DrawParams P)
+/* PIPELINED = false: one triangle per thread (the choice on one device: C4 33.6 us against 36.7 us pipelined --
+ * with every warp doing the full work, hiding the first link of the chain costs the occupancy that hides the
+ * other two).  PIPELINED = true: the resident, software-pipelined form, chosen for the ranks of a sort-first group,
+ * where most warps only load their triangles to find that none is theirs. */
+template <bool PIPELINED>
+__global__ void __launch_bounds__(128, PIPELINED ? SETUP_CTAS_PER_SM : 8) k_setup_bin(const __grid_constant__ DrawParams P)
 {
 	__shared__ float4 stage[4][32][4];       /* the warp's primitive records on their way out */
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-#if SETUP_PIPELINED
+	if (PIPELINED)
+	{
 	const uint32_t stride = gridDim.x * blockDim.x;
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	/* whole warps leave together: every shuffle / vote below is warp-wide */
@@ -855,13 +862,15 @@ __global__ void __launch_bounds__(128, SETUP_PIPELINED ? SETUP_CTAS_PER_SM : 8) 
 		a0 = b0; a1 = b1; a2 = b2;
 		b0 = c0; b1 = c1; b2 = c2;
 	}
-#else
+	}
+	else
+	{
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	float4 p0, p1, p2;
 	uint32_t s0 = 0, s1 = 0, s2 = 0;
 	if (t < P.ntri) tri_vertices<true>(P, t, p0, p1, p2, s0, s1, s2);
 	setup_group(P, stage, t, lane, wid, p0, p1, p2, s0, s1, s2);
-#endif
+	}
 }
 
 /* The tile's list length; the cursor is re-armed (zeroed) for the next draw.  Whole CTA calls it. */
@@ -1428,10 +1437,11 @@ static uint32_t th_shift_of(const swgldev_ctx* c, int path)
 	/* measured (tools/tile_rows_probe.py, r02): C1 (640x480, 1 200 tiles of 8 rows) 79.6 us with 8 rows, 73.5 with 4,
 	 * 85.3 with 2 (band entries and list insertions of its tall triangles grow faster than the raster kernel
 	 * shrinks); C2 (8 100 tiles) 51.8 / 56.7 / 141.7.  So: 4 rows below one resident wave of 8-row tiles, never 2
-	 * unless asked for. */
-	const uint32_t ranks = c->n_ranks ? c->n_ranks : 1u;
-	const size_t tiles8 = (size_t)c->tiles_x * ((c->H + 7u) >> 3) / ranks;
-	if (tiles8 < 148u * 32u && ((c->H + 3u) >> 2) <= 1023u) return 2u;
+	 * unless asked for.
+	 * The share of one rank of a sort-first group is a different matter: 4 050 tiles per rank of C4 at N = 8 take
+	 * 31.7 us with 8 rows and 32.8 with 4 (tools/stripe_probe.py): ranks keep 8 rows. */
+	const size_t tiles8 = (size_t)c->tiles_x * ((c->H + 7u) >> 3);
+	if (c->n_ranks <= 1 && tiles8 < 148u * 32u && ((c->H + 3u) >> 2) <= 1023u) return 2u;
 	return WT_H_SHIFT;
 }
 
@@ -1474,7 +1484,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = -1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -2327,15 +2337,15 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
 		uint32_t groups = (P.ntri + 127u) / 128u;
-#if SETUP_PIPELINED
-		if (groups > 148u * SETUP_CTAS_PER_SM) groups = 148u * SETUP_CTAS_PER_SM;     /* one resident wave, the threads stride over the stream */
-#endif
+		const bool pipelined = c->opt_setup_pipelined == 1 || (c->opt_setup_pipelined < 0 && P.n_ranks >= SWGL_SETUP_PIPELINED_FROM_RANKS);
+		if (pipelined && groups > 148u * SETUP_CTAS_PER_SM) groups = 148u * SETUP_CTAS_PER_SM;     /* one resident wave, the threads stride over the stream */
 		cfg.gridDim = dim3(groups ? groups : 1u); cfg.blockDim = dim3(128); cfg.stream = c->stream;
 		cudaLaunchAttribute at[1];
 		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		at[0].val.programmaticStreamSerializationAllowed = timing ? 0 : 1;
 		cfg.attrs = at; cfg.numAttrs = 1;
-		CK(cudaLaunchKernelEx(&cfg, k_setup_bin, P));
+		if (pipelined) CK(cudaLaunchKernelEx(&cfg, k_setup_bin<true>, P));
+		else CK(cudaLaunchKernelEx(&cfg, k_setup_bin<false>, P));
 	}
 	if (!P.inline_tall) k_bin_tall<<<148 * SWGL_BIN_TALL_CTAS_PER_SM, 256, 0, c->stream>>>(P);
 	STAGE(2);
@@ -2942,6 +2952,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "jit")) c->opt_jit = value ? 1 : 0;
 	else if (!strcmp(name, "tile_rows")) c->opt_tile_rows = (int)value;
 	else if (!strcmp(name, "overflow_pool")) c->opt_overflow_pool = value ? 1 : 0;
+	else if (!strcmp(name, "setup_pipelined")) c->opt_setup_pipelined = (int)value;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
