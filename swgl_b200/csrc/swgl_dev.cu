@@ -48,9 +48,6 @@
 #ifndef SWGL_BIN_TALL_CTAS_PER_SM
 #define SWGL_BIN_TALL_CTAS_PER_SM 8   /* a warp handles its band entries one after the other, three dependent loads each: many warps, few entries per warp */
 #endif
-#ifndef SWGL_SETUP_PIPELINED_FROM_RANKS
-#define SWGL_SETUP_PIPELINED_FROM_RANKS 4
-#endif
 #define SWGL_MAX_HOT_TILES 64       /* tiles whose list may exceed K and continue in the overflow pool */
 
 /* ========================================================================================
@@ -191,7 +188,7 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
-	int opt_setup_pipelined;             /* -1 (default): by the number of sort-first ranks; 0 / 1 pin the set-up kernel's form */
+	int opt_setup_pipelined;             /* 1: the software-pipelined set-up kernel (measured slower everywhere, kept as an option) */
 	int opt_overflow_pool;               /* 1 (default): lists longer than K continue in the overflow pool; 0: K grows for every tile */
 	int opt_tile_rows;                   /* warp rasteriser: 8, 4 or 2 rows per tile; 0 = chosen per draw (th_shift_of) */
 	uint32_t cur_th_shift;               /* of the draw being issued (list capacity is per tile of that size) */
@@ -828,10 +825,11 @@ __device__ __forceinline__ void tri_clip(const DrawParams& P, uint32_t t, uint32
 #ifndef SETUP_CTAS_PER_SM
 #define SETUP_CTAS_PER_SM 5
 #endif
-/* PIPELINED = false: one triangle per thread (the choice on one device: C4 33.6 us against 36.7 us pipelined --
- * with every warp doing the full work, hiding the first link of the chain costs the occupancy that hides the
- * other two).  PIPELINED = true: the resident, software-pipelined form, chosen for the ranks of a sort-first group,
- * where most warps only load their triangles to find that none is theirs. */
+/* PIPELINED = false: one triangle per thread, the form every draw uses.  PIPELINED = true: the resident,
+ * software-pipelined form, kept behind the "setup_pipelined" option as a measured alternative: C4 on one device
+ * 36.7 us against 33.6 us, and for the share of one rank of 8 / 4 / 2 (most warps only load their triangles to
+ * find that none is theirs) 23.6 / 26.4 / 33.7 us against 19.6 / 21.4 / 25.4 us (tools/stripe_probe.py) -- hiding
+ * the first link of the chain costs the occupancy that hides the other two. */
 template <bool PIPELINED>
 __global__ void __launch_bounds__(128, PIPELINED ? SETUP_CTAS_PER_SM : 8) k_setup_bin(const __grid_constant__ DrawParams P)
 {
@@ -1484,7 +1482,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = -1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = 0; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -2337,7 +2335,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
 		uint32_t groups = (P.ntri + 127u) / 128u;
-		const bool pipelined = c->opt_setup_pipelined == 1 || (c->opt_setup_pipelined < 0 && P.n_ranks >= SWGL_SETUP_PIPELINED_FROM_RANKS);
+		const bool pipelined = c->opt_setup_pipelined == 1;
 		if (pipelined && groups > 148u * SETUP_CTAS_PER_SM) groups = 148u * SETUP_CTAS_PER_SM;     /* one resident wave, the threads stride over the stream */
 		cfg.gridDim = dim3(groups ? groups : 1u); cfg.blockDim = dim3(128); cfg.stream = c->stream;
 		cudaLaunchAttribute at[1];
