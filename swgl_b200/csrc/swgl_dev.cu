@@ -2424,6 +2424,9 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 	}
 	/* the per-triangle LOD lives in the generic fragment path: a texture-shaped shader takes it too */
 	if (P.mip_lod && P.fs_kind == SWFS_TEXTURE) P.fs_kind = SWFS_GENERIC;
+	/* the built-in fragment shapes fetch a vec4 varying with 128-bit loads (swgl_host.c lays the records out for
+	 * that); a caller of this layer that packs them differently gets the IR path */
+	if (P.fs_kind == SWFS_VARYING && ((P.nvf | P.fs_slot) & 3u)) P.fs_kind = SWFS_GENERIC;
 	if (d->vs_image) memcpy(P.vs_image, d->vs_image, 4u * d->vs_words);
 	if (d->fs_image) memcpy(P.fs_image, d->fs_image, 4u * d->fs_words);
 	P.count_fragments = (uint32_t)c->opt_count_fragments;
@@ -2507,6 +2510,12 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	P.inline_tall = (rpath == 3 && small_triangle_draw(c, ntri)) ? 1u : 0u;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;
+	/* the raster kernel addresses the varying of a built-in shape with 32-bit float offsets */
+	if (((uint64_t)P.n_shade + 2ull * ntri + 1ull) * (uint64_t)(P.nvf ? P.nvf : 1u) + 16ull >= (1ull << 32))
+	{
+		set_err(c, "draw skipped: varying records of more than 2^32 floats", cudaSuccess);
+		return flush_clear(c);
+	}
 
 	/* scratch */
 	const size_t n_prims = 2ull * ntri;

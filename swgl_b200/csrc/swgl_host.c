@@ -800,6 +800,7 @@ static int assemble_draw(GLenum mode, GLint first, GLsizei count, int indexed, u
 		if (fi->type != vo->type) continue;
 		int n = vec_floats(fi->type);
 		if (n == 0) continue; /* int varyings interpolate to an unspecified value in the reference */
+		if (n == 4) slot = (slot + 3u) & ~3u;   /* vec4 varyings on 16-byte boundaries of the packed record: 128-bit loads */
 		if (d.n_varying >= 8 || slot + (uint32_t)n > SWGL_MAX_VARYING_FLOATS) { set_error("glDraw*: too many varyings"); return 0; }
 		swgldev_varying* v = &d.varying[d.n_varying++];
 		v->vs_word = vo->word; v->fs_word = fi->word; v->n_floats = (uint32_t)n; v->slot = slot;
@@ -811,6 +812,7 @@ static int assemble_draw(GLenum mode, GLint first, GLsizei count, int indexed, u
 		}
 		else vs_fast = 0;
 	}
+	for (uint32_t k = 0; k < d.n_varying; k++) if (d.varying[k].n_floats == 4) { slot = (slot + 3u) & ~3u; break; }   /* ... of every record */
 	d.varying_floats = slot;
 
 	/* vertex shape */

@@ -66,6 +66,11 @@ struct WarpShared
 	WarpTile<TH> w[WT_WARPS];
 };
 
+/* lane masks from the special registers: one instruction where the compiler re-derives (1 << lane) - 1 from the
+ * thread index on every use to save a register */
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint32_t lanemask_le() { uint32_t m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
+
 /* ascending sort of one value per lane (padding 0xffffffff sinks to the top lanes) */
 __device__ __forceinline__ uint32_t warp_sort32(uint32_t x, uint32_t lane)
 {
@@ -189,8 +194,10 @@ __device__ __noinline__ float4 weights_slow_entry(const DrawParams& P, uint32_t 
 /* Shading of a fragment that failed the depth test before the ordered part and passes in it (an
  * earlier fragment of the same step stored exactly 0.0 = "empty"): rare, kept out of the hot loop. */
 template <int FS>
-__device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, float px, float py)
+__device__ __noinline__ float4 shade_late(const DrawParams& P, uint32_t pid, int tile_x0, int band_last_y, uint32_t pix)
 {
+	/* the pixel's coordinates are worked out here, not by the caller: the hot loop only passes what it has */
+	const float px = (float)(tile_x0 + (int)(pix & (SWGL_TILE - 1))), py = (float)(band_last_y - (int)(pix >> SWGL_TILE_SHIFT));
 	const Prim qv = load_prim(P, pid);
 	const Prim* q = &qv;
 	BaryConst k;
@@ -292,8 +299,6 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	const bool tile_fast = fabsf(P.fvx) < 16777216.0f && P.xlimit < 16777216.0f;
 	const int t_lo = max(max((int)P.fvx, 0), tile_x0);
 	const int t_hi = min(min((int)ceilf(P.xlimit), (int)P.W), tile_x0 + SWGL_TILE);
-	/* packed vec4 varying records can be fetched with 128-bit loads */
-	const bool vary_vec4 = ((P.nvf | P.fs_slot) & 3u) == 0 && (((uintptr_t)P.vary) & 15u) == 0;
 	if (n_list > 0)
 	{
 		/* ---- ascending primitive id = submission order ---- */
@@ -394,7 +399,12 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				{
 					row0 = (uint32_t)(band_last_y - y_in);
 					fast = prim_fast_ok(a, b, c) ? 1u : 0u;
-					prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane * PC_VEC4]);
+					/* built-in shapes: the three words are the float offsets of the consumed varying in the packed
+					 * records (the host has checked that they fit 32 bits); IR shaders get the record ids */
+					if (FS == SWFS_VARYING || FS == SWFS_TEXTURE)
+						prim_consts(a, b, c, q.vid0 * P.nvf + P.fs_slot, q.vid1 * P.nvf + P.fs_slot, q.vid2 * P.nvf + P.fs_slot, pid, &T.pc[lane * PC_VEC4]);
+					else
+						prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane * PC_VEC4]);
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				const bool active = t < total;
 				/* the span of fragment t: the last one that starts at or before it */
 				const uint32_t starts = T.u.b.start_bits[t0 >> 5];
-				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & (0xffffffffu >> (31u - lane))) - 1u];
+				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & lanemask_le()) - 1u];
 				spans_before += (uint32_t)__popc(starts);
 				const float4* pc = &T.pc[((e >> 21) & 31u) * PC_VEC4];
 				const uint32_t tpix = (e + t) & 0x1fffu;         /* pixel of the tile: row * 32 + column */
@@ -552,18 +562,14 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 						if (FS != SWFS_GENERIC && FS != SWFS_JIT)
 						{
 							const float4 ids = pc[5];
-							const float* pa = P.vary + (size_t)__float_as_uint(ids.x) * P.nvf + P.fs_slot;
-							const float* pb = P.vary + (size_t)__float_as_uint(ids.y) * P.nvf + P.fs_slot;
-							const float* pv = P.vary + (size_t)__float_as_uint(ids.z) * P.nvf + P.fs_slot;
+							const float* pa = P.vary + __float_as_uint(ids.x);
+							const float* pb = P.vary + __float_as_uint(ids.y);
+							const float* pv = P.vary + __float_as_uint(ids.z);
 							if (FS == SWFS_VARYING)
 							{
-								if (vary_vec4) { va = __ldg((const float4*)pa); vb = __ldg((const float4*)pb); vc = __ldg((const float4*)pv); }
-								else
-								{
-									va = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
-									vb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
-									vc = make_float4(__ldg(pv), __ldg(pv + 1), __ldg(pv + 2), __ldg(pv + 3));
-								}
+								/* the host lays vec4 varyings out on 16-byte boundaries (the device layer demotes the draw to
+								 * the IR path otherwise): three 128-bit loads, no per-component alternative in the loop */
+								va = __ldg((const float4*)pa); vb = __ldg((const float4*)pb); vc = __ldg((const float4*)pv);
 							}
 							else
 							{
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					}
 				}
 				/* ---- ordered commit ---- */
-				const uint32_t my_turn = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+				const uint32_t my_turn = (uint32_t)__popc(peers & lanemask_lt());
 				const uint32_t turns = __reduce_max_sync(0xffffffffu, my_turn);
 #if WT_FIRST_TURN_FAST
 				/* the first fragment of each pixel group sees the depth it was tested against above (nothing has
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 							T.depth[pix] = z;
 							n_shaded++;
 							if (!shaded_early)
-								col = shade_late<FS>(P, __float_as_uint(pc[5].w), (float)(tile_x0 + (int)(pix & (SWGL_TILE - 1))), (float)(band_last_y - (int)(pix >> SWGL_TILE_SHIFT)));
+								col = shade_late<FS>(P, __float_as_uint(pc[5].w), tile_x0, band_last_y, pix);
 							T.color[pix] = blend_pack_lut(col.x, col.y, col.z, col.w, T.color[pix], S.lut);
 							dirty = true;
 						}
