@@ -48,7 +48,8 @@ void swglGetStats(swglStats* out);
 void swglSetDevice(int ordinal);
 
 /* Number of CUDA devices the NEXT glInit drives from the calling thread (default 1): ordinals d .. d+n-1 with d
- * the swglSetDevice ordinal (default 0).  The frame is sharded sort-first by tile-row bands, buffers and textures
+ * the swglSetDevice ordinal; with the default start (0) and fewer devices than are visible, every (visible / n)-th
+ * device in PCI bus order instead (neighbouring GPUs of a board share their path to host memory).  The frame is sharded sort-first by tile-row bands, buffers and textures
  * are replicated (swglBufferRespecify splits the transfer over the devices' PCIe links and completes it over
  * NVLink), and glGetFramePtr returns one pinned frame every device has written its bands into.  The
  * reference-compatible entry points need no other change.  Not available in this mode: swglFrameSubmit,
