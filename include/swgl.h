@@ -16,8 +16,13 @@
  *     GL_TEXTURE7 so every existing enumerator keeps its value.
  *   - glDrawElements is a new entry point (the reference has no indexed draw).  It is
  *     defined as "glDrawArrays over the de-indexed vertex stream".
- * Further extensions (depth readback, sync, statistics, multi-GPU stripes) are in
- * swgl_b200.h.
+ * Further extensions (depth readback, sync, statistics, multi-GPU) are in swgl_b200.h.
+ *
+ * Limits the reference does not have (a draw outside them is skipped and swglGetLastError() says why):
+ * framebuffers up to 65 504 x 8 184 pixels (2 047 tile columns, 1 023 tile rows), 2^30 triangles per draw,
+ * 16 varying floats per vertex.  A viewport that leaves the framebuffer rows is drawn like the reference
+ * draws it (rows outside fold onto the last row, swgl.c:3386) on a single device; sort-first ranks and
+ * device groups skip such draws.
  */
 #ifndef SOFTWARE_GL_H
 #define SOFTWARE_GL_H
