@@ -26,6 +26,9 @@
 #ifndef WT_FIRST_TURN_FAST
 #define WT_FIRST_TURN_FAST 1
 #endif
+#ifndef WT_PREFETCH_LEAN
+#define WT_PREFETCH_LEAN 1
+#endif
 #ifndef WT_MAGIC_I2F
 #define WT_MAGIC_I2F 0   /* measured: no gain (tools/ab_bench.sh, r02) */
 #endif
@@ -220,28 +223,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	constexpr int TH = 1 << THS;                 /* tile rows */
 	__shared__ WarpShared<TH> S;
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
-	__syncthreads();            /* the only block-level barrier */
-
 	/* the grid covers the tile rows this rank owns: owned row i -> tile row (sort-first bands of
 	 * band_rows x 32 framebuffer rows dealt round-robin, see owns_tile_row) */
 	const uint32_t tx = blockIdx.x * WT_WARPS + wid;     /* grid: (tile columns / WT_WARPS, owned tile rows) */
-	if (tx >= P.tiles_x) return;
 	uint32_t ty = blockIdx.y;
+	bool mine = tx < P.tiles_x;
 	if (P.n_ranks > 1)
 	{
 		const uint32_t per = P.band_rows << (5u - THS);      /* tile rows per ownership group */
 		ty = ((ty / per) * P.n_ranks + P.rank) * per + ty % per;
-		if (ty >= P.tiles_y || !owns_tile_row(P, ty)) return;
+		mine = mine && ty < P.tiles_y && owns_tile_row(P, ty);
 	}
 	const uint32_t tile = ty * P.tiles_x + tx;
+	/* the list length is requested first: its round trip runs under the table load and the barrier */
+	uint32_t n_raw = 0;
+	if (lane == 0 && mine) n_raw = *(volatile const uint32_t*)(P.tile_count + tile);
+	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
+	__syncthreads();            /* the only block-level barrier */
+	if (!mine) return;
 	WarpTile<TH>& T = S.w[wid];
 
-	/* list length; the cursor is re-armed for the next draw */
-	uint32_t n_raw = 0;
+	/* the cursor is re-armed for the next draw */
 	if (lane == 0)
 	{
-		n_raw = P.tile_count[tile];
 		if (n_raw) P.tile_count[tile] = 0u;
 		if (n_raw > P.bin_cap) atomicMax(&P.ctr->max_list, n_raw);
 		if (n_raw && P.count_fragments && (n_raw <= P.bin_cap || P.ov_cap)) atomicAdd(&P.ctr->pair_total, (unsigned long long)n_raw);
@@ -513,6 +517,14 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
 					asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)q + 32));
 				}
+#if WT_PREFETCH_LEAN
+				else if (nxt != 0xffffffffu && P.ibo)
+				{
+					/* record-less primitive: the first link of its gather chain (element indices -> vertices) */
+					const uint32_t* ix = P.ibo + ((unsigned long long)(long long)P.first + 3u * (nxt >> 2));
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(ix));
+				}
+#endif
 			}
 
 			/* ---- phase B: lane = fragment, dense steps of 32 in submission order ---- */
