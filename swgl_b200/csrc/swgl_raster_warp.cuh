@@ -27,7 +27,10 @@
 #define WT_FIRST_TURN_FAST 1
 #endif
 #ifndef WT_PREFETCH_LEAN
-#define WT_PREFETCH_LEAN 1
+#define WT_PREFETCH_LEAN 0   /* measured: prefetching the element indices of the next batch's record-less primitives 142.3 -> 144.3 us */
+#endif
+#ifndef WT_LUT
+#define WT_LUT 0             /* 1: byte / 255 through a shared-memory table (round 1); 0: arithmetically (byte_over_255) */
 #endif
 #ifndef WT_MAGIC_I2F
 #define WT_MAGIC_I2F 0   /* measured: no gain (tools/ab_bench.sh, r02) */
@@ -36,6 +39,11 @@
  * choice whenever the framebuffer has at least one resident wave of such tiles (148 SMs x 32 warps); smaller
  * framebuffers -- or the share of one rank of a sort-first group -- get shorter tiles, i.e. more and shorter
  * warps, because a tile is one warp's serial work and the slowest warp sets the kernel's time. */
+#if WT_LUT
+#define WT_BLEND(col, cur) blend_pack_lut((col).x, (col).y, (col).z, (col).w, (cur), S.lut)
+#else
+#define WT_BLEND(col, cur) blend_pack_arith((col).x, (col).y, (col).z, (col).w, (cur))
+#endif
 #define WT_H_SHIFT  3        /* the default tile height (and the only one of run-time compiled kernels) */
 #define WT_H_SHIFT_MIN 1
 #define WT_WARPS    4        /* tiles per CTA */
@@ -59,13 +67,15 @@ struct WarpTile
 			uint32_t start_bits[WT_MAX_FRAGS / 32];  /* bit f: fragment f is the first of a span */
 		} b;
 	} u;
-	float4   pc[32 * WT_PC_WORDS / 4];       /* [primitive lane][6]: constants staged by phase A */
+	float4   pc[PC_VEC4 * PC_STRIDE];        /* [field][primitive lane]: constants staged by phase A (prim_consts) */
 };
 
 template <int TH>
 struct WarpShared
 {
+#if WT_LUT
 	float    lut[256];             /* byte / 255.0f (swgl.c:3434-3437) */
+#endif
 	WarpTile<TH> w[WT_WARPS];
 };
 
@@ -238,8 +248,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 	/* the list length is requested first: its round trip runs under the table load and the barrier */
 	uint32_t n_raw = 0;
 	if (lane == 0 && mine) n_raw = *(volatile const uint32_t*)(P.tile_count + tile);
+#if WT_LUT
 	for (uint32_t i = threadIdx.x; i < 256; i += WT_WARPS * 32) S.lut[i] = __ldg(P.lut255 + i);
 	__syncthreads();            /* the only block-level barrier */
+#endif
 	if (!mine) return;
 	WarpTile<TH>& T = S.w[wid];
 
@@ -406,9 +418,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					/* built-in shapes: the three words are the float offsets of the consumed varying in the packed
 					 * records (the host has checked that they fit 32 bits); IR shaders get the record ids */
 					if (FS == SWFS_VARYING || FS == SWFS_TEXTURE)
-						prim_consts(a, b, c, q.vid0 * P.nvf + P.fs_slot, q.vid1 * P.nvf + P.fs_slot, q.vid2 * P.nvf + P.fs_slot, pid, &T.pc[lane * PC_VEC4]);
+						prim_consts(a, b, c, q.vid0 * P.nvf + P.fs_slot, q.vid1 * P.nvf + P.fs_slot, q.vid2 * P.nvf + P.fs_slot, pid, &T.pc[lane]);
 					else
-						prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane * PC_VEC4]);
+						prim_consts(a, b, c, q.vid0, q.vid1, q.vid2, pid, &T.pc[lane]);
 					float x0, x1, s1;
 					bool switched;
 					walk_to_row(P, w, band, ty, y_in, x0, x1, s1, switched);
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 				const uint32_t starts = T.u.b.start_bits[t0 >> 5];
 				const uint32_t e = T.u.b.span[spans_before + (uint32_t)__popc(starts & lanemask_le()) - 1u];
 				spans_before += (uint32_t)__popc(starts);
-				const float4* pc = &T.pc[((e >> 21) & 31u) * PC_VEC4];
+				const float4* pc = &T.pc[(e >> 21) & 31u];
 				const uint32_t tpix = (e + t) & 0x1fffu;         /* pixel of the tile: row * 32 + column */
 				const uint32_t r = tpix >> SWGL_TILE_SHIFT, lx = tpix & (SWGL_TILE - 1u);
 				const uint32_t pix = active ? tpix : (0x80000000u | lane);
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 #endif
 					if (!(frag_weights_fast(pc, px, py, u, v, w, z) && ((e >> 26) & 1u)))
 					{
-						const float4 s4 = weights_slow_entry(P, __float_as_uint(pc[5].w), px, py);
+						const float4 s4 = weights_slow_entry(P, __float_as_uint(pc[5 * PC_STRIDE].w), px, py);
 						u = s4.x; v = s4.y; w = s4.z; z = s4.w;
 					}
 					/* the fragment shader does not read the framebuffer: run it before the ordered
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 						float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va, vc = va;
 						if (FS != SWFS_GENERIC && FS != SWFS_JIT)
 						{
-							const float4 ids = pc[5];
+							const float4 ids = pc[5 * PC_STRIDE];
 							const float* pa = P.vary + __float_as_uint(ids.x);
 							const float* pb = P.vary + __float_as_uint(ids.y);
 							const float* pv = P.vary + __float_as_uint(ids.z);
@@ -597,7 +609,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 							col = sample_nearest(P.tex[P.fs_tex_unit], va.x * u + vb.x * v + vc.x * w, va.y * u + vb.y * v + vc.y * w);
 						else
 						{
-							const float4 ids = pc[5];
+							const float4 ids = pc[5 * PC_STRIDE];
 							FragIn fi;
 							fi.u = u; fi.v = v; fi.w = w;
 							fi.vid0 = __float_as_uint(ids.x); fi.vid1 = __float_as_uint(ids.y); fi.vid2 = __float_as_uint(ids.z);
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 					{
 						T.depth[pix] = z;
 						n_shaded++;
-						T.color[pix] = blend_pack_lut(col.x, col.y, col.z, col.w, T.color[pix], S.lut);
+						T.color[pix] = WT_BLEND(col, T.color[pix]);
 						dirty = true;
 					}
 					pending = false;
@@ -644,8 +656,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 8) k_raster_warp(const __grid_c
 							T.depth[pix] = z;
 							n_shaded++;
 							if (!shaded_early)
-								col = shade_late<FS>(P, __float_as_uint(pc[5].w), tile_x0, band_last_y, pix);
-							T.color[pix] = blend_pack_lut(col.x, col.y, col.z, col.w, T.color[pix], S.lut);
+								col = shade_late<FS>(P, __float_as_uint(pc[5 * PC_STRIDE].w), tile_x0, band_last_y, pix);
+							T.color[pix] = WT_BLEND(col, T.color[pix]);
 							dirty = true;
 						}
 						pending = false;
