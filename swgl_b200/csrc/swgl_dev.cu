@@ -188,6 +188,7 @@ struct swgldev_ctx
 
 	/* options */
 	int opt_fuse_clear, opt_count_fragments, opt_raster_path, opt_stage_timing, opt_diag, opt_host_mirror, opt_lean_prims;
+	int opt_setup_big;                   /* 1 (default): draws of big triangles are set up by a warp per triangle (k_setup_big) */
 	int opt_setup_pipelined;             /* 1: the software-pipelined set-up kernel (measured slower everywhere, kept as an option) */
 	int opt_overflow_pool;               /* 1 (default): lists longer than K continue in the overflow pool; 0: K grows for every tile */
 	int opt_tile_rows;                   /* warp rasteriser: 8, 4 or 2 rows per tile; 0 = chosen per draw (th_shift_of) */
@@ -931,6 +932,121 @@ __global__ void __launch_bounds__(256) k_bin_tall(const __grid_constant__ DrawPa
 	}
 }
 
+/* ---- set-up of a draw of BIG triangles (inline_tall = 0, e.g. BASELINE config 1): one WARP per input triangle.
+ * A tall primitive crosses dozens of tile rows; with a thread per triangle each thread walked them one after the
+ * other (and a second kernel, k_bin_tall, then worked through the band entries), on a grid of a few CTAs.  Here
+ * lane b takes tile row b of the primitive: it replays the two float recurrences from the primitive's first row
+ * to its own (the additions are the reference's, in its order, swgl.c:3356-3361, 3466-3471 -- only nobody waits
+ * for anybody), stores the band entry the rasteriser starts from, walks the rows of its band for the columns the
+ * spans touch and inserts the primitive into those tiles.  Near-clipped triangles (rare) keep the serial path on
+ * lane 0; their band entries are the only ones k_bin_tall still has to look at. ---- */
+__global__ void __launch_bounds__(256) k_setup_big(const __grid_constant__ DrawParams P)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (t >= P.ntri) return;
+	float4 p0, p1, p2;
+	uint32_t s0, s1, s2;
+	tri_vertices<true>(P, t, p0, p1, p2, s0, s1, s2);        /* every lane the same addresses: broadcast loads */
+	const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
+	if (in_mask != 7u)
+	{
+		if (in_mask != 0u && lane == 0)
+		{
+			const float2 zz = make_float2(0.0f, 0.0f);
+			const float2 c0 = (s0 < P.n_shade) ? P.clip_xy[s0] : zz, c1 = (s1 < P.n_shade) ? P.clip_xy[s1] : zz, c2 = (s2 < P.n_shade) ? P.clip_xy[s2] : zz;
+			const float4 p[3] = { make_float4(c0.x, c0.y, p0.z, p0.w), make_float4(c1.x, c1.y, p1.z, p1.w), make_float4(c2.x, c2.y, p2.z, p2.w) };
+			const uint32_t sid[3] = { s0, s1, s2 };
+			const uint32_t live = setup_clipped(P, t, p, sid, in_mask);
+			if (live) atomicAdd(&P.ctr->prims_out, live);
+		}
+		return;
+	}
+	TriSorted ts;
+	if (!tri_rows(p0, p1, p2, P, ts)) return;
+	const uint32_t tr_hi = (uint32_t)(P.ytop - ts.ys) >> P.th_shift;
+	const uint32_t tr_lo = (uint32_t)(P.ytop - (ts.ye - 1)) >> P.th_shift;
+	if (P.n_ranks > 1)
+	{
+		bool mine = false;
+		for (uint32_t tr = tr_lo; tr <= tr_hi && !mine; tr++) mine = owns_tile_row(P, tr);
+		if (!mine) return;
+	}
+	const uint32_t pid = 2u * t;
+	const float xmin = fminf(fminf(p0.x, p1.x), p2.x), xmax = fmaxf(fmaxf(p0.x, p1.x), p2.x);
+	const bool narrow = xmin >= -32768.0f && xmax <= 32768.0f && xmax - xmin <= 64.0f;
+	if (lane == 0) atomicAdd(&P.ctr->prims_out, 1u);
+	if (ts.ye - ts.ys <= (2 << P.th_shift) && narrow)
+	{
+		/* short and narrow: binned by the x extent of its vertices, like in k_setup_bin */
+		const bool has_record = !P.lean_prims || s0 >= P.n_shade || s1 >= P.n_shade || s2 >= P.n_shade;
+		const uint32_t entry = (pid << 1) | (has_record ? 1u : 0u);
+		if (has_record && lane < 4u)
+		{
+			float4* out = (float4*)prim_at(P, pid);
+			out[lane] = lane == 0 ? p0 : lane == 1 ? p1 : lane == 2 ? p2
+			          : make_float4(__uint_as_float(s0), __uint_as_float(s1), __uint_as_float(s2), __uint_as_float(0xffffffffu));
+		}
+		const int lo = max((int)xmin - 1, max((int)P.fvx, 0));
+		const int hi = min((int)xmax + 1, min((int)ceilf(P.xlimit), (int)P.W) - 1);
+		if (lo > hi || (P.diag & 1u)) return;
+		const uint32_t c0 = (uint32_t)lo >> SWGL_TILE_SHIFT, nc = ((uint32_t)hi >> SWGL_TILE_SHIFT) - c0 + 1u;
+		const uint32_t rows = tr_hi - tr_lo + 1u;           /* at most 3 */
+		for (uint32_t j = lane; j < rows * nc; j += 32)
+		{
+			const uint32_t tr = tr_hi - j / nc;
+			if (owns_tile_row(P, tr)) bin_insert(P, tr * P.tiles_x + c0 + j % nc, entry);
+		}
+		return;
+	}
+	/* tall or wide: a band entry per tile row */
+	const uint32_t nb = tr_hi - tr_lo + 1u;
+	uint32_t band = 0;
+	if (lane == 0) band = atomicAdd(&P.ctr->band_cursor, nb);
+	band = __shfl_sync(0xffffffffu, band, 0);
+	if ((unsigned long long)band + nb > (unsigned long long)P.cap_bands) { if (lane == 0) atomicOr(&P.ctr->overflow, 2u); return; }
+	const uint32_t entry = (pid << 1) | 1u;
+	if (lane < 4u)
+	{
+		float4* out = (float4*)prim_at(P, pid);
+		out[lane] = lane == 0 ? p0 : lane == 1 ? p1 : lane == 2 ? p2
+		          : make_float4(__uint_as_float(s0), __uint_as_float(s1), __uint_as_float(s2), __uint_as_float(band));
+	}
+	TriWalk w;
+	tri_slopes(ts, w);
+	const int th = 1 << P.th_shift;
+	for (uint32_t b = lane; b < nb; b += 32)
+	{
+		const uint32_t tr = tr_hi - b;
+		const int band_last_y = P.ytop - (int)(tr << P.th_shift);
+		const int y_in = max(w.ys, band_last_y - (th - 1)), y_out = min(w.ye - 1, band_last_y);
+		float x0 = w.c0x, x1 = w.c0x, sl = w.s1;
+		bool switched = false;
+		for (int y = w.ys; y < y_in; y++)
+		{
+			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; sl = w.s2; x1 = w.c1x; }
+			x0 += w.s0; x1 += sl;
+		}
+		BandEntry e;
+		e.x0 = x0; e.x1 = x1; e.prim = entry; e.cols = 0xffffffffu;      /* inserted right here: nothing left for k_bin_tall */
+		P.bands[band + b] = e;
+		if (!owns_tile_row(P, tr) || (P.diag & 1u)) continue;
+		int cmin = 0x7fffffff, cmax = -1;
+		for (int y = y_in; y <= y_out; y++)
+		{
+			int xa, xb;
+			row_span(x0, x1, P, xa, xb);
+			if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
+			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; sl = w.s2; x1 = w.c1x; }
+			x0 += w.s0; x1 += sl;
+		}
+		if (cmax < 0) continue;
+		const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
+		for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);
+	}
+}
+
+
 /* ---- per-tile rasteriser, pixel-owner form ----
  * CTA = one 32x32 tile, 256 threads; thread t owns the 4x1 strip (row t/8, columns 4*(t%8)..+3)
  * and keeps its colour words and depths in registers for the whole list, so the tile is
@@ -1482,7 +1598,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->tile_count = nullptr; c->winner = nullptr; c->ctr = nullptr; c->h_ctr = nullptr; c->ctr_event = nullptr;
 	c->ctr_pending = 0; c->last_draw_valid = 0; c->last_raster_path = 0;
 	c->opt_fuse_clear = 1; c->opt_count_fragments = 1; c->opt_raster_path = 0; c->opt_stage_timing = 0; c->opt_diag = 0; c->opt_bin_limit = (size_t)6 << 30;
-	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = 0; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
+	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = 0; c->opt_setup_big = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
 	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
@@ -2357,7 +2473,13 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		at[0].val.programmaticStreamSerializationAllowed = timing ? 0 : 1;
 		cfg.attrs = at; cfg.numAttrs = 1;
-		if (pipelined) CK(cudaLaunchKernelEx(&cfg, k_setup_bin<true>, P));
+		if (!P.inline_tall && c->opt_setup_big)
+		{
+			/* a draw of big triangles: a warp per triangle (k_setup_big) */
+			cfg.gridDim = dim3((P.ntri + 7u) / 8u); cfg.blockDim = dim3(256);
+			CK(cudaLaunchKernelEx(&cfg, k_setup_big, P));
+		}
+		else if (pipelined) CK(cudaLaunchKernelEx(&cfg, k_setup_bin<true>, P));
 		else CK(cudaLaunchKernelEx(&cfg, k_setup_bin<false>, P));
 	}
 	if (!P.inline_tall) k_bin_tall<<<148 * SWGL_BIN_TALL_CTAS_PER_SM, 256, 0, c->stream>>>(P);
@@ -2975,6 +3097,7 @@ void swgldev_set_option(swgldev_ctx* c, const char* name, int64_t value)
 	else if (!strcmp(name, "tile_rows")) c->opt_tile_rows = (int)value;
 	else if (!strcmp(name, "overflow_pool")) c->opt_overflow_pool = value ? 1 : 0;
 	else if (!strcmp(name, "setup_pipelined")) c->opt_setup_pipelined = (int)value;
+	else if (!strcmp(name, "setup_big")) c->opt_setup_big = value ? 1 : 0;
 	else if (!strcmp(name, "host_mirror")) { c->opt_host_mirror = (int)value; c->mirror_synced = 0; }
 	else if (!strcmp(name, "bin_limit_bytes") && value > 0) c->opt_bin_limit = (size_t)value;
 	else if (!strcmp(name, "bin_cap") && value > 0)
