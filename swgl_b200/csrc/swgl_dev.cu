@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(256) k_bin_tall(const __grid_constant__ DrawPa
  * to its own (the additions are the reference's, in its order, swgl.c:3356-3361, 3466-3471 -- only nobody waits
  * for anybody), stores the band entry the rasteriser starts from, walks the rows of its band for the columns the
  * spans touch and inserts the primitive into those tiles.  Near-clipped triangles (rare) keep the serial path on
- * lane 0; their band entries are the only ones k_bin_tall still has to look at. ---- */
+ * lane 0, which inserts as it walks (inline_tall): k_bin_tall is not launched for these draws. ---- */
 __global__ void __launch_bounds__(256) k_setup_big(const __grid_constant__ DrawParams P)
 {
 	const uint32_t lane = threadIdx.x & 31u;
@@ -1042,7 +1042,21 @@ __global__ void __launch_bounds__(256) k_setup_big(const __grid_constant__ DrawP
 		}
 		if (cmax < 0) continue;
 		const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
-		for (uint32_t cx = c0; cx <= c1; cx++) bin_insert(P, tr * P.tiles_x + cx, entry);
+		/* eight list cursors in flight at a time: one at a time the lane would wait out a round trip per tile */
+		for (uint32_t cb = c0; cb <= c1; cb += 8u)
+		{
+			uint32_t slot[8];
+#pragma unroll
+			for (uint32_t k = 0; k < 8u; k++) if (cb + k <= c1) slot[k] = atomicAdd(&P.tile_count[tr * P.tiles_x + cb + k], 1u);
+#pragma unroll
+			for (uint32_t k = 0; k < 8u; k++)
+				if (cb + k <= c1)
+				{
+					const uint32_t tile = tr * P.tiles_x + cb + k;
+					if (slot[k] < P.bin_cap) P.pairs[(size_t)tile * P.bin_cap + slot[k]] = entry;
+					else bin_overflow(P, tile, entry, slot[k]);
+				}
+		}
 	}
 }
 
@@ -2473,7 +2487,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		at[0].val.programmaticStreamSerializationAllowed = timing ? 0 : 1;
 		cfg.attrs = at; cfg.numAttrs = 1;
-		if (!P.inline_tall && c->opt_setup_big)
+		if (P.setup_big)
 		{
 			/* a draw of big triangles: a warp per triangle (k_setup_big) */
 			cfg.gridDim = dim3((P.ntri + 7u) / 8u); cfg.blockDim = dim3(256);
@@ -2645,6 +2659,10 @@ int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 	apply_jit(c, d, P, rpath == 3 && P.th_shift == WT_H_SHIFT);
 	P.lean_prims = (c->opt_lean_prims && rpath == 3) ? 1u : 0u;
 	P.inline_tall = (rpath == 3 && small_triangle_draw(c, ntri)) ? 1u : 0u;
+	/* draws of big triangles: a warp per triangle sets them up and inserts them (k_setup_big); the serial walk that is
+	 * left for near-clipped ones inserts inline, so there is nothing for k_bin_tall */
+	P.setup_big = (!P.inline_tall && c->opt_setup_big) ? 1u : 0u;
+	if (P.setup_big) P.inline_tall = 1u;
 	P.n_shade = d->ibo ? d->n_vertices : 3u * ntri;
 	P.clip_vid_base = P.n_shade;
 	/* the raster kernel addresses the varying of a built-in shape with 32-bit float offsets */

@@ -118,6 +118,7 @@ struct DrawParams
 	uint32_t* hot_store; uint32_t hot_cap;
 	uint32_t lean_prims;        /* short unclipped primitives have no record (warp rasteriser draws) */
 	uint32_t inline_tall;       /* tall primitives are inserted by the set-up kernel itself (no k_bin_tall launch) */
+	uint32_t setup_big;         /* host side: the draw is set up by k_setup_big (a warp per triangle) */
 	Counters* ctr;
 	const float* lut255;        /* byte / 255.0f (swgl.c:2116, 3434-3437), computed once on the device */
 	uint32_t* winner;           /* GL_POINTS: per-pixel index+1 of the last point submitted to it (0 = none) */
