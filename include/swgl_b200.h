@@ -147,6 +147,9 @@ void  swglHostFree(void* p);
  * reference does -- its level of detail goes through an rsqrt() with undefined behaviour, swgl.c:3240-3246; 1: the
  * chain is sampled with the per-triangle level the same code gives with a 32-bit pun, bit-identical to the reference
  * built that way, oracle/ref_shim.c);
+ * "setup_big" (1 default: draws of big triangles -- more than 64 pixels per triangle on average -- are set up by a warp per
+ * triangle; 0: a thread per triangle plus a second kernel for the tall ones), "setup_pipelined" (0 default; 1: the
+ * software-pipelined form of the set-up kernel, measured slower);
  * "tile_rows" (0 default: 8 rows per tile, 4 when the context owns less than one resident wave of 8-row tiles; 8 / 4 /
  * 2 pin it); "overflow_pool" (1 default: tile lists longer than bin_cap continue in a shared overflow pool; 0: bin_cap
  * grows for every tile instead);
