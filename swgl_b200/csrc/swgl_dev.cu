@@ -1015,30 +1015,52 @@ __global__ void __launch_bounds__(256) k_setup_big(const __grid_constant__ DrawP
 	TriWalk w;
 	tri_slopes(ts, w);
 	const int th = 1 << P.th_shift;
+	/* The state on entering row y is c0x (+) s0, (y - ys) times, and for the second edge c0x (+) s1 up to the switch
+	 * row, c1x (+) s2 after it (the switch happens after the first row y with (float)y + 1 >= c1y has been drawn,
+	 * swgl.c:3466-3471).  The additions are replayed one by one in loops that carry nothing else (two independent
+	 * 4-cycle chains), split at the switch row; a lane's next band (32 tile rows on) continues from where its
+	 * previous one started instead of from the primitive's first row. */
+	const int c1yi = (w.c1y >= 2147483648.0f) ? 0x7fffffff : (w.c1y <= -2147483648.0f) ? (int)0x80000000 : (int)w.c1y;
+	const int ysw = (c1yi <= w.ys) ? w.ys : c1yi - 1;            /* row after which the switch happens */
+	float x0 = w.c0x, x1 = w.c0x, sl = w.s1;
+	bool switched = false;
+	int y_at = w.ys;                                             /* (x0, x1, sl, switched) is the state on entering y_at */
 	for (uint32_t b = lane; b < nb; b += 32)
 	{
 		const uint32_t tr = tr_hi - b;
 		const int band_last_y = P.ytop - (int)(tr << P.th_shift);
 		const int y_in = max(w.ys, band_last_y - (th - 1)), y_out = min(w.ye - 1, band_last_y);
-		float x0 = w.c0x, x1 = w.c0x, sl = w.s1;
-		bool switched = false;
-		for (int y = w.ys; y < y_in; y++)
 		{
-			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; sl = w.s2; x1 = w.c1x; }
-			x0 += w.s0; x1 += sl;
+			int n = y_in - y_at;
+			if (!switched && ysw >= y_at && ysw < y_in)
+			{
+				for (int i = ysw - y_at; i > 0; i--) { x0 += w.s0; x1 += sl; }
+				switched = true; sl = w.s2; x1 = w.c1x;
+				x0 += w.s0; x1 += sl;
+				n = y_in - ysw - 1;
+			}
+			for (int i = n; i > 0; i--) { x0 += w.s0; x1 += sl; }
+			y_at = y_in;
 		}
+		const float ex0 = x0, ex1 = x1;
+		const float esl = sl;
+		const bool eswitched = switched;
 		BandEntry e;
-		e.x0 = x0; e.x1 = x1; e.prim = entry; e.cols = 0xffffffffu;      /* inserted right here: nothing left for k_bin_tall */
+		e.x0 = ex0; e.x1 = ex1; e.prim = entry; e.cols = 0xffffffffu;      /* inserted right here: nothing left for k_bin_tall */
 		P.bands[band + b] = e;
 		if (!owns_tile_row(P, tr) || (P.diag & 1u)) continue;
 		int cmin = 0x7fffffff, cmax = -1;
-		for (int y = y_in; y <= y_out; y++)
 		{
-			int xa, xb;
-			row_span(x0, x1, P, xa, xb);
-			if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
-			if (!switched && (float)y + 1.0f >= w.c1y) { switched = true; sl = w.s2; x1 = w.c1x; }
-			x0 += w.s0; x1 += sl;
+			float a0 = ex0, a1 = ex1, as = esl;
+			bool asw = eswitched;
+			for (int y = y_in; y <= y_out; y++)
+			{
+				int xa, xb;
+				row_span(a0, a1, P, xa, xb);
+				if (xa < xb) { cmin = min(cmin, xa); cmax = max(cmax, xb - 1); }
+				if (!asw && (float)y + 1.0f >= w.c1y) { asw = true; as = w.s2; a1 = w.c1x; }
+				a0 += w.s0; a1 += as;
+			}
 		}
 		if (cmax < 0) continue;
 		const uint32_t c0 = (uint32_t)max(cmin, 0) >> SWGL_TILE_SHIFT, c1 = (uint32_t)max(cmax, 0) >> SWGL_TILE_SHIFT;
