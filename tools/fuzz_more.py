@@ -27,6 +27,7 @@ VARIANTS = [{"raster_path": 0}, {"raster_path": 0, "lean_prims": 0}, {"raster_pa
             {"raster_path": 3, "setup_pipelined": 1, "setup_big": 0}]
 bad = 0
 n = 0
+folded = 0
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     sc, rng = _random_scene(seed)
     fill = (int(rng.integers(0, 1 << 32)), float(rng.choice([0.0, 0.5, -1.0])))
@@ -49,7 +50,9 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
         col, dep, stats, err = gpu_render(api, sc, indexed=sc.indices is not None, clear=clear, fill=fill)
         cmp = O.compare(col, dep, fc, fd)
         n += 1
-        if err or cmp["coverage_mismatch"] or cmp["depth_mismatch"] or cmp["color_mismatch"] or api.swglGetOption(b"draws_folded") < 1:
+        outside = sc.viewport[1] < 0 or sc.viewport[1] + sc.viewport[3] > sc.height
+        folded += int(api.swglGetOption(b"draws_folded") >= 1)
+        if err or cmp["coverage_mismatch"] or cmp["depth_mismatch"] or cmp["color_mismatch"] or (outside and api.swglGetOption(b"draws_folded") < 1):
             bad += 1
             print("MISMATCH folded", seed, sc.name, sc.viewport, err, cmp)
-print("seeds", sys.argv[1], sys.argv[2], "renders", n, "mismatches", bad)
+print("seeds", sys.argv[1], sys.argv[2], "renders", n, "of which folded draws", folded, "mismatches", bad)
