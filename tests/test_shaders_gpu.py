@@ -40,6 +40,23 @@ def test_generic_shader_matches_compiled_reference(gpu_api, reference, name, pat
     assert_bit_exact(O.compare(col, dep, fc, fd), name)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shader_matches_compiled_reference(gpu_api, reference, seed):
+    """Random well-typed programs of the executable subset (tests/shader_fuzz_gen.py; many more seeds:
+    tools/shader_fuzz.py, recorded under profiles/): compiled kernels and the interpreter against the reference."""
+    from shader_fuzz_gen import make
+    vs, fs, uniforms = make(seed)
+    scene = S.random_triangles(200, 256, 192, seed=4321 + seed, alpha=None if seed % 2 else 0.6, near_cross=seed % 3 == 0)
+    scene.vs, scene.fs, scene.uniforms = vs, fs, uniforms
+    fc, fd = reference.render(scene)
+    assert int((fd != 0).sum()) > 1000
+    for jit in (1, 0):
+        col, dep, stats, err = gpu_render(gpu_api, scene, options={"raster_path": 3, "jit": jit})
+        assert err == "", err
+        assert (3 in (gpu_api.swglGetOption(b"last_vs_kind"), gpu_api.swglGetOption(b"last_fs_kind"))) == bool(jit)
+        assert_bit_exact(O.compare(col, dep, fc, fd), f"seed {seed} jit {jit}\n{vs}\n{fs}")
+
+
 def test_clamp_wrap_and_rgb_texture(gpu_api, reference):
     """GL_CLAMP addressing, a 3-channel float texture (alpha reads 0), uv outside [0,1]."""
     import ctypes as C
