@@ -2573,6 +2573,11 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 	P.xlimit = (float)(uint32_t)((uint32_t)d->vx + d->vw);
 	P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
 	P.ytop = (int32_t)((int64_t)d->vh - 1 + 2 * (int64_t)d->vy - c->fold_shift);
+	/* A viewport that ends below row 0: the reference's row limit VY + VH wraps around in unsigned arithmetic
+	 * (swgl.c:3344, 3356), so its triangles are walked up to their last row whatever the viewport height, and every
+	 * one of those rows is stored on row Height-1.  The virtual target of draw_folded() only has the viewport's own
+	 * rows: the tile kernels get the limit that was meant, k_fold_row the wrapped one (draw_folded puts it back). */
+	if (c->in_fold && (int64_t)d->vy + (int64_t)d->vh < 0) P.ylimit = (float)((int64_t)d->vy + (int64_t)d->vh);
 	P.rank = c->rank; P.n_ranks = c->n_ranks; P.band_rows = c->band_rows ? c->band_rows : 1;
 	P.vbo = (const uint8_t*)(uintptr_t)d->vbo; P.vbo_bytes = d->vbo_bytes;
 	P.ibo = (const uint32_t*)(uintptr_t)d->ibo; P.ibo_count = d->ibo_bytes / 4u;
@@ -2793,6 +2798,7 @@ static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 		/* row H-1: every aliased raster row of every primitive, in submission order */
 		P.color = c->color; P.depth = c->depth; P.peer_color = nullptr; P.H = c->H;
 		P.ytop = (int32_t)((int64_t)d->vh - 1 + 2 * (int64_t)d->vy);
+		P.ylimit = (float)(uint32_t)((uint32_t)d->vy + d->vh);
 		P.clear.flags = 0;
 		if (P.fs_kind == SWFS_JIT) P.fs_kind = SWFS_GENERIC;      /* the interpreter: its op list is uploaded with every generic draw */
 		int x_lo = d->vx > 0 ? d->vx : 0;

@@ -337,8 +337,9 @@ def test_respecify_that_moves_the_storage_reaches_every_vertex_array_sharing_it(
     assert np.array_equal(col, want)
 
 
-@pytest.mark.parametrize("viewport", [(0, -40, W, H), (0, 30, W, H), (-10, -25, W + 20, H + 60), (13, -7, 150, 300)],
-                         ids=["below", "above", "both", "narrow_tall"])
+@pytest.mark.parametrize("viewport", [(0, -40, W, H), (0, 30, W, H), (-10, -25, W + 20, H + 60), (13, -7, 150, 300),
+                                      (89, -24, 101, 10), (0, H + 8, W, 50)],
+                         ids=["below", "above", "both", "narrow_tall", "entirely_below_row_limit_wraps", "entirely_above"])
 @pytest.mark.parametrize("kind", ["colour_alpha_nearclip", "textured_mesh", "generic_shader"])
 def test_viewport_that_leaves_the_framebuffer_rows_folds_onto_the_last_row(gpu_api, reference, viewport, kind):
     """swgl.c:3386: raster rows whose storage row would fall outside the framebuffer all land on row Height-1,
@@ -364,6 +365,11 @@ def test_viewport_that_leaves_the_framebuffer_rows_folds_onto_the_last_row(gpu_a
         api.glDrawArrays(G.GL_TRIANGLES, 3, st["n_draw"] - 3)     # a second draw blends over the folded row again
     a, b = _both(gpu_api, reference, script)
     assert gpu_api.swglGetOption(b"draws_folded") == 2 and gpu_api.swglGetOption(b"draws_refused") == 0
-    _assert_same(a, b, 100)
-    # the last row really collects fragments of several raster rows
-    assert int((b[1][H - 1].view(np.uint32) != 0).sum()) > 0
+    # (a viewport that ends below row 0: VY + VH wraps in the reference's unsigned arithmetic, swgl.c:3344 / 3356 -- the row
+    # limit is gone, every row of every triangle lands on row Height-1, and the depth clear covers every framebuffer row)
+    outside_all = viewport[1] + viewport[3] <= 0 or viewport[1] >= H
+    _assert_same(a, b, 0 if outside_all else 100)
+    # the last row really collects fragments of several raster rows (the mesh's triangles are less than a row tall in a
+    # 10-row viewport: the reference draws none of them)
+    if not (outside_all and kind == "textured_mesh"):
+        assert int((b[1][H - 1].view(np.uint32) != 0).sum()) > 0

@@ -1,0 +1,23 @@
+"""Many more seeds of tests/test_api_fuzz_gpu.py: random sequences of the reference's API calls issued to
+libswgl_b200.so and to the compiled reference, every frame read on the way and the final colour / depth compared.
+
+    python tools/api_fuzz.py <first> <last>"""
+import sys
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import swgl_b200
+from oracle import pyoracle as O
+import test_api_fuzz_gpu as F
+
+api = swgl_b200.load()
+ref = O.Reference()
+bad = n = draws = folded = 0
+for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+    msg = F.compare_seed(api, ref, seed)
+    n += 1
+    draws += sum(1 for o in F.make_ops(seed) if o[0] == "draw")
+    folded += int(api.swglGetOption(b"draws_folded"))
+    if msg:
+        bad += 1
+        print("MISMATCH", msg)
+print("api sequences", sys.argv[1], sys.argv[2], "run", n, "draw calls", draws, "of which folded", folded, "mismatches", bad,
+      "jit compiles", api.swglGetOption(b"jit_compiles"))
