@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import swgl_b200
 from oracle import pyoracle as O
 from swgl_b200 import gl as G, scenes as S
 
@@ -33,8 +34,9 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def make_ops(seed):
-    """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries)."""
+def make_ops(seed, inside=False):
+    """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries).
+    inside: viewports stay inside the framebuffer rows (device groups and sort-first ranks cannot fold)."""
     rng = np.random.default_rng(31000 + seed)
     arrays = []
     for k in range(int(rng.integers(2, 4))):
@@ -49,7 +51,17 @@ def make_ops(seed):
     ops += [("use", 0), ("vao", 0), ("clear", 3)]
     for _ in range(int(rng.integers(10, 26))):
         r = rng.random()
-        if r < 0.38:
+        if r < 0.04:
+            n = len(arrays[vao])
+            first = int(rng.integers(0, n - 1))
+            ops.append(("points", first, int(rng.integers(0, min(n - first, 60) + 1))))
+        elif r < 0.07:
+            unit = int(rng.integers(0, 2))
+            tex = S.lcg_texture(int(rng.choice([4, 16, 32])), seed=int(rng.integers(1, 99)))
+            ops.append(("teximage", unit, tex if rng.random() < 0.7 else np.ascontiguousarray(tex[:, :, :3])))
+            if rng.random() < 0.4:
+                ops.append(("mipmap", unit))
+        elif r < 0.38:
             n = len(arrays[vao])
             first = int(rng.integers(0, n - 3))
             if rng.random() < 0.8:
@@ -63,9 +75,9 @@ def make_ops(seed):
                 ops.append(("viewport", 0, 0, W, H))
             else:
                 x = int(rng.integers(-24, W // 2)) if rng.random() < 0.3 else int(rng.integers(0, W // 2))
-                y = int(rng.integers(-40, H // 2)) if rng.random() < 0.3 else int(rng.integers(0, H // 2))
+                y = int(rng.integers(-40, H // 2)) if rng.random() < 0.3 and not inside else int(rng.integers(0, H // 2))
                 w = int(rng.integers(8, W - max(x, 0) + (24 if rng.random() < 0.3 else 0) + 1))
-                h = int(rng.integers(8, H - max(y, 0) + (48 if rng.random() < 0.3 else 0) + 1))
+                h = int(rng.integers(8, H - max(y, 0) + (48 if rng.random() < 0.3 and not inside else 0) + 1))
                 ops.append(("viewport", x, y, w, h))
         elif r < 0.60:
             ops.append(("clearcolor",) + tuple(float(v) for v in rng.uniform(-0.2, 1.2, 4)))
@@ -90,15 +102,46 @@ def make_ops(seed):
     return ops
 
 
-def run_ops(api, ops, fill, depth_of):
-    """Issue `ops`; -> (frames read on the way + the final one, final depth)."""
+PERTURB = [("host_mirror", (0, 1, 2)), ("fuse_clear", (0, 1)), ("tile_rows", (0, 8, 4, 2)), ("raster_path", (0, 2, 3)),
+           ("lean_prims", (0, 1)), ("setup_big", (0, 1)), ("jit", (0, 1)), ("overflow_pool", (0, 1)), ("bin_cap", (8, 256)),
+           ("count_fragments", (0, 1)), ("finish",), ("stats",), ("submit_wait",), ("rgba8",)]
+
+
+def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
+    """Issue `ops`; -> (frames read on the way + the final one, final depth).
+    perturb: seed of library-only calls slipped in between (options that must not change a bit of the result, waits,
+    statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit."""
+    prng = np.random.default_rng(perturb) if perturb is not None else None
+    # (folding is a feature of the default rasteriser: the CTA cross-check kernel refuses such draws, by design)
+    leaves_rows = any(o[0] == "viewport" and (o[2] < 0 or o[2] + o[4] > H) for o in ops)
+    if devices > 1:
+        api.swglSetDeviceCount(devices)
     api.glInit(W, H)
+    if devices > 1:
+        api.swglSetDeviceCount(1)          # the setting is consumed by glInit: later tests get one device again
     fill(0x0A0B0C0D, 0.0)
     api.glViewport(0, 0, W, H)
     api.glClearColor(0.0, 0.0, 0.0, 1.0)
     frames, progs, vaos, cur = [], [], [], 0
     for op in ops:
         k = op[0]
+        if prng is not None and k != "setup" and prng.random() < 0.35:
+            pk = PERTURB[int(prng.integers(len(PERTURB)))]
+            if pk[0] == "finish":
+                api.swglFinish()
+            elif pk[0] == "stats":
+                st = swgl_b200.swglStats()
+                api.swglGetStats(C.byref(st))
+            elif pk[0] == "submit_wait" and devices == 1:
+                p = api.swglFrameWait(api.swglFrameSubmit())
+                assert bool(p)
+            elif pk[0] == "rgba8":
+                buf = np.empty((H, W, 4), np.uint8)
+                api.swglReadPixelsRGBA8(_ptr(buf))
+            elif len(pk) == 2:
+                v = int(pk[1][int(prng.integers(len(pk[1])))])
+                if not (pk[0] == "raster_path" and v == 2 and leaves_rows):
+                    api.swglSetOption(pk[0].encode(), v)
         if k == "setup":
             for vs, fs in PROGRAMS:
                 v = api.glCreateShader(G.GL_VERTEX_SHADER); api.glShaderSource(v, vs.encode()); api.glCompileShader(v)
@@ -128,6 +171,19 @@ def run_ops(api, ops, fill, depth_of):
                 api.glBindTexture(G.GL_TEXTURE_2D, t.value)
                 tt = np.ascontiguousarray(tex, np.uint8)
                 api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, tt.shape[1], tt.shape[0], 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(tt))
+            # the reference allocates a program's fragment `in` variables when it first shades a TRIANGLE fragment, and its
+            # GL_POINTS path copies into them unconditionally (swgl.c:3548-3551): one certain fragment per program first
+            warm = np.array([[-0.5, -0.5, -1.0, 1.0, 0.2, 0.4, 0.6, 1.0], [0.5, -0.5, -1.0, 1.0, 0.2, 0.4, 0.6, 1.0],
+                             [0.0, 0.5, -1.0, 1.0, 0.2, 0.4, 0.6, 1.0]], np.float32)
+            vao, vbo = C.c_uint32(0), C.c_uint32(0)
+            api.glGenVertexArrays(1, C.byref(vao)); api.glBindVertexArray(vao.value)
+            api.glGenBuffers(1, C.byref(vbo)); api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+            api.glBufferData(G.GL_ARRAY_BUFFER, warm.nbytes, _ptr(warm), G.GL_STATIC_DRAW)
+            api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
+            api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
+            for p in progs:
+                api.glUseProgram(p)
+                api.glDrawArrays(G.GL_TRIANGLES, 0, 3)
         elif k == "use":
             cur = progs[op[1]]
             api.glUseProgram(cur)
@@ -135,6 +191,16 @@ def run_ops(api, ops, fill, depth_of):
             api.glBindVertexArray(vaos[op[1]])
         elif k == "draw":
             api.glDrawArrays(G.GL_TRIANGLES, op[1], op[2])
+        elif k == "points":
+            api.glDrawArrays(G.GL_POINTS, op[1], op[2])
+        elif k == "teximage":
+            api.glActiveTexture(G.GL_TEXTURE0 + op[1])
+            tt = np.ascontiguousarray(op[2], np.uint8)
+            fmt = G.GL_RGBA if tt.shape[2] == 4 else G.GL_RGB
+            api.glTexImage2D(G.GL_TEXTURE_2D, 0, fmt, tt.shape[1], tt.shape[0], 0, fmt, G.GL_UNSIGNED_BYTE, _ptr(tt))
+        elif k == "mipmap":
+            api.glActiveTexture(G.GL_TEXTURE0 + op[1])
+            api.glGenerateMipmap(G.GL_TEXTURE_2D)
         elif k == "viewport":
             api.glViewport(*op[1:])
         elif k == "clearcolor":
@@ -162,11 +228,17 @@ def run_ops(api, ops, fill, depth_of):
     return frames, depth_of()
 
 
-def compare_seed(gpu_api, reference, seed):
+def compare_seed(gpu_api, reference, seed, perturb=False, devices=1):
     """-> '' if the two libraries agree on every frame of the sequence, else a description."""
-    ops = make_ops(seed)
-    gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
-                     lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy())
+    ops = make_ops(seed, inside=devices > 1)
+    try:
+        gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
+                         lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
+                         perturb=5000 + seed if perturb else None, devices=devices)
+    finally:
+        for name, values in [p for p in PERTURB if len(p) == 2]:       # back to the defaults for whoever comes next
+            gpu_api.swglSetOption(name.encode(), {"host_mirror": 1, "fuse_clear": 1, "lean_prims": 1, "setup_big": 1, "jit": 1,
+                                                  "overflow_pool": 1, "bin_cap": 256, "count_fragments": 1}.get(name, 0))
     err = gpu_api.swglGetLastError().decode()
     if err:
         return f"seed {seed}: {err}"
@@ -184,3 +256,17 @@ def compare_seed(gpu_api, reference, seed):
 @pytest.mark.parametrize("seed", range(12))
 def test_random_call_sequence_matches_compiled_reference(gpu_api, reference, seed):
     assert compare_seed(gpu_api, reference, seed) == ""
+
+
+@pytest.mark.parametrize("seed", range(12, 24))
+def test_random_call_sequence_with_library_options_changing_underneath(gpu_api, reference, seed):
+    """The same, with tuning options, waits, statistics and the other read-back calls slipped in between the
+    reference's calls on the library's side: none of them may change a bit of any frame."""
+    assert compare_seed(gpu_api, reference, seed, perturb=True) == ""
+
+
+@pytest.mark.parametrize("seed,devices", [(24, 2), (25, 2), (26, 3), (27, 4)])
+def test_random_call_sequence_on_a_device_group(gpu_api, reference, seed, devices, monkeypatch):
+    """The same through swglSetDeviceCount (members wrap around the visible devices when there are fewer)."""
+    monkeypatch.setenv("SWGL_B200_GROUP_EMULATE", "1")
+    assert compare_seed(gpu_api, reference, seed, perturb=seed % 2 == 0, devices=devices) == ""
