@@ -21,8 +21,8 @@
  * Limits the reference does not have (a draw outside them is skipped and swglGetLastError() says why):
  * framebuffers up to 65 504 x 8 184 pixels (2 047 tile columns, 1 023 tile rows), 2^30 triangles per draw,
  * 16 varying floats per vertex.  A viewport that leaves the framebuffer rows is drawn like the reference
- * draws it (rows outside fold onto the last row, swgl.c:3386) on a single device; sort-first ranks and
- * device groups skip such draws.
+ * draws it (rows outside fold onto the last row, swgl.c:3386) on a single device and on a device group
+ * (swglSetDeviceCount); sort-first ranks of separate processes (swglSetStripe) skip such draws.
  */
 #ifndef SOFTWARE_GL_H
 #define SOFTWARE_GL_H

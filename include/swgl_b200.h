@@ -158,7 +158,7 @@ void  swglHostFree(void* p);
  * draw as launched: 0 interpreter, 1 / 2 built-in shapes, 3 run-time compiled), "jit_compiles", "jit_cache_hits",
  * "jit_compile_us_total", "draws_folded" (draws whose viewport leaves the framebuffer rows: the reference folds the raster
  * rows outside onto row Height-1, swgl.c:3386; drawn identically here, through a slower two-part path), "draws_refused"
- * (such draws in configurations that cannot fold -- sort-first ranks, device groups, assembled targets, a virtual
+ * (such draws in configurations that cannot fold -- sort-first ranks of separate processes, peer / shared-mirror targets, a virtual
  * framebuffer beyond 8184 rows: nothing is drawn and swglGetLastError says so), "overflow_pool_entries", "pairs_bytes",
  * "bin_cap". */
 void swglSetOption(const char* name, int64_t value);

@@ -2624,11 +2624,19 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 }
 
 static int draw_folded(swgldev_ctx* c, const swgldev_draw* d);
+static int group_draw_folded(swgldev_ctx* c, const swgldev_draw* d);
 
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d)
 {
 	if (IS_GROUP(c))
 	{
+		/* a viewport that leaves the framebuffer rows: the fold needs the whole frame on one device */
+		if ((d->vy < 0 || (uint64_t)d->vy + d->vh > c->H) && d->vw <= 0x7fffffffu && d->vh <= 0x7fffffffu && c->tiles_x <= 2047u
+		    && (d->count + 2u) / 3u != 0 && d->vh != 0)
+		{
+			const int rc = group_draw_folded(c, d);
+			if (rc != 1) return rc;
+		}
 		return group_each(c, [&](int i, swgldev_ctx* m)
 		{
 			swgldev_draw di = *d;
@@ -2816,6 +2824,62 @@ static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 	}
 	cudaFreeAsync(vcol, c->stream); cudaFreeAsync(vdep, c->stream); cudaFreeAsync(vcount, c->stream);
 	CK(cudaGetLastError());
+	return rc ? -1 : 0;
+}
+
+/* The same for a device group: the frame is spread over the members in bands, and the fold is one row that collects
+ * fragments of every primitive.  The members' bands are brought together in the leader's attachments (peer copies),
+ * the leader renders the draw alone like a single device does (draw_folded), and every member gets its bands back.
+ * Correct, not fast -- like the single-device fold.  Returns 1 when it cannot be done (the draw is then refused). */
+static int group_draw_folded(swgldev_ctx* c, const swgldev_draw* d)
+{
+	const int n = c->n_group;
+	if (raster_path_for(c, 0) != 3 || c->peer_color) return 1;
+	/* every member: earlier draws finished, its pending clear applied to its own rows */
+	if (group_each(c, [&](int, swgldev_ctx* m)
+	    {
+		    if (settle_last_draw(m) || flush_clear(m)) return -1;
+		    return cudaStreamSynchronize(m->stream) == cudaSuccess ? 0 : -1;
+	    })) { set_err(c, "folded draw on a device group: a member could not be brought to rest", cudaSuccess); return -1; }
+	cudaSetDevice(c->device);
+	const size_t band_px = (size_t)32u * (c->band_rows ? c->band_rows : 1u) * c->W, total = (size_t)c->W * c->H;
+	auto move_bands = [&](bool to_leader) -> int
+	{
+		for (int i = 1; i < n; i++)
+		{
+			swgldev_ctx* m = c->group[i];
+			for (size_t b = (size_t)i; b * band_px < total; b += (size_t)n)
+			{
+				const size_t off = b * band_px, cnt = (off + band_px < total ? band_px : total - off) * 4;
+				if (to_leader)
+				{
+					CK(cudaMemcpyPeerAsync(c->color + off, c->device, m->color + off, m->device, cnt, c->stream));
+					CK(cudaMemcpyPeerAsync(c->depth + off, c->device, m->depth + off, m->device, cnt, c->stream));
+				}
+				else
+				{
+					CK(cudaMemcpyPeerAsync(m->color + off, m->device, c->color + off, c->device, cnt, c->stream));
+					CK(cudaMemcpyPeerAsync(m->depth + off, m->device, c->depth + off, c->device, cnt, c->stream));
+				}
+			}
+		}
+		return 0;
+	};
+	if (move_bands(true)) return -1;
+	/* the leader alone, as a single device that owns every row and keeps no assembled mirror */
+	const uint32_t rank = c->rank, n_ranks = c->n_ranks;
+	uint32_t* const sm = c->shared_mirror; uint32_t* const smd = c->shared_mirror_dev;
+	const int borrowed = c->mirror_borrowed;
+	c->rank = 0; c->n_ranks = 1; c->shared_mirror = nullptr; c->shared_mirror_dev = nullptr; c->mirror_borrowed = 0; c->n_group = 1;
+	int rc = draw_folded(c, d);
+	if (!rc) rc = settle_last_draw(c);
+	c->rank = rank; c->n_ranks = n_ranks; c->shared_mirror = sm; c->shared_mirror_dev = smd; c->mirror_borrowed = borrowed; c->n_group = n;
+	if (rc == 1) return 1;
+	if (!rc) rc = move_bands(false);
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = -1;
+	/* the members' bands of the assembled mirror are out of date: their next read-back copies them */
+	for (int i = 0; i < n; i++) c->group[i]->mirror_synced = 0;
+	if (rc) set_err(c, "folded draw on a device group failed", cudaGetLastError());
 	return rc ? -1 : 0;
 }
 

@@ -36,7 +36,7 @@ def _ptr(a):
 
 def make_ops(seed, inside=False):
     """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries).
-    inside: viewports stay inside the framebuffer rows (device groups and sort-first ranks cannot fold)."""
+    inside: viewports stay inside the framebuffer rows (sort-first ranks of separate processes cannot fold)."""
     rng = np.random.default_rng(31000 + seed)
     arrays = []
     for k in range(int(rng.integers(2, 4))):
@@ -230,7 +230,7 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
 
 def compare_seed(gpu_api, reference, seed, perturb=False, devices=1):
     """-> '' if the two libraries agree on every frame of the sequence, else a description."""
-    ops = make_ops(seed, inside=devices > 1)
+    ops = make_ops(seed)
     try:
         gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
                          lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
@@ -265,8 +265,9 @@ def test_random_call_sequence_with_library_options_changing_underneath(gpu_api, 
     assert compare_seed(gpu_api, reference, seed, perturb=True) == ""
 
 
-@pytest.mark.parametrize("seed,devices", [(24, 2), (25, 2), (26, 3), (27, 4)])
+@pytest.mark.parametrize("seed,devices", [(24, 2), (25, 2), (26, 3), (27, 4), (239, 2), (635, 3)])
 def test_random_call_sequence_on_a_device_group(gpu_api, reference, seed, devices, monkeypatch):
-    """The same through swglSetDeviceCount (members wrap around the visible devices when there are fewer)."""
+    """The same through swglSetDeviceCount (members wrap around the visible devices when there are fewer); viewports that
+    leave the framebuffer rows are folded on the leader with every member's bands gathered there (group_draw_folded)."""
     monkeypatch.setenv("SWGL_B200_GROUP_EMULATE", "1")
     assert compare_seed(gpu_api, reference, seed, perturb=seed % 2 == 0, devices=devices) == ""

@@ -22,7 +22,7 @@ bad = n = draws = folded = 0
 for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     msg = F.compare_seed(api, ref, seed, perturb=perturb, devices=devices)
     n += 1
-    draws += sum(1 for o in F.make_ops(seed, inside=devices > 1) if o[0] in ("draw", "points"))
+    draws += sum(1 for o in F.make_ops(seed) if o[0] in ("draw", "points"))
     folded += int(api.swglGetOption(b"draws_folded"))
     if msg:
         bad += 1
