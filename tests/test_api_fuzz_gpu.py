@@ -44,15 +44,22 @@ def make_ops(seed, inside=False):
                                 extent=float(rng.choice([0.08, 0.25, 0.6, 1.3])),
                                 alpha=None if rng.random() < 0.5 else float(rng.choice([1.0, 0.5, 0.15])),
                                 near_cross=bool(rng.random() < 0.4), centre_range=float(rng.choice([0.8, 1.0, 1.3])))
-        arrays.append(np.ascontiguousarray(sc.vertices, np.float32))
+        if rng.random() < 0.3:
+            # an indexed mesh: the library draws it with glDrawElements, the reference (which has no indexed draw) draws
+            # the de-indexed stream -- "glDrawArrays over the de-indexed vertex stream" is the definition of the extension
+            sc = S.grid_mesh(int(rng.integers(3, 28)), W, H, seed=int(rng.integers(1, 1 << 30)), alpha=float(rng.choice([1.0, 0.5])),
+                             layers=int(rng.integers(1, 3)))
+            arrays.append((np.ascontiguousarray(sc.vertices, np.float32), np.ascontiguousarray(sc.indices, np.uint32)))
+            continue
+        arrays.append((np.ascontiguousarray(sc.vertices, np.float32), None))
     textures = [S.checker_texture(int(rng.choice([8, 32]))), S.lcg_texture(int(rng.choice([16, 64])), seed=int(rng.integers(1, 99)))]
     ops = [("setup", arrays, textures)]
     prog, vao = 0, 0
     ops += [("use", 0), ("vao", 0), ("clear", 3)]
     for _ in range(int(rng.integers(10, 26))):
         r = rng.random()
-        if r < 0.04:
-            n = len(arrays[vao])
+        if r < 0.04 and arrays[vao][1] is None:
+            n = len(arrays[vao][0])
             first = int(rng.integers(0, n - 1))
             ops.append(("points", first, int(rng.integers(0, min(n - first, 60) + 1))))
         elif r < 0.07:
@@ -62,7 +69,7 @@ def make_ops(seed, inside=False):
             if rng.random() < 0.4:
                 ops.append(("mipmap", unit))
         elif r < 0.38:
-            n = len(arrays[vao])
+            n = len(arrays[vao][0]) if arrays[vao][1] is None else len(arrays[vao][1])
             first = int(rng.integers(0, n - 3))
             if rng.random() < 0.8:
                 first -= first % 3
@@ -107,10 +114,11 @@ PERTURB = [("host_mirror", (0, 1, 2)), ("fuse_clear", (0, 1)), ("tile_rows", (0,
            ("count_fragments", (0, 1)), ("finish",), ("stats",), ("submit_wait",), ("rgba8",)]
 
 
-def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
+def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
     """Issue `ops`; -> (frames read on the way + the final one, final depth).
     perturb: seed of library-only calls slipped in between (options that must not change a bit of the result, waits,
-    statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit."""
+    statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit;
+    indexed: the library has glDrawElements (otherwise indexed arrays are drawn as their de-indexed stream)."""
     prng = np.random.default_rng(perturb) if perturb is not None else None
     # (folding is a feature of the default rasteriser: the CTA cross-check kernel refuses such draws, by design)
     leaves_rows = any(o[0] == "viewport" and (o[2] < 0 or o[2] + o[4] > H) for o in ops)
@@ -122,7 +130,7 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
     fill(0x0A0B0C0D, 0.0)
     api.glViewport(0, 0, W, H)
     api.glClearColor(0.0, 0.0, 0.0, 1.0)
-    frames, progs, vaos, cur = [], [], [], 0
+    frames, progs, vaos, cur, has_ebo, cur_vao = [], [], [], 0, [], 0
     for op in ops:
         k = op[0]
         if prng is not None and k != "setup" and prng.random() < 0.35:
@@ -156,14 +164,20 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
                     loc = api.glGetUniformLocation(p, name)
                     if loc >= 0:
                         setter(loc)
-            for verts in op[1]:
-                vao, vbo = C.c_uint32(0), C.c_uint32(0)
+            for verts, idx in op[1]:
+                if idx is not None and not indexed:
+                    verts = np.ascontiguousarray(verts[idx])
+                vao, vbo, ebo = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
                 api.glGenVertexArrays(1, C.byref(vao)); api.glBindVertexArray(vao.value)
                 api.glGenBuffers(1, C.byref(vbo)); api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
                 api.glBufferData(G.GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), G.GL_STATIC_DRAW)
                 api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
                 api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
+                if idx is not None and indexed:
+                    api.glGenBuffers(1, C.byref(ebo)); api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, ebo.value)
+                    api.glBufferData(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), G.GL_STATIC_DRAW)
                 vaos.append(vao.value)
+                has_ebo.append(idx is not None and indexed)
             for unit, tex in enumerate(op[2]):
                 t = C.c_uint32(0)
                 api.glGenTextures(1, C.byref(t))
@@ -188,9 +202,13 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1):
             cur = progs[op[1]]
             api.glUseProgram(cur)
         elif k == "vao":
-            api.glBindVertexArray(vaos[op[1]])
+            cur_vao = op[1]
+            api.glBindVertexArray(vaos[cur_vao])
         elif k == "draw":
-            api.glDrawArrays(G.GL_TRIANGLES, op[1], op[2])
+            if has_ebo[cur_vao]:
+                api.glDrawElements(G.GL_TRIANGLES, op[2], G.GL_UNSIGNED_INT, C.c_void_p(4 * op[1]))
+            else:
+                api.glDrawArrays(G.GL_TRIANGLES, op[1], op[2])
         elif k == "points":
             api.glDrawArrays(G.GL_POINTS, op[1], op[2])
         elif k == "teximage":
@@ -234,7 +252,7 @@ def compare_seed(gpu_api, reference, seed, perturb=False, devices=1):
     try:
         gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
                          lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
-                         perturb=5000 + seed if perturb else None, devices=devices)
+                         perturb=5000 + seed if perturb else None, devices=devices, indexed=True)
     finally:
         for name, values in [p for p in PERTURB if len(p) == 2]:       # back to the defaults for whoever comes next
             gpu_api.swglSetOption(name.encode(), {"host_mirror": 1, "fuse_clear": 1, "lean_prims": 1, "setup_big": 1, "jit": 1,
