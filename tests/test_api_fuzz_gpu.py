@@ -16,7 +16,7 @@ from swgl_b200 import gl as G, scenes as S
 
 pytestmark = pytest.mark.gpu
 
-W, H = 200, 152
+SIZES = [(200, 152), (200, 152), (97, 75), (333, 211), (256, 64), (130, 300)]
 
 VS_COLOUR = S.VS_PASSTHROUGH
 FS_COLOUR = S.FS_COLOR
@@ -38,8 +38,9 @@ def make_ops(seed, inside=False):
     """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries).
     inside: viewports stay inside the framebuffer rows (sort-first ranks of separate processes cannot fold)."""
     rng = np.random.default_rng(31000 + seed)
-    arrays = []
-    for k in range(int(rng.integers(2, 4))):
+    W, H = SIZES[int(rng.integers(len(SIZES)))] if seed >= 12 else SIZES[0]      # odd sizes: partial tiles, unaligned rows
+
+    def new_array():
         sc = S.random_triangles(int(rng.integers(40, 260)), W, H, seed=int(rng.integers(1, 1 << 30)),
                                 extent=float(rng.choice([0.08, 0.25, 0.6, 1.3])),
                                 alpha=None if rng.random() < 0.5 else float(rng.choice([1.0, 0.5, 0.15])),
@@ -49,16 +50,27 @@ def make_ops(seed, inside=False):
             # the de-indexed stream -- "glDrawArrays over the de-indexed vertex stream" is the definition of the extension
             sc = S.grid_mesh(int(rng.integers(3, 28)), W, H, seed=int(rng.integers(1, 1 << 30)), alpha=float(rng.choice([1.0, 0.5])),
                              layers=int(rng.integers(1, 3)))
-            arrays.append((np.ascontiguousarray(sc.vertices, np.float32), np.ascontiguousarray(sc.indices, np.uint32)))
-            continue
-        arrays.append((np.ascontiguousarray(sc.vertices, np.float32), None))
+            return (np.ascontiguousarray(sc.vertices, np.float32), np.ascontiguousarray(sc.indices, np.uint32))
+        return (np.ascontiguousarray(sc.vertices, np.float32), None)
+
+    arrays = [new_array() for _ in range(int(rng.integers(2, 4)))]
     textures = [S.checker_texture(int(rng.choice([8, 32]))), S.lcg_texture(int(rng.choice([16, 64])), seed=int(rng.integers(1, 99)))]
-    ops = [("setup", arrays, textures)]
+    ops = [("setup", list(arrays), textures, W, H)]
     prog, vao = 0, 0
     ops += [("use", 0), ("vao", 0), ("clear", 3)]
     for _ in range(int(rng.integers(10, 26))):
         r = rng.random()
-        if r < 0.04 and arrays[vao][1] is None:
+        if rng.random() < 0.06:
+            # new contents for a vertex array's buffers (the streaming client of bench.py's end-to-end step): the library
+            # re-specifies in place (swglBufferRespecify, the reference ignores re-specification, swgl.c:3140), the
+            # reference gets a fresh vertex array -- same geometry from here on either way
+            vao = int(rng.integers(len(arrays)))
+            new = new_array()
+            if (new[1] is None) != (arrays[vao][1] is None):          # keep the array's kind (indexed or not)
+                new = (new[0], None) if arrays[vao][1] is None else (arrays[vao][0], arrays[vao][1][: 3 * int(rng.integers(1, len(arrays[vao][1]) // 3 + 1))].copy())
+            arrays[vao] = new
+            ops.append(("respecify", vao, new))
+        elif r < 0.04 and arrays[vao][1] is None:
             n = len(arrays[vao][0])
             first = int(rng.integers(0, n - 1))
             ops.append(("points", first, int(rng.integers(0, min(n - first, 60) + 1))))
@@ -70,7 +82,7 @@ def make_ops(seed, inside=False):
                 ops.append(("mipmap", unit))
         elif r < 0.38:
             n = len(arrays[vao][0]) if arrays[vao][1] is None else len(arrays[vao][1])
-            first = int(rng.integers(0, n - 3))
+            first = int(rng.integers(0, max(n - 2, 1)))
             if rng.random() < 0.8:
                 first -= first % 3
             count = int(rng.integers(0, n - first + 1))
@@ -114,11 +126,13 @@ PERTURB = [("host_mirror", (0, 1, 2)), ("fuse_clear", (0, 1)), ("tile_rows", (0,
            ("count_fragments", (0, 1)), ("finish",), ("stats",), ("submit_wait",), ("rgba8",)]
 
 
-def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
+def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
     """Issue `ops`; -> (frames read on the way + the final one, final depth).
     perturb: seed of library-only calls slipped in between (options that must not change a bit of the result, waits,
     statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit;
-    indexed: the library has glDrawElements (otherwise indexed arrays are drawn as their de-indexed stream)."""
+    ours: the library has glDrawElements and swglBufferRespecify (the reference draws an indexed array as its
+    de-indexed stream and gets a fresh vertex array where the library re-specifies one)."""
+    W, H = ops[0][3], ops[0][4]
     prng = np.random.default_rng(perturb) if perturb is not None else None
     # (folding is a feature of the default rasteriser: the CTA cross-check kernel refuses such draws, by design)
     leaves_rows = any(o[0] == "viewport" and (o[2] < 0 or o[2] + o[4] > H) for o in ops)
@@ -130,7 +144,28 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
     fill(0x0A0B0C0D, 0.0)
     api.glViewport(0, 0, W, H)
     api.glClearColor(0.0, 0.0, 0.0, 1.0)
-    frames, progs, vaos, cur, has_ebo, cur_vao = [], [], [], 0, [], 0
+    frames, progs, vaos, cur, has_ebo, cur_vao, names = [], [], [], 0, [], 0, []
+
+    def make_array(j, verts, idx):
+        """vertex array j from scratch: named buffers that own the data (specified with no vertex array bound, swgl.c:3123-3126),
+        then bound into a new vertex array (which snapshots their fields, 3116-3122)"""
+        if idx is not None and not ours:
+            verts = np.ascontiguousarray(verts[idx])
+        vao, vbo, ebo = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        api.glBindVertexArray(0)
+        api.glGenBuffers(1, C.byref(vbo)); api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+        api.glBufferData(G.GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), G.GL_STATIC_DRAW)
+        if idx is not None and ours:
+            api.glGenBuffers(1, C.byref(ebo)); api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, ebo.value)
+            api.glBufferData(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), G.GL_STATIC_DRAW)
+        api.glGenVertexArrays(1, C.byref(vao)); api.glBindVertexArray(vao.value)
+        api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+        api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
+        api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
+        if ebo.value:
+            api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, ebo.value)
+        vaos[j], names[j], has_ebo[j] = vao.value, (vbo.value, ebo.value), bool(ebo.value)
+
     for op in ops:
         k = op[0]
         if prng is not None and k != "setup" and prng.random() < 0.35:
@@ -165,19 +200,8 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
                     if loc >= 0:
                         setter(loc)
             for verts, idx in op[1]:
-                if idx is not None and not indexed:
-                    verts = np.ascontiguousarray(verts[idx])
-                vao, vbo, ebo = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
-                api.glGenVertexArrays(1, C.byref(vao)); api.glBindVertexArray(vao.value)
-                api.glGenBuffers(1, C.byref(vbo)); api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
-                api.glBufferData(G.GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), G.GL_STATIC_DRAW)
-                api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
-                api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
-                if idx is not None and indexed:
-                    api.glGenBuffers(1, C.byref(ebo)); api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, ebo.value)
-                    api.glBufferData(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx), G.GL_STATIC_DRAW)
-                vaos.append(vao.value)
-                has_ebo.append(idx is not None and indexed)
+                vaos.append(None); names.append(None); has_ebo.append(False)
+                make_array(len(vaos) - 1, verts, idx)
             for unit, tex in enumerate(op[2]):
                 t = C.c_uint32(0)
                 api.glGenTextures(1, C.byref(t))
@@ -204,6 +228,18 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
         elif k == "vao":
             cur_vao = op[1]
             api.glBindVertexArray(vaos[cur_vao])
+        elif k == "respecify":
+            cur_vao = op[1]
+            verts, idx = op[2]
+            if ours:
+                api.glBindVertexArray(vaos[cur_vao])
+                api.glBindBuffer(G.GL_ARRAY_BUFFER, names[cur_vao][0])
+                api.swglBufferRespecify(G.GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts))
+                if has_ebo[cur_vao]:
+                    api.glBindBuffer(G.GL_ELEMENT_ARRAY_BUFFER, names[cur_vao][1])
+                    api.swglBufferRespecify(G.GL_ELEMENT_ARRAY_BUFFER, idx.nbytes, _ptr(idx))
+            else:
+                make_array(cur_vao, verts, idx)
         elif k == "draw":
             if has_ebo[cur_vao]:
                 api.glDrawElements(G.GL_TRIANGLES, op[2], G.GL_UNSIGNED_INT, C.c_void_p(4 * op[1]))
@@ -249,10 +285,11 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, indexed=False):
 def compare_seed(gpu_api, reference, seed, perturb=False, devices=1):
     """-> '' if the two libraries agree on every frame of the sequence, else a description."""
     ops = make_ops(seed)
+    W, H = ops[0][3], ops[0][4]
     try:
         gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
                          lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
-                         perturb=5000 + seed if perturb else None, devices=devices, indexed=True)
+                         perturb=5000 + seed if perturb else None, devices=devices, ours=True)
     finally:
         for name, values in [p for p in PERTURB if len(p) == 2]:       # back to the defaults for whoever comes next
             gpu_api.swglSetOption(name.encode(), {"host_mirror": 1, "fuse_clear": 1, "lean_prims": 1, "setup_big": 1, "jit": 1,

@@ -9,5 +9,5 @@ import test_api_fuzz_gpu as F
 api = swgl_b200.load()
 ops = F.make_ops(int(sys.argv[1]))
 F.run_ops(api, ops, lambda w, d: api.swglFillFramebuffer(w, C.c_float(d)),
-          lambda: np.ctypeslib.as_array(api.swglGetDepthPtr(), shape=(F.H, F.W)).copy())
+          lambda: np.ctypeslib.as_array(api.swglGetDepthPtr(), shape=(ops[0][4], ops[0][3])).copy())
 print("error:", api.swglGetLastError().decode())
