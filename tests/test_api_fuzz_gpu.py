@@ -34,9 +34,12 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def make_ops(seed, inside=False):
+def make_ops(seed, inside=False, lod=False):
     """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries).
-    inside: viewports stay inside the framebuffer rows (sort-first ranks of separate processes cannot fold)."""
+    inside: viewports stay inside the framebuffer rows (sort-first ranks of separate processes cannot fold);
+    lod: for runs that SAMPLE mip chains ("mip_lod"): every texture object gets at most one chain and is not re-specified
+    afterwards (the reference appends a second chain to the first and keeps a chain when its image is replaced,
+    swgl.c:2094-2098, 2134-2166: not reproduced), and one chain exists from the start."""
     rng = np.random.default_rng(31000 + seed)
     W, H = SIZES[int(rng.integers(len(SIZES)))] if seed >= 12 else SIZES[0]      # odd sizes: partial tiles, unaligned rows
 
@@ -57,6 +60,10 @@ def make_ops(seed, inside=False):
     textures = [S.checker_texture(int(rng.choice([8, 32]))), S.lcg_texture(int(rng.choice([16, 64])), seed=int(rng.integers(1, 99)))]
     ops = [("setup", list(arrays), textures, W, H)]
     prog, vao = 0, 0
+    bound, chained = 1, set()             # the texture object the texture calls act on: the one bound last (swgl.c:2062)
+    if lod:
+        ops.append(("mipmap", 1))
+        chained.add(bound)
     ops += [("use", 0), ("vao", 0), ("clear", 3)]
     for _ in range(int(rng.integers(10, 26))):
         r = rng.random()
@@ -77,9 +84,15 @@ def make_ops(seed, inside=False):
         elif r < 0.07:
             unit = int(rng.integers(0, 2))
             tex = S.lcg_texture(int(rng.choice([4, 16, 32])), seed=int(rng.integers(1, 99)))
-            ops.append(("teximage", unit, tex if rng.random() < 0.7 else np.ascontiguousarray(tex[:, :, :3])))
-            if rng.random() < 0.4:
+            tex = tex if rng.random() < 0.7 else np.ascontiguousarray(tex[:, :, :3])
+            if rng.random() < 0.3:
+                bound = int(rng.integers(0, 2))
+                ops.append(("bindtex", unit, bound))      # texture object `bound` onto `unit`; it becomes the one texture calls act on
+            if not (lod and bound in chained):
+                ops.append(("teximage", unit, tex))
+            if rng.random() < 0.4 and not (lod and bound in chained):
                 ops.append(("mipmap", unit))
+                chained.add(bound)
         elif r < 0.38:
             n = len(arrays[vao][0]) if arrays[vao][1] is None else len(arrays[vao][1])
             first = int(rng.integers(0, max(n - 2, 1)))
@@ -126,7 +139,7 @@ PERTURB = [("host_mirror", (0, 1, 2)), ("fuse_clear", (0, 1)), ("tile_rows", (0,
            ("count_fragments", (0, 1)), ("finish",), ("stats",), ("submit_wait",), ("rgba8",)]
 
 
-def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
+def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, points=True, options=None):
     """Issue `ops`; -> (frames read on the way + the final one, final depth).
     perturb: seed of library-only calls slipped in between (options that must not change a bit of the result, waits,
     statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit;
@@ -141,10 +154,12 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
     api.glInit(W, H)
     if devices > 1:
         api.swglSetDeviceCount(1)          # the setting is consumed by glInit: later tests get one device again
+    for name, value in (options or {}).items():      # device options start from their defaults at every glInit
+        api.swglSetOption(name.encode(), value)
     fill(0x0A0B0C0D, 0.0)
     api.glViewport(0, 0, W, H)
     api.glClearColor(0.0, 0.0, 0.0, 1.0)
-    frames, progs, vaos, cur, has_ebo, cur_vao, names = [], [], [], 0, [], 0, []
+    frames, progs, vaos, cur, has_ebo, cur_vao, names, texs = [], [], [], 0, [], 0, [], []
 
     def make_array(j, verts, idx):
         """vertex array j from scratch: named buffers that own the data (specified with no vertex array bound, swgl.c:3123-3126),
@@ -205,6 +220,7 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
             for unit, tex in enumerate(op[2]):
                 t = C.c_uint32(0)
                 api.glGenTextures(1, C.byref(t))
+                texs.append(t.value)
                 api.glActiveTexture(G.GL_TEXTURE0 + unit)
                 api.glBindTexture(G.GL_TEXTURE_2D, t.value)
                 tt = np.ascontiguousarray(tex, np.uint8)
@@ -245,7 +261,7 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
                 api.glDrawElements(G.GL_TRIANGLES, op[2], G.GL_UNSIGNED_INT, C.c_void_p(4 * op[1]))
             else:
                 api.glDrawArrays(G.GL_TRIANGLES, op[1], op[2])
-        elif k == "points":
+        elif k == "points" and points:
             api.glDrawArrays(G.GL_POINTS, op[1], op[2])
         elif k == "teximage":
             api.glActiveTexture(G.GL_TEXTURE0 + op[1])
@@ -255,6 +271,9 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
         elif k == "mipmap":
             api.glActiveTexture(G.GL_TEXTURE0 + op[1])
             api.glGenerateMipmap(G.GL_TEXTURE_2D)
+        elif k == "bindtex":
+            api.glActiveTexture(G.GL_TEXTURE0 + op[1])
+            api.glBindTexture(G.GL_TEXTURE_2D, texs[op[2]])
         elif k == "viewport":
             api.glViewport(*op[1:])
         elif k == "clearcolor":
@@ -282,29 +301,37 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False):
     return frames, depth_of()
 
 
-def compare_seed(gpu_api, reference, seed, perturb=False, devices=1):
-    """-> '' if the two libraries agree on every frame of the sequence, else a description."""
-    ops = make_ops(seed)
+def compare_seed(gpu_api, reference, seed, perturb=False, devices=1, lod=False):
+    """-> '' if the two libraries agree on every frame of the sequence, else a description.
+    lod: the library samples mip chains with the per-triangle level ("mip_lod" = 1) and `reference` is the build with
+    the defined rsqrt (oracle/ref_shim.c); GL_POINTS draws are left out (their level is the last triangle's in the
+    reference, a global -- DESIGN.md section 8)."""
+    ops = make_ops(seed, lod=lod)
+    return compare_ops(gpu_api, reference, ops, f"seed {seed}", perturb=5000 + seed if perturb else None, devices=devices, lod=lod)
+
+
+def compare_ops(gpu_api, reference, ops, what, perturb=None, devices=1, lod=False):
     W, H = ops[0][3], ops[0][4]
     try:
         gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
                          lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
-                         perturb=5000 + seed if perturb else None, devices=devices, ours=True)
+                         perturb=perturb, devices=devices, ours=True, points=not lod, options={"mip_lod": 1} if lod else None)
     finally:
+        gpu_api.swglSetOption(b"mip_lod", 0)
         for name, values in [p for p in PERTURB if len(p) == 2]:       # back to the defaults for whoever comes next
             gpu_api.swglSetOption(name.encode(), {"host_mirror": 1, "fuse_clear": 1, "lean_prims": 1, "setup_big": 1, "jit": 1,
                                                   "overflow_pool": 1, "bin_cap": 256, "count_fragments": 1}.get(name, 0))
     err = gpu_api.swglGetLastError().decode()
     if err:
-        return f"seed {seed}: {err}"
+        return f"{what}: {err}"
     rf, rd = run_ops(reference.api, ops, lambda w, d: reference.lib.swglref_fill(w, C.c_float(d)),
-                     lambda: np.ctypeslib.as_array(reference.lib.swglref_depth_ptr(), shape=(H, W)).copy())
+                     lambda: np.ctypeslib.as_array(reference.lib.swglref_depth_ptr(), shape=(H, W)).copy(), points=not lod)
     for i, (a, b) in enumerate(zip(gf, rf)):
         if not np.array_equal(a, b):
-            return f"seed {seed}: frame {i} of {len(gf)} differs in {int((a != b).sum())} pixels; ops {[o[0] for o in ops]}"
+            return f"{what}: frame {i} of {len(gf)} differs in {int((a != b).sum())} pixels; ops {[o[0] for o in ops]}"
     cmp = O.compare(gf[-1], gd, rf[-1], rd)
     if cmp["color_mismatch"] or cmp["depth_mismatch"] or cmp["coverage_mismatch"]:
-        return f"seed {seed}: {cmp}"
+        return f"{what}: {cmp}"
     return ""
 
 
@@ -326,3 +353,18 @@ def test_random_call_sequence_on_a_device_group(gpu_api, reference, seed, device
     leave the framebuffer rows are folded on the leader with every member's bands gathered there (group_draw_folded)."""
     monkeypatch.setenv("SWGL_B200_GROUP_EMULATE", "1")
     assert compare_seed(gpu_api, reference, seed, perturb=seed % 2 == 0, devices=devices) == ""
+
+
+@pytest.fixture(scope="module")
+def reference_lod():
+    try:
+        return O.Reference(defined_rsqrt=True)
+    except Exception as e:                                  # pragma: no cover
+        pytest.skip(f"oracle/_ref/libswgl_ref_lod.so not available: {e}")
+
+
+@pytest.mark.parametrize("seed", range(1000, 1008))
+def test_random_call_sequence_with_mip_levels(gpu_api, reference_lod, seed):
+    """Sequences that build mip chains, with the library's "mip_lod" on, against the reference compiled with the
+    defined rsqrt (the level of detail is undefined behaviour in the plain build)."""
+    assert compare_seed(gpu_api, reference_lod, seed, lod=True) == ""
