@@ -1443,7 +1443,7 @@ __device__ __forceinline__ bool fold_aliased(const DrawParams& P, int y)
 }
 
 template <int FS>
-__device__ __forceinline__ void fold_prim(const DrawParams& P, int x, const float4& a, const float4& b, const float4& c,
+__device__ __forceinline__ void fold_prim(const DrawParams& P, int x, int count_from, const float4& a, const float4& b, const float4& c,
                                           uint32_t v0, uint32_t v1, uint32_t v2, uint32_t& col, float& dep,
                                           uint32_t& n_tested, uint32_t& n_shaded)
 {
@@ -1464,7 +1464,7 @@ __device__ __forceinline__ void fold_prim(const DrawParams& P, int x, const floa
 			row_span(x0, x1, P, xa, xb);
 			if (x >= xa && x < xb)
 			{
-				n_tested++;
+				if (y >= count_from) n_tested++;       /* the rows below count_from were walked -- and counted -- by the tile kernels */
 				FragIn fi;
 				float z;
 				frag_weights(k, (float)x, (float)y, fi.u, fi.v, fi.w, z);
@@ -1489,7 +1489,7 @@ __device__ __forceinline__ void fold_prim(const DrawParams& P, int x, const floa
 }
 
 template <int FS>
-__global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawParams P, int x_lo, int x_hi)
+__global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawParams P, int x_lo, int x_hi, int count_from)
 {
 	const int x = x_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (x >= x_hi) return;
@@ -1503,7 +1503,7 @@ __global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawPa
 		uint32_t s0, s1, s2;
 		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
 		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
-		if (in_mask == 7u) { fold_prim<FS>(P, x, p0, p1, p2, s0, s1, s2, col, dep, n_tested, n_shaded); continue; }
+		if (in_mask == 7u) { fold_prim<FS>(P, x, count_from, p0, p1, p2, s0, s1, s2, col, dep, n_tested, n_shaded); continue; }
 		if (in_mask == 0u) continue;
 		/* near clip again (swgl.c:563-696); the varyings of the new vertices were written by the set-up kernel */
 		const float2 zz = make_float2(0.0f, 0.0f);
@@ -1518,15 +1518,15 @@ __global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawPa
 		{
 			const int ia = in_idx[0];
 			const float4 q1 = near_intersect(p[ia], p[out_idx[0]], t0), q2 = near_intersect(p[ia], p[out_idx[1]], t1);
-			fold_prim<FS>(P, x, to_screen(p[ia], P), to_screen(q1, P), to_screen(q2, P), sid[ia], new0, new1, col, dep, n_tested, n_shaded);
+			fold_prim<FS>(P, x, count_from, to_screen(p[ia], P), to_screen(q1, P), to_screen(q2, P), sid[ia], new0, new1, col, dep, n_tested, n_shaded);
 		}
 		else
 		{
 			const int ia = in_idx[0], ib = in_idx[1], io = out_idx[0];
 			const float4 q0 = near_intersect(p[ia], p[io], t0), q1 = near_intersect(p[ib], p[io], t1);
 			const float4 sq0 = to_screen(q0, P);
-			fold_prim<FS>(P, x, to_screen(p[ia], P), to_screen(p[ib], P), sq0, sid[ia], sid[ib], new0, col, dep, n_tested, n_shaded);
-			fold_prim<FS>(P, x, to_screen(p[ib], P), sq0, to_screen(q1, P), sid[ib], new0, new1, col, dep, n_tested, n_shaded);
+			fold_prim<FS>(P, x, count_from, to_screen(p[ia], P), to_screen(p[ib], P), sq0, sid[ia], sid[ib], new0, col, dep, n_tested, n_shaded);
+			fold_prim<FS>(P, x, count_from, to_screen(p[ib], P), sq0, to_screen(q1, P), sid[ib], new0, new1, col, dep, n_tested, n_shaded);
 		}
 	}
 	P.color[pix] = col;
@@ -2776,7 +2776,10 @@ static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 	CK(cudaMallocAsync((void**)&vdep, npx * 4, c->stream));
 	CK(cudaMallocAsync((void**)&vcount, ntiles * 4, c->stream));
 	CK(cudaMemsetAsync(vcol, 0, npx * 4, c->stream));
-	CK(cudaMemsetAsync(vdep, 0, npx * 4, c->stream));
+	/* the rows of the virtual target that stand for the fold hold NaN depth: no fragment passes the test there (cur == 0
+	 * and cur >= z are both false), so the tile kernels only count -- and shade -- what lands on real rows; every
+	 * fragment is still TESTED there exactly once, which is the reference's count */
+	CK(cudaMemsetAsync(vdep, 0xff, npx * 4, c->stream));
 	CK(cudaMemsetAsync(vcount, 0, ntiles * 4, c->stream));
 	/* real rows 0 .. H-2 keep their place in the virtual framebuffer; row H-1 and the rows outside are the fold */
 	const size_t keep = (size_t)(c->H - 1u) * c->W * 4;
@@ -2815,9 +2818,13 @@ static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 		if (x_hi > x_lo)
 		{
 			const dim3 grid(((uint32_t)(x_hi - x_lo) + 127u) / 128u);
-			if (P.fs_kind == SWFS_VARYING) k_fold_row<SWFS_VARYING><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
-			else if (P.fs_kind == SWFS_TEXTURE) k_fold_row<SWFS_TEXTURE><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
-			else k_fold_row<SWFS_GENERIC><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi);
+			/* fragments are counted as tested by whoever walks their row: the tile kernels up to the row limit they
+			 * were given, this kernel beyond it (only a viewport that ends below row 0 has rows beyond) */
+			const int64_t top = (int64_t)d->vy + (int64_t)d->vh;
+			const int count_from = top < 0 ? (int)top : 0x7fffffff;
+			if (P.fs_kind == SWFS_VARYING) k_fold_row<SWFS_VARYING><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi, count_from);
+			else if (P.fs_kind == SWFS_TEXTURE) k_fold_row<SWFS_TEXTURE><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi, count_from);
+			else k_fold_row<SWFS_GENERIC><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi, count_from);
 			c->n_launches++;
 		}
 		c->draws_folded++;
@@ -2879,6 +2886,9 @@ static int group_draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 	if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = -1;
 	/* the members' bands of the assembled mirror are out of date: their next read-back copies them */
 	for (int i = 0; i < n; i++) c->group[i]->mirror_synced = 0;
+	/* the draw's counters are the leader's: the other members still hold those of their last own draw */
+	group_each(c, [&](int i, swgldev_ctx* m) { if (i) cudaMemsetAsync(m->ctr, 0, sizeof(Counters), m->stream); return 0; });
+	cudaSetDevice(c->device);
 	if (rc) set_err(c, "folded draw on a device group failed", cudaGetLastError());
 	return rc ? -1 : 0;
 }

@@ -373,3 +373,21 @@ def test_viewport_that_leaves_the_framebuffer_rows_folds_onto_the_last_row(gpu_a
     # 10-row viewport: the reference draws none of them)
     if not (outside_all and kind == "textured_mesh"):
         assert int((b[1][H - 1].view(np.uint32) != 0).sum()) > 0
+
+
+@pytest.mark.parametrize("viewport", [(0, -40, W, H), (0, 30, W, H), (-10, -25, W + 20, H + 60), (13, -7, 150, 300),
+                                      (89, -24, 101, 10), (0, H + 8, W, 50)],
+                         ids=["below", "above", "both", "narrow_tall", "entirely_below_row_limit_wraps", "entirely_above"])
+def test_folded_draw_counts_fragments_like_the_restatement(gpu_api, restatement, viewport):
+    """The C restatement folds rows like the reference (checked against it on the CPU: tests/test_oracle.py, test_restatement_folds_rows_like_the_compiled_reference) and
+    counts Barycentric calls and depth passes: a folded draw must report the same numbers -- every fragment tested once
+    (by the tile kernels for the rows they walk, by k_fold_row beyond) and shaded on the real row it lands on."""
+    from util import gpu_render
+    scene = S.random_triangles(400, W, H, seed=21, near_cross=True, alpha=None, centre_range=1.2)
+    scene.viewport = viewport
+    rc, rd, rstats = restatement.render(scene)
+    col, dep, stats, err = gpu_render(gpu_api, scene)
+    assert err == "" and gpu_api.swglGetOption(b"draws_folded") == 1
+    cmp = O.compare(col, dep, rc, rd)
+    assert cmp["color_mismatch"] == 0 and cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0, cmp
+    assert (stats["tested"], stats["shaded"]) == (rstats["tested"], rstats["shaded"])

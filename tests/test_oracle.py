@@ -71,6 +71,21 @@ def test_no_clear_and_partial_draw(restatement, reference):
     assert cmp["depth_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
 
 
+@pytest.mark.parametrize("viewport", [(0, -40, 200, 152), (0, 30, 200, 152), (-10, -25, 220, 212), (13, -7, 150, 300),
+                                      (89, -24, 101, 10), (0, 160, 200, 50)])
+def test_restatement_folds_rows_like_the_compiled_reference(restatement, reference, viewport):
+    """Viewports that leave the framebuffer rows (swgl.c:3386: rows outside land on row Height-1; a viewport that ends
+    below row 0 also loses its row limit, 3344 / 3356).  The restatement's fragment counts for such draws are what
+    tests/test_api_edge_gpu.py holds the library's folded draws to."""
+    scene = S.random_triangles(400, 200, 152, seed=21, near_cross=True, alpha=None, centre_range=1.2)
+    scene.viewport = viewport
+    c1, d1, stats = restatement.render(scene)
+    c2, d2 = reference.render(scene)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+    assert stats["tested"] > 0 and int((d2[151].view(np.uint32) != 0).sum()) > 0
+
+
 def test_restatement_matches_fullsize_golden_c2(restatement):
     """BASELINE config 2 at full size (1080p, 100,352 triangles): the restatement against the hashes the
     compiled reference produced (tests/golden/fullsize_kats.json); also the survey's K3 values."""

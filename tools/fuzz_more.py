@@ -43,12 +43,16 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
             bad += 1
             print("MISMATCH", seed, sc.name, opts, err, cmp, stats["tested"], rstats["tested"])
     if ref is not None and seed % 4 == 0:
-        # folded viewport: the restatement does not model rows outside the framebuffer, the compiled reference does
+        # folded viewport: against the compiled reference (and the restatement's fragment counts)
         vp = sc.viewport or (0, 0, sc.width, sc.height)
         sc.viewport = (vp[0], vp[1] - int(rng.integers(1, 40)), vp[2], vp[3] + int(rng.integers(0, 60)))
         fc, fd = ref.render(sc, clear=clear, fill=fill)
+        _, _, fstats = rest.render(sc, clear=clear, fill=fill)          # the restatement folds too; it also counts fragments
         col, dep, stats, err = gpu_render(api, sc, indexed=sc.indices is not None, clear=clear, fill=fill)
         cmp = O.compare(col, dep, fc, fd)
+        if (stats["tested"], stats["shaded"]) != (fstats["tested"], fstats["shaded"]):
+            cmp["coverage_mismatch"] += 1
+            print("COUNTS folded", seed, stats["tested"], fstats["tested"], stats["shaded"], fstats["shaded"])
         n += 1
         outside = sc.viewport[1] < 0 or sc.viewport[1] + sc.viewport[3] > sc.height
         folded += int(api.swglGetOption(b"draws_folded") >= 1)
