@@ -53,9 +53,10 @@ typedef struct
 	int32_t  fpp;          /* channels per texel, 1..4 (swgl.c:2099-2102) */
 	int32_t  is_float;     /* 0: bytes, converted with /255.0f at sample time; 1: floats */
 	int32_t  wrap_s_repeat, wrap_t_repeat;
-	/* glGenerateMipmap chain (swgl.c:2122-2173), built by swgldev_build_mipmaps: 16 words of level
-	 * offsets (in floats, relative to the end of the header) followed by the levels as floats;
-	 * level k is (width >> (k + 1)) x (height >> (k + 1)).  0 = no chain. */
+	/* glGenerateMipmap chain (swgl.c:2122-2173), built by swgldev_build_mipmaps: a table of 32 entries x 4
+	 * fields, field-major (offset in floats behind the table, width, height, floats per texel at build time),
+	 * followed by the levels as floats.  The levels keep their own sizes because the reference's vector
+	 * outlives the image it was built from.  0 = no chain. */
 	swgldev_ptr mips;
 	int32_t  n_mips;
 	int32_t  _pad;
@@ -144,7 +145,10 @@ uint32_t     swgldev_max_index_after_stream(swgldev_ctx* c, swgldev_ptr indices,
 int          swgldev_upload_indices(swgldev_ctx* c, swgldev_ptr dst, const void* src, uint64_t bytes, uint32_t* max_index);
 
 /* glGenerateMipmap (swgl.c:2122-2173): the 2x2 box chain of `base` as one allocation (layout: see
- * swgldev_texture.mips); *n_levels = levels built (0: the base level is too small, nothing allocated).
+ * swgldev_texture.mips).  base->mips / n_mips = the chain the texture already has: its levels come first in the
+ * new allocation, unchanged, and the levels of the current image behind them, as in the reference, whose
+ * vector is only ever appended to (the caller frees the old allocation).  *n_levels = levels in the new
+ * chain; returns 0 when nothing was added (image too small, 32 levels reached) or on error.
  * The chain is only sampled when the "mip_lod" option selects the defined LOD (swgl_b200.h). */
 swgldev_ptr  swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, int32_t* n_levels);
 

@@ -2329,6 +2329,7 @@ swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, i
 		{
 			swgldev_texture b = *base;
 			b.data = member_ptr(c, i, base->data);
+			b.mips = member_ptr(c, i, base->mips);
 			reps[(size_t)i] = swgldev_build_mipmaps(m, &b, &levels[(size_t)i]);
 			return 0;
 		});
@@ -2347,42 +2348,69 @@ swgldev_ptr swgldev_build_mipmaps(swgldev_ctx* c, const swgldev_texture* base, i
 	cudaSetDevice(c->device);
 	*n_levels = 0;
 	if (!base->data || base->fpp < 1 || base->fpp > 4) return 0;
+	/* The reference never clears a texture's MipMaps vector: a second glGenerateMipmap APPENDS the levels of the
+	 * current image behind the ones that are there, and glTexImage2D leaves them in place (swgl.c:2094-2118,
+	 * 2134-2166).  `base->mips` is that earlier chain (0 = none): its levels come first, unchanged. */
+	uint32_t hdr[SWGL_MIP_HEADER_WORDS];
+	memset(hdr, 0, sizeof(hdr));
+	int n_prev = 0;
+	size_t prev_floats = 0;
+	if (base->mips && base->n_mips > 0)
+	{
+		if (settle_last_draw(c)) return 0;
+		if (cudaStreamSynchronize(c->stream) != cudaSuccess
+		    || cudaMemcpy(hdr, (const void*)(uintptr_t)base->mips, sizeof(hdr), cudaMemcpyDeviceToHost) != cudaSuccess)
+		{
+			set_err(c, "glGenerateMipmap: reading the earlier chain", cudaGetLastError());
+			return 0;
+		}
+		n_prev = base->n_mips < SWGL_MIP_MAX_LEVELS ? base->n_mips : SWGL_MIP_MAX_LEVELS;
+		for (int k = 0; k < n_prev; k++)
+		{
+			const size_t end_k = (size_t)hdr[k] + (size_t)hdr[SWGL_MIP_MAX_LEVELS + k] * hdr[2 * SWGL_MIP_MAX_LEVELS + k] * hdr[3 * SWGL_MIP_MAX_LEVELS + k];
+			if (end_k > prev_floats) prev_floats = end_k;
+		}
+	}
 	/* levels while CurWidth + CurHeight > 4, halving with integer division (swgl.c:2129-2135, 2167-2168) */
-	uint32_t off[16];
-	int cw = base->width / 2, ch = base->height / 2, n = 0;
-	size_t floats = 0;
-	while (cw + ch > 4 && n < 16)
+	int cw = base->width / 2, ch = base->height / 2, n = n_prev;
+	size_t floats = prev_floats;
+	while (cw + ch > 4 && n < SWGL_MIP_MAX_LEVELS)
 	{
 		if (floats > 0xffffffffull) { set_err(c, "glGenerateMipmap: chain too large", cudaSuccess); return 0; }
-		off[n++] = (uint32_t)floats;
-		floats += (size_t)cw * (size_t)ch * (size_t)base->fpp;
+		hdr[n] = (uint32_t)floats;
+		hdr[SWGL_MIP_MAX_LEVELS + n] = (uint32_t)(cw > 0 ? cw : 0);
+		hdr[2 * SWGL_MIP_MAX_LEVELS + n] = (uint32_t)(ch > 0 ? ch : 0);
+		hdr[3 * SWGL_MIP_MAX_LEVELS + n] = (uint32_t)base->fpp;
+		floats += (size_t)(cw > 0 ? cw : 0) * (size_t)(ch > 0 ? ch : 0) * (size_t)base->fpp;
+		n++;
 		cw /= 2; ch /= 2;
 	}
-	if (n == 0) return 0;
-	for (int k = n; k < 16; k++) off[k] = 0;
-	const swgldev_ptr chain = swgldev_alloc(c, 64 + floats * 4 + 4);
+	if (n == n_prev) return 0;           /* nothing new (image too small, or the level table is full): the earlier chain stays */
+	const swgldev_ptr chain = swgldev_alloc(c, sizeof(hdr) + floats * 4 + 4);
 	if (!chain) return 0;
-	if (cudaMemcpyAsync((void*)(uintptr_t)chain, off, 64, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+	float* data = (float*)(uintptr_t)(chain + sizeof(hdr));
+	bool ok = cudaMemcpyAsync((void*)(uintptr_t)chain, hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+	if (ok && prev_floats)
+		ok = cudaMemcpyAsync(data, (const void*)(uintptr_t)(base->mips + sizeof(hdr)), prev_floats * 4, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+	if (!ok)
 	{
 		set_err(c, "glGenerateMipmap: upload of the level table", cudaGetLastError());
 		swgldev_free(c, chain);
 		return 0;
 	}
-	float* data = (float*)(uintptr_t)(chain + 64);
 	const void* prev = (const void*)(uintptr_t)base->data;
 	int prev_u8 = base->is_float ? 0 : 1;
-	cw = base->width / 2; ch = base->height / 2;
-	for (int k = 0; k < n; k++)
+	for (int k = n_prev; k < n; k++)
 	{
-		if (cw > 0 && ch > 0)
+		const int lw = (int)hdr[SWGL_MIP_MAX_LEVELS + k], lh = (int)hdr[2 * SWGL_MIP_MAX_LEVELS + k];
+		if (lw > 0 && lh > 0)
 		{
-			k_mipmap_box<<<dim3(((uint32_t)cw + 255u) / 256u, (uint32_t)ch), 256, 0, c->stream>>>(prev, prev_u8, c->lut255, base->fpp, cw, ch, data + off[k]);
+			k_mipmap_box<<<dim3(((uint32_t)lw + 255u) / 256u, (uint32_t)lh), 256, 0, c->stream>>>(prev, prev_u8, c->lut255, base->fpp, lw, lh, data + hdr[k]);
 			c->n_launches++;
 		}
-		prev = data + off[k]; prev_u8 = 0;
-		cw /= 2; ch /= 2;
+		prev = data + hdr[k]; prev_u8 = 0;
 	}
-	/* off[] is on this stack: the copy must have read it before returning */
+	/* hdr[] is on this stack: the copy must have read it before returning */
 	if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
 	{
 		set_err(c, "glGenerateMipmap: k_mipmap_box", cudaGetLastError());

@@ -76,7 +76,7 @@ struct DevTex
 {
 	const void* data;
 	int32_t w, h, fpp, is_float, rep_s, rep_t;
-	const uint32_t* mips;       /* glGenerateMipmap chain: 16 offset words, then float levels (swgldev_texture.mips) */
+	const uint32_t* mips;       /* glGenerateMipmap chain: SWGL_MIP_HEADER_WORDS of level table, then float levels (swgldev_texture.mips) */
 	int32_t n_mips, _pad;
 };
 

@@ -573,10 +573,8 @@ void glTexImage2D(GLenum target, GLint level, GLint internalformat, GLsizei widt
 	if (!data || border != 0 || target != GL_TEXTURE_2D || !G.active_texture || !G.dev) return;
 	gl_texture* t = G.active_texture;
 	if (t->data) { swgldev_free(G.dev, t->data); t->data = 0; }
-	/* the reference keeps the old chain (MipMaps is never cleared, swgl.c:2094) and so keeps sampling the old
-	 * image's levels; not reproduced: the chain goes with the image it was built from */
-	if (t->mips) { swgldev_free(G.dev, t->mips); t->mips = 0; }
-	t->n_mipmaps = 0;
+	/* the chain stays: the reference never clears MipMaps (swgl.c:2094-2118) and goes on sampling the old image's
+	 * levels, with the new image's floats per texel, until glGenerateMipmap appends new ones behind them */
 	if (internalformat != (GLint)format) return; /* the reference returns here with the old data freed */
 	if (internalformat == GL_RGBA) t->fpp = 4;
 	if (internalformat == GL_RGB) t->fpp = 3;
@@ -607,13 +605,17 @@ void glGenerateMipmap(GLenum target)
 	 * defined variant -- rsqrt with a 32-bit pun -- in which the chain is sampled with the
 	 * per-triangle level (tests/test_mipmap_gpu.py, against the reference built the same way). */
 	gl_texture* t = G.active_texture;
-	if (t->n_mipmaps > 0) return;   /* a second call appends levels of the smallest level in the reference: not reproduced */
 	swgldev_texture base;
 	memset(&base, 0, sizeof(base));
 	base.data = t->data; base.width = t->width; base.height = t->height; base.fpp = t->fpp; base.is_float = t->is_float;
+	/* a chain that is already there is kept and the new levels go behind it (swgl.c:2134-2166 pushes onto the same
+	 * vector): the device layer builds old + new as one allocation */
+	base.mips = t->mips; base.n_mips = t->n_mipmaps;
 	int32_t n = 0;
-	t->mips = swgldev_build_mipmaps(G.dev, &base, &n);
-	t->n_mipmaps = t->mips ? n : 0;
+	const swgldev_ptr chain = swgldev_build_mipmaps(G.dev, &base, &n);
+	if (!chain) return;             /* nothing new (image too small, table full) or an error: what was there stays */
+	if (t->mips) swgldev_free(G.dev, t->mips);
+	t->mips = chain; t->n_mipmaps = n;
 }
 
 /* ---------------------------------------------------------------------------------------- */

@@ -119,6 +119,10 @@ typedef struct
 #define SWGL_MAX_VARYING_FLOATS 16
 #define SWGL_MAX_FETCH      16
 #define SWGL_MAX_TEX_UNITS  8
+/* glGenerateMipmap chains (swgldev_texture.mips): a table of SWGL_MIP_MAX_LEVELS entries x 4 fields, field-major
+ * -- float offset of the level behind the table, width, height, floats per texel it was built with -- then the levels */
+#define SWGL_MIP_MAX_LEVELS    32
+#define SWGL_MIP_HEADER_WORDS  (4 * SWGL_MIP_MAX_LEVELS)
 
 typedef struct swgl_ir_code
 {

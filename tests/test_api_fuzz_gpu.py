@@ -37,9 +37,11 @@ def _ptr(a):
 def make_ops(seed, inside=False, lod=False):
     """The call sequence of a seed as a list of tuples (data only: the same list drives both libraries).
     inside: viewports stay inside the framebuffer rows (sort-first ranks of separate processes cannot fold);
-    lod: for runs that SAMPLE mip chains ("mip_lod"): every texture object gets at most one chain and is not re-specified
-    afterwards (the reference appends a second chain to the first and keeps a chain when its image is replaced,
-    swgl.c:2094-2098, 2134-2166: not reproduced), and one chain exists from the start."""
+    lod: for runs that SAMPLE mip chains ("mip_lod"): one chain exists from the start, and a texture object that has
+    levels never gets an image with MORE floats per texel than they were built with (the reference never clears a
+    texture's levels and addresses them with the current image's floats per texel, swgl.c:2094-2118, 2559: with more of
+    them it reads past the level's allocation).  Second chains appended behind the first and levels of images that
+    have since been replaced are part of the game."""
     rng = np.random.default_rng(31000 + seed)
     W, H = SIZES[int(rng.integers(len(SIZES)))] if seed >= 12 else SIZES[0]      # odd sizes: partial tiles, unaligned rows
 
@@ -60,10 +62,11 @@ def make_ops(seed, inside=False, lod=False):
     textures = [S.checker_texture(int(rng.choice([8, 32]))), S.lcg_texture(int(rng.choice([16, 64])), seed=int(rng.integers(1, 99)))]
     ops = [("setup", list(arrays), textures, W, H)]
     prog, vao = 0, 0
-    bound, chained = 1, set()             # the texture object the texture calls act on: the one bound last (swgl.c:2062)
+    bound, level_fpp = 1, {}              # the texture object the texture calls act on: the one bound last (swgl.c:2062)
+    cur_fpp = {0: 4, 1: 4}
     if lod:
         ops.append(("mipmap", 1))
-        chained.add(bound)
+        level_fpp[bound] = 4
     ops += [("use", 0), ("vao", 0), ("clear", 3)]
     for _ in range(int(rng.integers(10, 26))):
         r = rng.random()
@@ -88,11 +91,12 @@ def make_ops(seed, inside=False, lod=False):
             if rng.random() < 0.3:
                 bound = int(rng.integers(0, 2))
                 ops.append(("bindtex", unit, bound))      # texture object `bound` onto `unit`; it becomes the one texture calls act on
-            if not (lod and bound in chained):
+            if not (lod and tex.shape[2] > level_fpp.get(bound, 4)):
                 ops.append(("teximage", unit, tex))
-            if rng.random() < 0.4 and not (lod and bound in chained):
+                cur_fpp[bound] = tex.shape[2]
+            if rng.random() < 0.4:
                 ops.append(("mipmap", unit))
-                chained.add(bound)
+                level_fpp[bound] = min(level_fpp.get(bound, 4), cur_fpp[bound])
         elif r < 0.38:
             n = len(arrays[vao][0]) if arrays[vao][1] is None else len(arrays[vao][1])
             first = int(rng.integers(0, max(n - 2, 1)))

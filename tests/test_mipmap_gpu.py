@@ -145,6 +145,46 @@ def test_two_mipped_textures_in_a_generic_shader_and_a_near_clipped_scene(gpu_ap
     _check(a, b)
 
 
+def test_levels_outlive_their_image_and_second_chains_are_appended(gpu_api, reference_lod):
+    """The reference never clears a texture's level vector (swgl.c:2094-2118, 2134-2166): glTexImage2D leaves the old
+    image's levels in place (sampled with their own sizes), a second glGenerateMipmap pushes the new image's levels
+    behind them, and min(level, count - 1) then reaches into the second chain.  Four frames, each after one more call."""
+    scene = S.random_triangles(800, W, H, seed=5, extent=0.12, textured=True)      # levels from below 1 to beyond 10
+    first = S.lcg_texture(64, seed=3)
+    second = S.lcg_texture(16, seed=9)
+    third = np.ascontiguousarray(S.lcg_texture(32, seed=11)[:, :, :3])       # fewer floats per texel than the levels: still inside them
+    frames = []
+
+    def script(api):
+        st = G.setup_scene(api, scene, indexed=False, init=False)
+
+        def frame():
+            api.glClear(3)
+            api.glDrawArrays(G.GL_TRIANGLES, 0, st["n_draw"])
+            return G.frame_color(api, W, H).copy()
+        api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 64, 64, 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(first))
+        api.glGenerateMipmap(G.GL_TEXTURE_2D)
+        out = [frame()]
+        api.glGenerateMipmap(G.GL_TEXTURE_2D)                    # the same four levels once more, behind the first four
+        out.append(frame())
+        api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 16, 16, 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(second))
+        out.append(frame())                                      # a 16x16 image with the 64x64 image's eight levels
+        api.glGenerateMipmap(G.GL_TEXTURE_2D)                    # + two levels of the 16x16 image
+        out.append(frame())
+        api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGB, 32, 32, 0, G.GL_RGB, G.GL_UNSIGNED_BYTE, _ptr(third))
+        out.append(frame())                                      # RGB image over RGBA levels: stride 3 inside 4-float texels
+        frames.append(out)
+    a, b = _frames(gpu_api, reference_lod, script, 3)
+    _check(a, b)
+    ours, theirs = frames
+    for k, (x, y) in enumerate(zip(ours, theirs)):
+        assert np.array_equal(x, y), f"frame {k}: {int((x != y).sum())} pixels differ"
+    # the second chain, the third chain and the narrower image change what is sampled; replacing the image alone does
+    # not change a pixel (a positive level only ever reads the old image's levels)
+    changed = [int((theirs[k] != theirs[k + 1]).sum()) for k in range(4)]
+    assert changed[0] > 500 and changed[1] == 0 and changed[2] > 500 and changed[3] > 500, changed
+
+
 def test_default_stays_bug_compatible(gpu_api, reference):
     """Without the option the chain is built but never sampled, like the compiled reference."""
     scene = S.grid_mesh(24, W, H, textured=True)
