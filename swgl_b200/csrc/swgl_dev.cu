@@ -2854,6 +2854,10 @@ static int draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 			else if (P.fs_kind == SWFS_TEXTURE) k_fold_row<SWFS_TEXTURE><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi, count_from);
 			else k_fold_row<SWFS_GENERIC><<<grid, 128, 0, c->stream>>>(P, x_lo, x_hi, count_from);
 			c->n_launches++;
+			/* k_fold_row reads the element buffer, the textures and the draw's scratch: the draw's event has to lie
+			 * behind it, or a re-specification of those buffers that follows the draw would only wait for the tile
+			 * kernels (found by the API-sequence fuzz: an index buffer re-specified right after a folded draw) */
+			if (stamp_draw(c, d)) rc = -1;
 		}
 		c->draws_folded++;
 	}

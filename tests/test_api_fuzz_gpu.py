@@ -28,6 +28,11 @@ FS_TEX = "in vec2 vUV;\nuniform sampler2D uTex;\nout vec4 FragColor;\nvoid main(
 FS_TINT = ("in vec4 vCol;\nuniform vec4 tint;\nuniform sampler2D uTex;\nout vec4 FragColor;\nvoid main()\n{\n"
            "vec4 t = texture(uTex,vCol.zy) * tint;\nFragColor = vec4(t.x, vCol.y, t.z, vCol.w);\n}\n")
 PROGRAMS = [(VS_COLOUR, FS_COLOUR), (VS_MATRIX, FS_COLOUR), (VS_UV, FS_TEX), (VS_COLOUR, FS_TINT), (VS_MATRIX, FS_TINT)]
+# ... and a pool of random well-typed programs (tests/shader_fuzz_gen.py): varyings of every width, uniforms u1 .. u4 that
+# the sequences change under way; compiled at run time once per process, interpreted on the fold row
+from shader_fuzz_gen import make as _random_program          # noqa: E402
+RANDOM_PROGRAMS = [_random_program(900 + k) for k in range(6)]
+PROGRAMS += [(vs, fs) for vs, fs, _ in RANDOM_PROGRAMS]
 
 
 def _ptr(a):
@@ -128,7 +133,11 @@ def make_ops(seed, inside=False, lod=False):
             m = np.eye(4, dtype=np.float32) + rng.uniform(-0.15, 0.15, (4, 4)).astype(np.float32)
             ops.append(("matrix", m))
         elif r < 0.91:
-            ops.append(("tint",) + tuple(float(v) for v in rng.uniform(0.1, 1.3, 4)))
+            if rng.random() < 0.5:
+                ops.append(("tint",) + tuple(float(v) for v in rng.uniform(0.1, 1.3, 4)))
+            else:
+                n = int(rng.integers(1, 5))                   # u1 (float) .. u4 (vec4) of the random programs
+                ops.append(("uni", n) + tuple(float(v) for v in rng.uniform(0.1, 1.5, n)))
         elif r < 0.95:
             ops.append(("sampler", int(rng.integers(0, 2))))
         elif r < 0.97:
@@ -218,6 +227,10 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, point
                     loc = api.glGetUniformLocation(p, name)
                     if loc >= 0:
                         setter(loc)
+                k = len(progs) - 1 - (len(PROGRAMS) - len(RANDOM_PROGRAMS))
+                if k >= 0:
+                    for name, (kind, vals) in RANDOM_PROGRAMS[k][2].items():
+                        getattr(api, "glUniform" + kind)(api.glGetUniformLocation(p, name.encode()), *[float(x) for x in vals])
             for verts, idx in op[1]:
                 vaos.append(None); names.append(None); has_ebo.append(False)
                 make_array(len(vaos) - 1, verts, idx)
@@ -292,6 +305,10 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, point
             loc = api.glGetUniformLocation(cur, b"tint")
             if loc >= 0:
                 api.glUniform4f(loc, *op[1:])
+        elif k == "uni":
+            loc = api.glGetUniformLocation(cur, f"u{op[1]}".encode())
+            if loc >= 0:
+                getattr(api, f"glUniform{op[1]}f")(loc, *op[2:])
         elif k == "sampler":
             loc = api.glGetUniformLocation(cur, b"uTex")
             if loc >= 0:
