@@ -1,0 +1,66 @@
+"""CPU: the random generators behind the GPU fuzz tests produce what they promise -- sequences and shaders inside the
+reference's DEFINED behaviour.  The compiled reference runs every generated call sequence here (a sequence outside its
+defined behaviour shows as a crash or as a frame that changes between two runs), the library's front end accepts
+every generated shader, and a few of them go through the run-time compiler (no device needed)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import swgl_b200
+from oracle import pyoracle as O
+from swgl_b200 import gl as G
+
+import test_api_fuzz_gpu as F
+from shader_fuzz_gen import make
+from test_jit import _compile
+
+
+def _run_on_reference(ref, ops, points=True):
+    W, H = ops[0][3], ops[0][4]
+    return F.run_ops(ref.api, ops, lambda w, d: ref.lib.swglref_fill(w, C.c_float(d)),
+                     lambda: np.ctypeslib.as_array(ref.lib.swglref_depth_ptr(), shape=(H, W)).copy(), points=points)
+
+
+def test_call_sequences_are_deterministic_on_the_compiled_reference(reference):
+    kinds = set()
+    for seed in range(0, 60):
+        ops = F.make_ops(seed)
+        kinds.update(o[0] for o in ops)
+        f1, d1 = _run_on_reference(reference, ops)
+        f2, d2 = _run_on_reference(reference, ops)
+        assert len(f1) == len(f2) and all(np.array_equal(a, b) for a, b in zip(f1, f2)), seed
+        assert np.array_equal(d1.view(np.uint32), d2.view(np.uint32)), seed
+    # the generator reaches every kind of call it knows
+    assert {"setup", "use", "vao", "draw", "points", "viewport", "clear", "clearcolor", "matrix", "tint", "uni", "sampler",
+            "wrap", "teximage", "mipmap", "bindtex", "respecify", "read"} <= kinds
+    assert F.make_ops(7)[1:5] == F.make_ops(7)[1:5]
+
+
+def test_mip_level_sequences_run_on_the_defined_rsqrt_reference():
+    try:
+        ref = O.Reference(defined_rsqrt=True)
+    except Exception as e:                                  # pragma: no cover
+        pytest.skip(f"oracle/_ref/libswgl_ref_lod.so not available: {e}")
+    for seed in range(1000, 1030):
+        ops = F.make_ops(seed, lod=True)
+        assert ops[1] == ("mipmap", 1)
+        f1, _ = _run_on_reference(ref, ops, points=False)
+        f2, _ = _run_on_reference(ref, ops, points=False)
+        assert all(np.array_equal(a, b) for a, b in zip(f1, f2)), seed
+
+
+def test_random_shaders_are_accepted_by_the_front_end_and_compile():
+    api = swgl_b200.load()
+    for seed in range(40):
+        vs, fs, uniforms = make(seed)
+        assert make(seed) == (vs, fs, uniforms)
+        for kind, src in ((G.GL_VERTEX_SHADER, vs), (G.GL_FRAGMENT_SHADER, fs)):
+            sh = api.glCreateShader(kind)
+            api.glShaderSource(sh, src.encode())
+            api.glCompileShader(sh)
+            assert api.swglGetShaderCompiled(sh) == 1, (seed, src)
+    api.swglGetLastError()
+    for seed in (900, 903, 905):                            # three of the programs tests/test_api_fuzz_gpu.py pools
+        vs, fs, _ = make(seed)
+        assert _compile(api, vs, fs) == 0, api.swglGetLastError().decode()
