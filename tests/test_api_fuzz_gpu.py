@@ -152,7 +152,7 @@ PERTURB = [("host_mirror", (0, 1, 2)), ("fuse_clear", (0, 1)), ("tile_rows", (0,
            ("count_fragments", (0, 1)), ("finish",), ("stats",), ("submit_wait",), ("rgba8",)]
 
 
-def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, points=True, options=None):
+def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, points=True, options=None, stripe=None):
     """Issue `ops`; -> (frames read on the way + the final one, final depth).
     perturb: seed of library-only calls slipped in between (options that must not change a bit of the result, waits,
     statistics, the pipelined and the byte-swizzled read-back); devices: swglSetDeviceCount before glInit;
@@ -169,6 +169,8 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, point
         api.swglSetDeviceCount(1)          # the setting is consumed by glInit: later tests get one device again
     for name, value in (options or {}).items():      # device options start from their defaults at every glInit
         api.swglSetOption(name.encode(), value)
+    if stripe:
+        api.swglSetStripe(*stripe)                   # (rank, ranks, band height in 32-row units): sort-first share of one rank
     fill(0x0A0B0C0D, 0.0)
     api.glViewport(0, 0, W, H)
     api.glClearColor(0.0, 0.0, 0.0, 1.0)
@@ -354,6 +356,48 @@ def compare_ops(gpu_api, reference, ops, what, perturb=None, devices=1, lod=Fals
     if cmp["color_mismatch"] or cmp["depth_mismatch"] or cmp["coverage_mismatch"]:
         return f"{what}: {cmp}"
     return ""
+
+
+def compare_seed_in_ranks(gpu_api, reference, seed, ranks, band_rows=1, perturb=False):
+    """The sequence once per sort-first rank (swglSetStripe: the rank rasterises and clears the bands it owns only), the
+    ranks' bands stitched together like the peer / shared-mirror targets assemble them, against the reference's frames.
+    Viewports stay inside the framebuffer rows (ranks of separate processes refuse folded draws)."""
+    ops = make_ops(seed, inside=True)
+    W, H = ops[0][3], ops[0][4]
+    owner = ((np.arange(H) >> 5) // band_rows) % ranks
+    frames, depth = None, None
+    try:
+        for r in range(ranks):
+            gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
+                             lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
+                             perturb=5000 + seed if perturb else None, ours=True, stripe=(r, ranks, band_rows))
+            err = gpu_api.swglGetLastError().decode()
+            if err:
+                return f"seed {seed} rank {r}: {err}"
+            if frames is None:
+                frames, depth = [f.copy() for f in gf], gd.copy()
+            for f, g in zip(frames, gf):
+                f[owner == r] = g[owner == r]
+            depth[owner == r] = gd[owner == r]
+    finally:
+        gpu_api.swglSetStripe(0, 1, 1)
+        for name, values in [p for p in PERTURB if len(p) == 2]:
+            gpu_api.swglSetOption(name.encode(), {"host_mirror": 1, "fuse_clear": 1, "lean_prims": 1, "setup_big": 1, "jit": 1,
+                                                  "overflow_pool": 1, "bin_cap": 256, "count_fragments": 1}.get(name, 0))
+    rf, rd = run_ops(reference.api, ops, lambda w, d: reference.lib.swglref_fill(w, C.c_float(d)),
+                     lambda: np.ctypeslib.as_array(reference.lib.swglref_depth_ptr(), shape=(H, W)).copy())
+    for i, (a, b) in enumerate(zip(frames, rf)):
+        if not np.array_equal(a, b):
+            return f"seed {seed}: stitched frame {i} of {len(frames)} differs in {int((a != b).sum())} pixels; ops {[o[0] for o in ops]}"
+    cmp = O.compare(frames[-1], depth, rf[-1], rd)
+    if cmp["color_mismatch"] or cmp["depth_mismatch"] or cmp["coverage_mismatch"]:
+        return f"seed {seed}: {cmp}"
+    return ""
+
+
+@pytest.mark.parametrize("seed,ranks,band_rows", [(30, 2, 1), (31, 3, 1), (32, 2, 2), (33, 4, 1)])
+def test_random_call_sequence_in_sort_first_ranks(gpu_api, reference, seed, ranks, band_rows):
+    assert compare_seed_in_ranks(gpu_api, reference, seed, ranks, band_rows, perturb=seed % 2 == 1) == ""
 
 
 @pytest.mark.parametrize("seed", range(12))
