@@ -206,6 +206,7 @@ struct swgldev_ctx
 
 	swgldev_stats stats;
 	uint64_t n_draws;
+	float* d_last_level;                 /* mip_lod: the reference's global MipMapLevel (what the last triangle left; GL_POINTS samples with it) */
 	int in_fold;                         /* the draw being issued renders into the virtual framebuffer of draw_folded() */
 	int64_t fold_shift;                  /* virtual storage row = real storage row - fold_shift (<= 0) */
 	uint64_t draws_folded;
@@ -1409,7 +1410,7 @@ __global__ void __launch_bounds__(256) k_points_write(const __grid_constant__ Dr
 		for (uint32_t k = 0; k < P.n_varying; k++)
 			for (uint32_t j = 0; j < P.varying[k].n_floats; j++)
 				V[P.varying[k].fs_word + j] = __float_as_uint(vv[P.varying[k].slot + j]);
-		ir_execute(P.fs_ops, P.fs_nops, V, P, 0.0f);   /* points: base level (the reference keeps the last triangle's level) */
+		ir_execute(P.fs_ops, P.fs_nops, V, P, P.mip_lod ? *P.last_level : 0.0f);   /* points: the level the last triangle left (k_last_level) */
 		for (uint32_t k = 0; k < P.out_floats; k++) o[k] = __uint_as_float(V[P.out_word + k]);
 	}
 	const float r = RMIN(RMAX(o[0], 0.0f), 1.0f), g = RMIN(RMAX(o[1], 0.0f), 1.0f);
@@ -1538,6 +1539,45 @@ __global__ void __launch_bounds__(128) k_fold_row(const __grid_constant__ DrawPa
 	}
 }
 
+/* mip_lod: MipMapLevel is a global of the reference that every DrawTriangle call sets first thing (swgl.c:3314-3316) and
+ * that GL_POINTS draws then sample with (their path never sets it).  One thread finds the last triangle of the draw
+ * that reaches DrawTriangle -- the last input triangle not entirely behind the near plane, and of the two triangles the
+ * clipper may make of it the second -- and leaves its level where k_points_write reads it. */
+__global__ void k_last_level(const __grid_constant__ DrawParams P)
+{
+	for (uint32_t t = P.ntri; t-- > 0; )
+	{
+		float4 p0, p1, p2;
+		uint32_t s0, s1, s2;
+		tri_vertices(P, t, p0, p1, p2, s0, s1, s2);
+		const uint32_t in_mask = (p0.z >= -p0.w ? 1u : 0u) | (p1.z >= -p1.w ? 2u : 0u) | (p2.z >= -p2.w ? 4u : 0u);
+		if (in_mask == 0u) continue;
+		if (in_mask != 7u)
+		{
+			const float2 zz = make_float2(0.0f, 0.0f);
+			const float2 c0 = (s0 < P.n_shade) ? P.clip_xy[s0] : zz, c1 = (s1 < P.n_shade) ? P.clip_xy[s1] : zz, c2 = (s2 < P.n_shade) ? P.clip_xy[s2] : zz;
+			const float4 p[3] = { make_float4(c0.x, c0.y, p0.z, p0.w), make_float4(c1.x, c1.y, p1.z, p1.w), make_float4(c2.x, c2.y, p2.z, p2.w) };
+			int in_idx[3], out_idx[3], n_in = 0, n_out = 0;
+			for (int j = 0; j < 3; j++) { if ((in_mask >> j) & 1u) in_idx[n_in++] = j; else out_idx[n_out++] = j; }
+			float t0, t1;
+			if (n_in == 1)
+			{
+				p0 = to_screen(p[in_idx[0]], P);
+				p1 = to_screen(near_intersect(p[in_idx[0]], p[out_idx[0]], t0), P);
+				p2 = to_screen(near_intersect(p[in_idx[0]], p[out_idx[1]], t1), P);
+			}
+			else
+			{
+				p0 = to_screen(p[in_idx[1]], P);
+				p1 = to_screen(near_intersect(p[in_idx[0]], p[out_idx[0]], t0), P);
+				p2 = to_screen(near_intersect(p[in_idx[1]], p[out_idx[0]], t1), P);
+			}
+		}
+		*P.last_level = mip_level(p0.x, p0.y, p1.x, p1.y, p2.x, p2.y);
+		return;
+	}
+}
+
 /* raster_path: 1 = pixel-owner CTA per 32x32 tile (k_raster), 2 = fragment-parallel CTA per 32x32
  * tile (k_raster_frag), 3 = warp per 32x8 tile (k_raster_warp).  0 = default = the warp kernel for
  * every draw.  All three produce identical bits. */
@@ -1637,7 +1677,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	c->n_launches = 0; c->stage_draws = 0; c->selftest_mismatches = -1; c->opt_lean_prims = 1; c->opt_mip_lod = 0; c->opt_jit = 1; c->opt_overflow_pool = 1; c->opt_setup_pipelined = 0; c->opt_setup_big = 1; c->opt_tile_rows = 0; c->cur_th_shift = WT_H_SHIFT; c->jit_failed = 0; c->last_vs_kind = -1; c->last_fs_kind = -1;
 	c->mirror_synced = 0; c->wt_predict = 0; c->draws_since_map = 0; c->opt_host_mirror = 1; c->color_exposed = 0; c->wt_draws = 0;
 	c->h_mirror[0] = c->h_mirror[1] = nullptr; c->frame_ev[0] = c->frame_ev[1] = nullptr; c->frame_serial = 0; c->rgba_staging = nullptr; c->copy = nullptr; c->frame_done = nullptr; c->copy_inflight = 0;
-	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr;
+	c->upload = nullptr; c->draw_serial = 0; c->d_maxidx = nullptr; c->h_maxidx = nullptr; c->lut255 = nullptr; c->d_last_level = nullptr;
 	for (int i = 0; i < 8; i++) c->draw_ev[i] = nullptr;
 	for (int i = 0; i < 8; i++) { c->stage_ev[i] = nullptr; c->stage_us[i] = 0.0; }
 	memset(&c->pending_clear, 0, sizeof(c->pending_clear));
@@ -1662,6 +1702,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	       && cudaMalloc((void**)&c->d_maxidx, 4) == cudaSuccess
 	       && cudaMallocHost((void**)&c->h_maxidx, 4) == cudaSuccess
 	       && cudaMalloc((void**)&c->lut255, 256 * sizeof(float)) == cudaSuccess
+	       && cudaMalloc((void**)&c->d_last_level, sizeof(float)) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[0], cudaEventDisableTiming) == cudaSuccess
 	       && cudaEventCreateWithFlags(&c->frame_ev[1], cudaEventDisableTiming) == cudaSuccess
 	       && cudaHostAlloc((void**)&c->h_depth, (npx ? npx : 1) * 4, cudaHostAllocPortable) == cudaSuccess
@@ -1692,6 +1733,7 @@ swgldev_ctx* swgldev_create(int device, uint32_t width, uint32_t height)
 	}
 	memset(c->h_ctr, 0, sizeof(Counters));
 	k_init_lut255<<<1, 256, 0, c->stream>>>(c->lut255);
+	cudaMemsetAsync(c->d_last_level, 0, sizeof(float), c->stream);     /* the reference's global starts at 0: base level */
 	c->h_color = c->h_mirror[0];
 	for (int i = 0; i < 8; i++)
 		if (cudaEventCreateWithFlags(&c->draw_ev[i], cudaEventDisableTiming) != cudaSuccess) { swgldev_destroy(c); return nullptr; }
@@ -1817,6 +1859,7 @@ void swgldev_destroy(swgldev_ctx* c)
 	if (c->d_maxidx) cudaFree(c->d_maxidx);
 	if (c->h_maxidx) cudaFreeHost(c->h_maxidx);
 	if (c->lut255) cudaFree(c->lut255);
+	if (c->d_last_level) cudaFree(c->d_last_level);
 	for (int i = 0; i < 2; i++) if (c->frame_ev[i]) cudaEventDestroy(c->frame_ev[i]);
 	for (int i = 0; i < 8; i++) if (c->draw_ev[i]) cudaEventDestroy(c->draw_ev[i]);
 	cudaFree(c->tile_count); cudaFree(c->ctr); cudaFreeHost(c->h_ctr);
@@ -2569,6 +2612,7 @@ static int launch_draw(swgldev_ctx* c, DrawParams& P)
 	c->last_vs_kind = P.vs_kind; c->last_fs_kind = P.fs_kind;
 	STAGE(3);
 #undef STAGE
+	if (c->opt_mip_lod) { k_last_level<<<1, 1, 0, c->stream>>>(P); c->n_launches++; }     /* what a later GL_POINTS draw samples with */
 	c->n_launches += P.inline_tall ? 3 : 4;
 	CK(cudaGetLastError());
 	if (timing)
@@ -2647,7 +2691,7 @@ static int fill_common_params(swgldev_ctx* c, const swgldev_draw* d, DrawParams&
 		P.fs_ops = upload_code(c, d->fs_code_id, d->fs_code); P.fs_nops = d->fs_code->n_ops;
 		if (!P.fs_ops) { set_err(c, "fragment shader upload failed", cudaGetLastError()); return 1; }
 	}
-	P.tile_count = c->tile_count; P.ctr = c->ctr; P.lut255 = c->lut255;
+	P.tile_count = c->tile_count; P.ctr = c->ctr; P.lut255 = c->lut255; P.last_level = c->d_last_level;
 	return 0;
 }
 

@@ -133,6 +133,7 @@ struct DrawParams
 	float pos_matrix[16];
 	uint32_t fs_slot, fs_slot_floats, fs_swz_u, fs_swz_v; int32_t fs_tex_unit;
 	DevTex tex[SWGL_MAX_TEX_UNITS];
+	float* last_level;          /* mip_lod: MipMapLevel as the last DrawTriangle call left it (a global in the reference, swgl.c:3314-3316) */
 	/* fused clear */
 	ClearParams clear;
 	uint32_t count_fragments;

@@ -327,8 +327,8 @@ def run_ops(api, ops, fill, depth_of, perturb=None, devices=1, ours=False, point
 def compare_seed(gpu_api, reference, seed, perturb=False, devices=1, lod=False):
     """-> '' if the two libraries agree on every frame of the sequence, else a description.
     lod: the library samples mip chains with the per-triangle level ("mip_lod" = 1) and `reference` is the build with
-    the defined rsqrt (oracle/ref_shim.c); GL_POINTS draws are left out (their level is the last triangle's in the
-    reference, a global -- DESIGN.md section 8)."""
+    the defined rsqrt (oracle/ref_shim.c); GL_POINTS draws sample with the level the last triangle left (a global in
+    the reference; k_last_level here)."""
     ops = make_ops(seed, lod=lod)
     return compare_ops(gpu_api, reference, ops, f"seed {seed}", perturb=5000 + seed if perturb else None, devices=devices, lod=lod)
 
@@ -338,7 +338,7 @@ def compare_ops(gpu_api, reference, ops, what, perturb=None, devices=1, lod=Fals
     try:
         gf, gd = run_ops(gpu_api, ops, lambda w, d: gpu_api.swglFillFramebuffer(w, C.c_float(d)),
                          lambda: np.ctypeslib.as_array(gpu_api.swglGetDepthPtr(), shape=(H, W)).copy(),
-                         perturb=perturb, devices=devices, ours=True, points=not lod, options={"mip_lod": 1} if lod else None)
+                         perturb=perturb, devices=devices, ours=True, options={"mip_lod": 1} if lod else None)
     finally:
         gpu_api.swglSetOption(b"mip_lod", 0)
         for name, values in [p for p in PERTURB if len(p) == 2]:       # back to the defaults for whoever comes next
@@ -348,7 +348,7 @@ def compare_ops(gpu_api, reference, ops, what, perturb=None, devices=1, lod=Fals
     if err:
         return f"{what}: {err}"
     rf, rd = run_ops(reference.api, ops, lambda w, d: reference.lib.swglref_fill(w, C.c_float(d)),
-                     lambda: np.ctypeslib.as_array(reference.lib.swglref_depth_ptr(), shape=(H, W)).copy(), points=not lod)
+                     lambda: np.ctypeslib.as_array(reference.lib.swglref_depth_ptr(), shape=(H, W)).copy())
     for i, (a, b) in enumerate(zip(gf, rf)):
         if not np.array_equal(a, b):
             return f"{what}: frame {i} of {len(gf)} differs in {int((a != b).sum())} pixels; ops {[o[0] for o in ops]}"

@@ -45,8 +45,8 @@ def test_mip_level_sequences_run_on_the_defined_rsqrt_reference():
     for seed in range(1000, 1030):
         ops = F.make_ops(seed, lod=True)
         assert ops[1] == ("mipmap", 1)
-        f1, _ = _run_on_reference(ref, ops, points=False)
-        f2, _ = _run_on_reference(ref, ops, points=False)
+        f1, _ = _run_on_reference(ref, ops)
+        f2, _ = _run_on_reference(ref, ops)
         assert all(np.array_equal(a, b) for a, b in zip(f1, f2)), seed
 
 

@@ -185,6 +185,55 @@ def test_levels_outlive_their_image_and_second_chains_are_appended(gpu_api, refe
     assert changed[0] > 500 and changed[1] == 0 and changed[2] > 500 and changed[3] > 500, changed
 
 
+FS_POINT_TEX = ("in vec4 vCol;\nuniform sampler2D uTex;\nout vec4 FragColor;\nvoid main()\n{\n"
+                "vec4 t = texture(uTex,vCol.xy);\nFragColor = vec4(t.x, t.y, t.z, 1.0);\n}\n")
+
+
+def _points_after_triangles(api, tri_scene, pts, with_triangles):
+    v = api.glCreateShader(G.GL_VERTEX_SHADER); api.glShaderSource(v, S.VS_PASSTHROUGH.encode()); api.glCompileShader(v)
+    f = api.glCreateShader(G.GL_FRAGMENT_SHADER); api.glShaderSource(f, FS_POINT_TEX.encode()); api.glCompileShader(f)
+    p = api.glCreateProgram(); api.glAttachShader(p, v); api.glAttachShader(p, f); api.glLinkProgram(p); api.glUseProgram(p)
+    verts = np.ascontiguousarray(np.concatenate([tri_scene.vertices, pts]), np.float32)
+    vao, vbo, t = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    api.glGenVertexArrays(1, C.byref(vao)); api.glBindVertexArray(vao.value)
+    api.glGenBuffers(1, C.byref(vbo)); api.glBindBuffer(G.GL_ARRAY_BUFFER, vbo.value)
+    api.glBufferData(G.GL_ARRAY_BUFFER, verts.nbytes, _ptr(verts), G.GL_STATIC_DRAW)
+    api.glVertexAttribPointer(0, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(0))
+    api.glVertexAttribPointer(1, 4, G.GL_FLOAT, G.GL_FALSE, 32, C.c_void_p(16))
+    tex = S.lcg_texture(64, seed=3)
+    api.glGenTextures(1, C.byref(t)); api.glBindTexture(G.GL_TEXTURE_2D, t.value)
+    api.glTexImage2D(G.GL_TEXTURE_2D, 0, G.GL_RGBA, 64, 64, 0, G.GL_RGBA, G.GL_UNSIGNED_BYTE, _ptr(tex))
+    api.glUniform1i(api.glGetUniformLocation(p, b"uTex"), 0)
+    api.glClear(3)
+    nt = len(tri_scene.vertices)
+    # one triangle first in both runs: the reference only allocates a program's fragment inputs when a triangle is shaded
+    api.glDrawArrays(G.GL_TRIANGLES, 0, 3)
+    api.glGenerateMipmap(G.GL_TEXTURE_2D)
+    if with_triangles:
+        api.glDrawArrays(G.GL_TRIANGLES, 3, nt - 3)          # the LAST of them leaves its level behind
+    api.glClear(3)
+    api.glDrawArrays(G.GL_POINTS, nt, len(pts))
+
+
+def test_points_sample_with_the_level_the_last_triangle_left(gpu_api, reference_lod):
+    """MipMapLevel is a global in the reference, set by every DrawTriangle call (swgl.c:3314-3316) and read by texture()
+    whatever the primitive: a GL_POINTS draw samples with what the last triangle before it left (k_last_level)."""
+    tri_scene = S.random_triangles(60, W, H, seed=8, extent=0.05, near_cross=True)        # small triangles: levels well above 1
+    # ... behind one big triangle (level below 1: the half-size level), which is all the second run draws before its points
+    tri_scene.vertices[0:3, 0:4] = [[-0.9, -0.9, 0.5, 1.0], [0.9, -0.8, 0.5, 1.0], [0.0, 0.9, 0.5, 1.0]]
+    rng = np.random.default_rng(4)
+    pts = np.zeros((3000, 8), np.float32)
+    pts[:, 0:2] = rng.uniform(-0.95, 0.95, (3000, 2)); pts[:, 2] = 0.5; pts[:, 3] = 1.0
+    pts[:, 4:8] = rng.uniform(0.0, 1.0, (3000, 4))
+    frames = {}
+    for with_triangles in (True, False):
+        a, b = _frames(gpu_api, reference_lod, lambda api: _points_after_triangles(api, tri_scene, pts, with_triangles), 3)
+        _check(a, b)
+        frames[with_triangles] = b[0]
+    # the level really reaches the points: without the triangles in between they sample another level
+    assert int((frames[True] != frames[False]).sum()) > 300
+
+
 def test_default_stays_bug_compatible(gpu_api, reference):
     """Without the option the chain is built but never sampled, like the compiled reference."""
     scene = S.grid_mesh(24, W, H, textured=True)
