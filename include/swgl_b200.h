@@ -146,7 +146,9 @@ void  swglHostFree(void* p);
  * "mip_lod" (0 default: glGenerateMipmap builds the chain but the base level is sampled, which is what the compiled
  * reference does -- its level of detail goes through an rsqrt() with undefined behaviour, swgl.c:3240-3246; 1: the
  * chain is sampled with the per-triangle level the same code gives with a 32-bit pun, bit-identical to the reference
- * built that way, oracle/ref_shim.c);
+ * built that way, oracle/ref_shim.c -- including what the reference does around it: levels outlive the image they were
+ * built from, a second glGenerateMipmap appends its levels behind the first, GL_POINTS sample with the level the last
+ * triangle left);
  * "setup_big" (1 default: draws of big triangles -- more than 64 pixels per triangle on average -- are set up by a warp per
  * triangle; 0: a thread per triangle plus a second kernel for the tall ones), "setup_pipelined" (0 default; 1: the
  * software-pipelined form of the set-up kernel, measured slower);
