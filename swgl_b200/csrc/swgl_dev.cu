@@ -252,8 +252,8 @@ static int group_each(swgldev_ctx* c, const std::function<int(int, swgldev_ctx*)
 static void set_err(swgldev_ctx* c, const char* what, cudaError_t e)
 {
 	if (c->error[0]) return; /* keep the first */
-	if (e != cudaSuccess) snprintf(c->error, sizeof(c->error), "%s: %s", what, cudaGetErrorString(e));
-	else snprintf(c->error, sizeof(c->error), "%s", what);
+	if (e != cudaSuccess) snprintf(c->error, sizeof(c->error), "%.300s: %.200s", what, cudaGetErrorString(e));
+	else snprintf(c->error, sizeof(c->error), "%.500s", what);
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(c, #call, e_); return -1; } } while (0)
