@@ -66,6 +66,12 @@ class _Shader(C.Structure):
         ("tex_fpp", C.c_int32),
         ("wrap_s_repeat", C.c_int32),
         ("wrap_t_repeat", C.c_int32),
+        ("lod", C.c_int32),
+        ("n_mips", C.c_int32),
+        ("mip_data", C.POINTER(C.c_float)),
+        ("mip_off", C.POINTER(C.c_int32)),
+        ("mip_w", C.POINTER(C.c_int32)),
+        ("mip_h", C.POINTER(C.c_int32)),
     ]
 
 
@@ -122,6 +128,9 @@ class Restatement:
             C.POINTER(_Target), C.POINTER(_Shader), C.c_void_p, C.c_size_t,
             C.c_void_p, C.c_uint32, C.POINTER(Stats)]
         L.swglo_texels_from_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.swglo_build_mipmaps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(C.c_size_t)]
+        L.swglo_build_mipmaps.restype = C.c_int
         L.swglo_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
         L.swglo_fnv1a64.restype = C.c_uint64
         L.swglo_timed_frame.argtypes = [
@@ -133,7 +142,7 @@ class Restatement:
         a = np.ascontiguousarray(a).view(np.uint32).reshape(-1)
         return int(self.lib.swglo_fnv1a64(a.ctypes.data_as(C.c_void_p), a.size))
 
-    def _prep(self, scene, color, depth, keep):
+    def _prep(self, scene, color, depth, keep, mipmaps=False):
         t = _Target()
         t.width, t.height = scene.width, scene.height
         vp = scene.viewport or (0, 0, scene.width, scene.height)
@@ -144,18 +153,34 @@ class Restatement:
         if scene.texture is not None:
             tf, t8 = keep[0], keep[1]
             self.lib.swglo_texels_from_u8(t8.ctypes.data_as(C.c_void_p), tf.ctypes.data_as(C.c_void_p), tf.size)
+            if mipmaps:
+                # glGenerateMipmap + the defined level of detail (swgl_oracle.h): size query, then the levels
+                total = C.c_size_t(0)
+                n = self.lib.swglo_build_mipmaps(tf.ctypes.data_as(C.c_void_p), s.tex_w, s.tex_h, s.tex_fpp, None, None, None, None, C.byref(total))
+                data = np.zeros(max(int(total.value), 1), np.float32)
+                off, lw, lh = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+                self.lib.swglo_build_mipmaps(tf.ctypes.data_as(C.c_void_p), s.tex_w, s.tex_h, s.tex_fpp, data.ctypes.data_as(C.c_void_p),
+                                             off.ctypes.data_as(C.c_void_p), lw.ctypes.data_as(C.c_void_p), lh.ctypes.data_as(C.c_void_p), C.byref(total))
+                keep += [data, off, lw, lh]
+                s.lod, s.n_mips = 1, n
+                s.mip_data = data.ctypes.data_as(C.POINTER(C.c_float))
+                s.mip_off = off.ctypes.data_as(C.POINTER(C.c_int32))
+                s.mip_w = lw.ctypes.data_as(C.POINTER(C.c_int32))
+                s.mip_h = lh.ctypes.data_as(C.POINTER(C.c_int32))
         return t, s
 
     def render(self, scene, *, clear: bool = True, color=None, depth=None,
-               first: int = 0, count: Optional[int] = None, fill=(0, 0.0)):
-        """Returns (color uint32 [H,W], depth float32 [H,W], stats dict)."""
+               first: int = 0, count: Optional[int] = None, fill=(0, 0.0), mipmaps: bool = False):
+        """Returns (color uint32 [H,W], depth float32 [H,W], stats dict).
+        mipmaps: glGenerateMipmap on the scene's texture and the DEFINED level of detail (the checker of that mode is
+        Reference(defined_rsqrt=True), rendered with mipmaps=True too)."""
         H, W = scene.height, scene.width
         if color is None:
             color = np.full((H, W), fill[0], np.uint32)
         if depth is None:
             depth = np.full((H, W), fill[1], np.float32)
         keep: list = []
-        t, s = self._prep(scene, color, depth, keep)
+        t, s = self._prep(scene, color, depth, keep, mipmaps)
         if clear:
             self.lib.swglo_clear(C.byref(t), 3, *[C.c_float(c) for c in scene.clear_color])
         st = Stats()
@@ -213,11 +238,13 @@ class Reference:
         self.lib.swglref_timed_frame.restype = C.c_double
 
     def render(self, scene, *, clear: bool = True, first: int = 0, count: Optional[int] = None,
-               fill=(0, 0.0)):
+               fill=(0, 0.0), mipmaps: bool = False):
         """Returns (color uint32 [H,W], depth float32 [H,W]).  Indexed scenes are de-indexed
         on the host first: the reference has no glDrawElements."""
         G = self.G
         st = G.setup_scene(self.api, scene, indexed=False)
+        if mipmaps:
+            self.api.glGenerateMipmap(G.GL_TEXTURE_2D)
         self.lib.swglref_fill(fill[0], fill[1])
         if clear:
             self.api.glClear(3)

@@ -139,6 +139,104 @@ static void sample_nearest(const swglo_shader* s, float u, float v, float rgba[4
 	if (s->tex_fpp == 4) rgba[3] = p[3];
 }
 
+/* rsqrt (swgl.c:3238-3254) with the pun through a 32-bit integer: the defined variant (see swgl_oracle.h). */
+static float rsqrt_defined(float number)
+{
+	int32_t i;
+	float x2, y;
+	const float threehalfs = 1.5F;
+	x2 = number * 0.5F;
+	y = number;
+	memcpy(&i, &y, 4);
+	i = 0x5f3759df - (i >> 1);
+	memcpy(&y, &i, 4);
+	y = y * (threehalfs - (x2 * y * y));
+	y = y * (threehalfs - (x2 * y * y));
+	y = y * (threehalfs - (x2 * y * y));
+	return y;
+}
+
+/* DistBetweenPointAndLine (swgl.c:3299-3312) and MipMapLevel = 40 / distance (swgl.c:3316). */
+static float mip_level(float x1, float y1, float x2, float y2, float x3, float y3)
+{
+	float m = (y2 - y1) / RMAX(x2 - x1, 1.0f);
+	float c = y1 - m * x1;
+	float distance = (m * x3 - y3 + c);
+	if (distance < 0.0f) distance *= -1.0f;
+	distance *= rsqrt_defined(m * m + 1);
+	return 40.0f / distance;
+}
+
+static void texel_of(const float* data, int w, int h, int fpp, int rep_s, int rep_t, float u, float v, float rgba[4])
+{
+	int tx = u * w;
+	int ty = v * h;
+	if (rep_s) tx %= w;
+	tx = RMIN(RMAX(tx, 0), w - 1);
+	if (rep_t) ty %= h;
+	ty = RMIN(RMAX(ty, 0), h - 1);
+	const float* p = data + (size_t)fpp * ((size_t)tx + (size_t)ty * w);
+	rgba[0] = rgba[1] = rgba[2] = rgba[3] = 0.0f;
+	if (fpp >= 1) rgba[0] = p[0];
+	if (fpp >= 2) rgba[1] = p[1];
+	if (fpp >= 3) rgba[2] = p[2];
+	if (fpp == 4) rgba[3] = p[3];
+}
+
+/* texture() with mip levels (swgl.c:2516-2595): level L > 0 reads MipMaps[MIN(L, n-1)] and MipMaps[MIN(L-1, n-1)]
+ * (the float is truncated to the vector index) and mixes them with T = 1 - (L - (int)L). */
+static void sample_lod(const swglo_shader* s, float u, float v, float level, float rgba[4])
+{
+	if (!(s->n_mips > 0 && level > 0.0f)) { sample_nearest(s, u, v, rgba); return; }
+	const int k0 = (int)RMIN(level, s->n_mips - 1);
+	const int k1 = (int)RMIN(level - 1, s->n_mips - 1);
+	float hi[4];
+	texel_of(s->mip_data + s->mip_off[k0], s->mip_w[k0], s->mip_h[k0], s->tex_fpp, s->wrap_s_repeat, s->wrap_t_repeat, u, v, rgba);
+	texel_of(s->mip_data + s->mip_off[k1], s->mip_w[k1], s->mip_h[k1], s->tex_fpp, s->wrap_s_repeat, s->wrap_t_repeat, u, v, hi);
+	float T = level - (int)level;
+	T = 1.0f - T;
+	if (s->tex_fpp >= 1) rgba[0] = rgba[0] + T * (hi[0] - rgba[0]);
+	if (s->tex_fpp >= 2) rgba[1] = rgba[1] + T * (hi[1] - rgba[1]);
+	if (s->tex_fpp >= 3) rgba[2] = rgba[2] + T * (hi[2] - rgba[2]);
+	if (s->tex_fpp == 4) rgba[3] = rgba[3] + T * (hi[3] - rgba[3]);
+}
+
+int swglo_build_mipmaps(const float* base, int32_t w, int32_t h, int32_t fpp,
+                        float* out, int32_t* off, int32_t* lw, int32_t* lh, size_t* total_floats)
+{
+	int cw = w / 2, ch = h / 2, n = 0;
+	size_t floats = 0;
+	const float* prev = base;
+	while (cw + ch > 4) /* swgl.c:2134 */
+	{
+		if (out)
+		{
+			float* cur = out + floats;
+			off[n] = (int32_t)floats; lw[n] = cw; lh[n] = ch;
+			for (int y = 0; y < ch; y++)
+				for (int x = 0; x < cw; x++)
+				{
+					float* cp = cur + fpp * (x + y * cw);
+					for (int k = 0; k < fpp; k++) cp[k] = 0.0f;
+					for (int sy = 0; sy < 2; sy++)
+						for (int sx = 0; sx < 2; sx++)
+						{
+							/* the row stride of the previous level is taken as 2 * CurWidth (swgl.c:2151) */
+							const float* pp = prev + fpp * ((x * 2 + sx) + (y * 2 + sy) * cw * 2);
+							for (int k = 0; k < fpp; k++) cp[k] += pp[k];
+						}
+					for (int k = 0; k < fpp; k++) cp[k] /= 4.0f;
+				}
+			prev = cur;
+		}
+		floats += (size_t)cw * ch * fpp;
+		n++;
+		cw /= 2; ch /= 2;
+	}
+	if (total_floats) *total_floats = floats;
+	return n;
+}
+
 /* DrawTriangle (swgl.c:3314-3473). `o` = the three vertices in submission order with
  * pos = ((float)X, (float)Y, z_clip, w_clip). */
 static void draw_triangle(const swglo_target* t, const swglo_shader* s, const overtex o[3],
@@ -147,6 +245,9 @@ static void draw_triangle(const swglo_target* t, const swglo_shader* s, const ov
 	const uint32_t W = t->width, H = t->height;
 	const int32_t VX = t->vx, VY = t->vy;
 	const uint32_t VW = t->vw, VH = t->vh;
+
+	/* swgl.c:3316: the level of detail of the whole triangle, from the vertices as submitted */
+	const float level = s->lod ? mip_level(o[0].pos.x, o[0].pos.y, o[1].pos.x, o[1].pos.y, o[2].pos.x, o[2].pos.y) : 0.0f;
 
 	/* sort a copy by y with the reference's three compare-swaps (swgl.c:3323-3342) */
 	vec4 c[3] = { o[0].pos, o[1].pos, o[2].pos };
@@ -214,7 +315,7 @@ static void draw_triangle(const swglo_target* t, const swglo_shader* s, const ov
 					vr[k] = o[0].var[k] * uc + o[1].var[k] * vc + o[2].var[k] * wc;
 
 				float out[4];
-				if (s->fs_mode == 1) sample_nearest(s, vr[0], vr[1], out);
+				if (s->fs_mode == 1) { if (s->lod) sample_lod(s, vr[0], vr[1], level, out); else sample_nearest(s, vr[0], vr[1], out); }
 				else { out[0] = vr[0]; out[1] = vr[1]; out[2] = vr[2]; out[3] = vr[3]; }
 
 				float r = RMIN(RMAX(out[0], 0.0f), 1.0f); /* swgl.c:3428-3431 */

@@ -8,7 +8,8 @@
  * reference (oracle/_ref/libswgl_ref.so) and against golden hashes in tests/golden/.
  *
  * It knows only what the hot path needs: a flat vertex stream, a "shader description"
- * covering the shader shapes of the BASELINE configs, one texture, one framebuffer.
+ * covering the shader shapes of the BASELINE configs, one texture (with its mip levels and the defined
+ * level of detail, pinned against oracle/_ref/libswgl_ref_lod.so), one framebuffer.
  */
 #ifndef SWGL_ORACLE_H
 #define SWGL_ORACLE_H
@@ -45,6 +46,17 @@ typedef struct
 	const float* tex;         /* float texels as stored by glTexImage2D (swgl.c:2107-2118) */
 	int32_t  tex_w, tex_h, tex_fpp;
 	int32_t  wrap_s_repeat, wrap_t_repeat;
+	/* glGenerateMipmap levels (swgl.c:2122-2173) and the per-triangle level of detail, the DEFINED variant: the
+	 * reference's rsqrt() puns a 4-byte float through an 8-byte long (swgl.c:3240-3246, undefined behaviour); with
+	 * lod != 0 the restatement uses the same code with a 32-bit pun, which is what oracle/_ref/libswgl_ref_lod.so
+	 * (ref_shim.c, -DSWGLREF_DEFINED_RSQRT) is built with and what the library's "mip_lod" option selects.
+	 * n_mips levels: level k is mip_w[k] x mip_h[k] texels at mip_data + mip_off[k] (floats).  0 = no chain. */
+	int32_t  lod;
+	int32_t  n_mips;
+	const float*   mip_data;
+	const int32_t* mip_off;
+	const int32_t* mip_w;
+	const int32_t* mip_h;
 } swglo_shader;
 
 typedef struct
@@ -68,6 +80,12 @@ void swglo_draw_arrays(const swglo_target* t, const swglo_shader* s,
 void swglo_draw_elements(const swglo_target* t, const swglo_shader* s,
                          const uint8_t* vbo, size_t vbo_bytes,
                          const uint32_t* indices, uint32_t count, swglo_stats* stats);
+
+/* glGenerateMipmap (swgl.c:2122-2173): 2x2 box levels of a float image while CurWidth + CurHeight > 4.  Call with
+ * out == NULL to get the number of levels and floats; with buffers to fill them (offsets in floats).  Returns the
+ * number of levels. */
+int swglo_build_mipmaps(const float* base, int32_t w, int32_t h, int32_t fpp,
+                        float* out, int32_t* off, int32_t* lw, int32_t* lh, size_t* total_floats);
 
 /* glTexImage2D's byte->float conversion (swgl.c:2116). out has n floats. */
 void swglo_texels_from_u8(const uint8_t* in, float* out, size_t n);

@@ -234,6 +234,26 @@ def test_points_sample_with_the_level_the_last_triangle_left(gpu_api, reference_
     assert int((frames[True] != frames[False]).sum()) > 300
 
 
+@pytest.mark.parametrize("path", [3, 2], ids=["warp_tile", "fragment_parallel"])
+def test_mip_levels_match_the_restatement_and_its_golden_frames(gpu_api, restatement, path):
+    """The same frames against the C restatement of the mip chain and the defined level of detail (pinned on the CPU
+    against the reference built that way, tests/test_oracle.py) and against tests/golden/lod_kats.json: colour, depth
+    and the fragment counters, indexed draws included."""
+    import json
+    import os
+    from test_oracle import lod_scenes
+    from util import assert_bit_exact, gpu_render
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lod_kats.json")))
+    for name, scene in lod_scenes().items():
+        rc, rd, rstats = restatement.render(scene, mipmaps=True)
+        col, dep, stats, err = gpu_render(gpu_api, scene, indexed=scene.indices is not None, mipmaps=True,
+                                          options={"mip_lod": 1, "raster_path": path})
+        assert err == "", err
+        assert_bit_exact(O.compare(col, dep, rc, rd), name)
+        assert (stats["tested"], stats["shaded"]) == (rstats["tested"], rstats["shaded"])
+        assert f"{restatement.fnv(col):016x}" == kats[name]["color_fnv"] and f"{restatement.fnv(dep):016x}" == kats[name]["depth_fnv"]
+
+
 def test_default_stays_bug_compatible(gpu_api, reference):
     """Without the option the chain is built but never sampled, like the compiled reference."""
     scene = S.grid_mesh(24, W, H, textured=True)

@@ -33,6 +33,23 @@ with open(GOLDEN) as f:
     KATS = json.load(f)
 
 
+def lod_scenes():
+    """Mip-mapped scenes of the DEFINED level-of-detail variant (tests/golden/make_golden_lod.py): triangles from far
+    larger than 40 pixels (level below 1) to a few pixels (level beyond the chain), both wrap modes, near clipping."""
+    sc = {
+        "lod_grid9": S.grid_mesh(9, 320, 240, textured=True),
+        "lod_grid24": S.grid_mesh(24, 320, 240, textured=True),
+        "lod_grid60_clamp": S.grid_mesh(60, 320, 240, textured=True),
+        "lod_random_near": S.random_triangles(600, 320, 240, seed=5, extent=0.12, textured=True, near_cross=True),
+    }
+    sc["lod_grid60_clamp"].tex_wrap = "clamp"
+    return sc
+
+
+LOD_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "lod_kats.json")
+LOD_KATS = json.load(open(LOD_GOLDEN)) if os.path.exists(LOD_GOLDEN) else {}
+
+
 @pytest.mark.parametrize("name", sorted(KATS))
 def test_restatement_matches_golden(restatement, name):
     scene = golden_scenes()[name]
@@ -49,6 +66,32 @@ def test_restatement_matches_compiled_reference(restatement, reference, name):
     scene = golden_scenes()[name]
     c1, d1, _ = restatement.render(scene)
     c2, d2 = reference.render(scene)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+
+
+@pytest.mark.parametrize("name", sorted(LOD_KATS))
+def test_restatement_mip_levels_match_golden(restatement, name):
+    """glGenerateMipmap + per-triangle level of detail in the restatement (swgl_oracle.c: swglo_build_mipmaps, mip_level,
+    sample_lod) against the frames of the reference built with the defined rsqrt."""
+    scene = lod_scenes()[name]
+    col, dep, stats = restatement.render(scene, mipmaps=True)
+    k = LOD_KATS[name]
+    assert f"{restatement.fnv(col):016x}" == k["color_fnv"] and f"{restatement.fnv(dep):016x}" == k["depth_fnv"]
+    assert stats["tested"] == k["tested"] and stats["shaded"] == k["shaded"]
+    base, _, _ = restatement.render(scene)
+    assert int((col != base).sum()) == k["differs_from_base_level"] > 10000
+
+
+@pytest.mark.parametrize("name", sorted(LOD_KATS))
+def test_restatement_mip_levels_match_the_defined_rsqrt_reference(restatement, name):
+    try:
+        ref = O.Reference(defined_rsqrt=True)
+    except Exception as e:                                  # pragma: no cover
+        pytest.skip(f"oracle/_ref/libswgl_ref_lod.so not available: {e}")
+    scene = lod_scenes()[name]
+    c1, d1, _ = restatement.render(scene, mipmaps=True)
+    c2, d2 = ref.render(scene, mipmaps=True)
     cmp = O.compare(c1, d1, c2, d2)
     assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
 

@@ -10,8 +10,9 @@ from swgl_b200 import gl as G
 
 
 def gpu_render(api, scene, *, indexed=True, clear=True, fill=(0, 0.0), first=0, count=None,
-               options=None, stripe=None, draws=None):
-    """Render ``scene`` with the CUDA library; returns (color, depth, stats dict, error str)."""
+               options=None, stripe=None, draws=None, mipmaps=False):
+    """Render ``scene`` with the CUDA library; returns (color, depth, stats dict, error str).
+    mipmaps: glGenerateMipmap on the scene's texture (sampled when options has mip_lod = 1)."""
     api.glInit(scene.width, scene.height)
     err = api.swglGetLastError()
     assert not err, f"glInit failed: {err!r}"
@@ -21,6 +22,8 @@ def gpu_render(api, scene, *, indexed=True, clear=True, fill=(0, 0.0), first=0, 
     if stripe:
         api.swglSetStripe(*stripe)
     st = G.setup_scene(api, scene, indexed=indexed, init=False)
+    if mipmaps:
+        api.glGenerateMipmap(G.GL_TEXTURE_2D)
     api.swglFillFramebuffer(fill[0], C.c_float(fill[1]))
     if clear:
         api.glClear(3)
