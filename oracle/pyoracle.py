@@ -127,6 +127,7 @@ class Restatement:
         L.swglo_draw_elements.argtypes = [
             C.POINTER(_Target), C.POINTER(_Shader), C.c_void_p, C.c_size_t,
             C.c_void_p, C.c_uint32, C.POINTER(Stats)]
+        L.swglo_draw_points.argtypes = [C.POINTER(_Target), C.POINTER(_Shader), C.c_void_p, C.c_size_t, C.c_int32, C.c_uint32]
         L.swglo_texels_from_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.swglo_build_mipmaps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.POINTER(C.c_size_t)]
@@ -170,8 +171,9 @@ class Restatement:
         return t, s
 
     def render(self, scene, *, clear: bool = True, color=None, depth=None,
-               first: int = 0, count: Optional[int] = None, fill=(0, 0.0), mipmaps: bool = False):
+               first: int = 0, count: Optional[int] = None, fill=(0, 0.0), mipmaps: bool = False, points=None):
         """Returns (color uint32 [H,W], depth float32 [H,W], stats dict).
+        points = (first, count): a glDrawArrays(GL_POINTS, first, count) over the same vertex stream after the triangles.
         mipmaps: glGenerateMipmap on the scene's texture and the DEFINED level of detail (the checker of that mode is
         Reference(defined_rsqrt=True), rendered with mipmaps=True too)."""
         H, W = scene.height, scene.width
@@ -194,6 +196,8 @@ class Restatement:
             n = len(v) if count is None else count
             self.lib.swglo_draw_arrays(C.byref(t), C.byref(s), v.ctypes.data_as(C.c_void_p), v.nbytes,
                                        first, n, C.byref(st))
+        if points is not None:
+            self.lib.swglo_draw_points(C.byref(t), C.byref(s), v.ctypes.data_as(C.c_void_p), v.nbytes, points[0], points[1])
         return color, depth, st.as_dict()
 
     def timed_frame(self, scene, count: Optional[int] = None, reps: int = 1):
@@ -238,9 +242,10 @@ class Reference:
         self.lib.swglref_timed_frame.restype = C.c_double
 
     def render(self, scene, *, clear: bool = True, first: int = 0, count: Optional[int] = None,
-               fill=(0, 0.0), mipmaps: bool = False):
+               fill=(0, 0.0), mipmaps: bool = False, points=None):
         """Returns (color uint32 [H,W], depth float32 [H,W]).  Indexed scenes are de-indexed
-        on the host first: the reference has no glDrawElements."""
+        on the host first: the reference has no glDrawElements.
+        points = (first, count): glDrawArrays(GL_POINTS, first, count) after the triangles."""
         G = self.G
         st = G.setup_scene(self.api, scene, indexed=False)
         if mipmaps:
@@ -250,6 +255,8 @@ class Reference:
             self.api.glClear(3)
         n = st["n_draw"] if count is None else count
         self.api.glDrawArrays(G.GL_TRIANGLES, first, n)
+        if points is not None:
+            self.api.glDrawArrays(G.GL_POINTS, points[0], points[1])
         H, W = scene.height, scene.width
         col = G.frame_color(self.api, W, H)
         dep = np.ctypeslib.as_array(self.lib.swglref_depth_ptr(), shape=(H, W)).copy()

@@ -139,6 +139,10 @@ static void sample_nearest(const swglo_shader* s, float u, float v, float rgba[4
 	if (s->tex_fpp == 4) rgba[3] = p[3];
 }
 
+/* MipMapLevel (swgl.c:3314): a global that every DrawTriangle call sets and texture() reads whatever the primitive --
+ * a GL_POINTS draw samples with what the last triangle left. */
+static float g_mip_level = 0.0f;
+
 /* rsqrt (swgl.c:3238-3254) with the pun through a 32-bit integer: the defined variant (see swgl_oracle.h). */
 static float rsqrt_defined(float number)
 {
@@ -248,6 +252,7 @@ static void draw_triangle(const swglo_target* t, const swglo_shader* s, const ov
 
 	/* swgl.c:3316: the level of detail of the whole triangle, from the vertices as submitted */
 	const float level = s->lod ? mip_level(o[0].pos.x, o[0].pos.y, o[1].pos.x, o[1].pos.y, o[2].pos.x, o[2].pos.y) : 0.0f;
+	if (s->lod) g_mip_level = level;
 
 	/* sort a copy by y with the reference's three compare-swaps (swgl.c:3323-3342) */
 	vec4 c[3] = { o[0].pos, o[1].pos, o[2].pos };
@@ -389,6 +394,41 @@ static void draw_common(const swglo_target* t, const swglo_shader* s,
 			if (stats) stats->prims_out++;
 			draw_triangle(t, s, scr, stats);
 		}
+	}
+}
+
+/* glDrawArrays(GL_POINTS, first, count) (swgl.c:3496-3608): one pixel per vertex.  X is scaled with ViewportHeight / 2
+ * (3531), the varyings are the vertex's own, depth is written without a test and without the row flip of the triangle
+ * path (3582-3583), colour without a blend (3599-3604). */
+void swglo_draw_points(const swglo_target* t, const swglo_shader* s,
+                       const uint8_t* vbo, size_t vbo_bytes, int32_t first, uint32_t count)
+{
+	vs_state st;
+	memset(&st, 0, sizeof(st));
+	store_matrix(s, st.D);
+	for (int i = first; (uint32_t)i < (uint32_t)first + count; i++)
+	{
+		overtex v;
+		run_vertex(s, &st, vbo, vbo_bytes, (uint64_t)(uint32_t)i, &v);
+		int X = v.pos.x / v.pos.w * (t->vh / 2) + (t->vw / 2) + t->vx;
+		int Y = v.pos.y / v.pos.w * (t->vh / 2) + (t->vh / 2) + t->vy;
+		if (X < 0 || (uint32_t)X >= t->width) continue;
+		if (Y < 0 || (uint32_t)Y >= t->height) continue;
+		float out[4];
+		if (s->fs_mode == 1) { if (s->lod) sample_lod(s, v.var[0], v.var[1], g_mip_level, out); else sample_nearest(s, v.var[0], v.var[1], out); }
+		else { out[0] = v.var[0]; out[1] = v.var[1]; out[2] = v.var[2]; out[3] = v.var[3]; }
+		float r = RMIN(RMAX(out[0], 0.0f), 1.0f);
+		float g = RMIN(RMAX(out[1], 0.0f), 1.0f);
+		float bl = RMIN(RMAX(out[2], 0.0f), 1.0f);
+		float al = RMIN(RMAX(out[3], 0.0f), 1.0f);
+		const uint32_t idx = (uint32_t)X + (uint32_t)Y * t->width;
+		t->depth[idx] = v.pos.z;
+		uint32_t word = 0;
+		word |= (uint32_t)((int)(r * 255)) << 24;
+		word |= (uint32_t)((int)(g * 255)) << 16;
+		word |= (uint32_t)((int)(bl * 255)) << 8;
+		word |= (uint32_t)((int)(al * 255));
+		t->color[idx] = word;
 	}
 }
 

@@ -9,7 +9,7 @@
  *
  * It knows only what the hot path needs: a flat vertex stream, a "shader description"
  * covering the shader shapes of the BASELINE configs, one texture (with its mip levels and the defined
- * level of detail, pinned against oracle/_ref/libswgl_ref_lod.so), one framebuffer.
+ * level of detail, pinned against oracle/_ref/libswgl_ref_lod.so), GL_TRIANGLES and GL_POINTS, one framebuffer.
  */
 #ifndef SWGL_ORACLE_H
 #define SWGL_ORACLE_H
@@ -74,6 +74,11 @@ void swglo_clear(const swglo_target* t, uint32_t flags, float r, float g, float 
 void swglo_draw_arrays(const swglo_target* t, const swglo_shader* s,
                        const uint8_t* vbo, size_t vbo_bytes,
                        int32_t first, uint32_t count, swglo_stats* stats);
+
+/* glDrawArrays(GL_POINTS, first, count) (swgl.c:3496-3608).  Under `lod` the points sample with the level the last
+ * swglo_draw_* triangle left (the reference's global MipMapLevel). */
+void swglo_draw_points(const swglo_target* t, const swglo_shader* s,
+                       const uint8_t* vbo, size_t vbo_bytes, int32_t first, uint32_t count);
 
 /* Same, fetching vertex i of the stream as vbo[indices[i]] -- the *definition* of the
  * glDrawElements extension: glDrawArrays over the de-indexed stream. */

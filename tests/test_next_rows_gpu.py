@@ -279,3 +279,20 @@ def test_read_pixels_rgba8_and_ppm(gpu_api, reference, tmp_path):
     assert np.array_equal(np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3), want_bytes[:, :, :3])
     assert gpu_api.swglWritePPM(b"/nonexistent-dir/x.ppm") != 0
     assert b"swglWritePPM" in gpu_api.swglGetLastError()
+
+
+@pytest.mark.parametrize("name", ["colour_near", "colour_viewport", "textured", "matrix"])
+@pytest.mark.parametrize("lod", [0, 1])
+def test_points_match_the_restatement(gpu_api, restatement, name, lod):
+    """GL_POINTS against the C restatement (swglo_draw_points, pinned on the CPU against the compiled reference,
+    tests/test_oracle.py), also with mip levels sampled: a point takes the level the last triangle left."""
+    from test_oracle import _point_scenes
+    from util import assert_bit_exact, gpu_render
+    scene = _point_scenes()[name]
+    if lod and scene.texture is None:
+        pytest.skip("no texture")
+    kw = dict(count=300, points=(300, len(scene.vertices) - 300), mipmaps=bool(lod))
+    rc, rd, _ = restatement.render(scene, **kw)
+    col, dep, stats, err = gpu_render(gpu_api, scene, indexed=False, options={"mip_lod": lod}, **kw)
+    assert err == "", err
+    assert_bit_exact(O.compare(col, dep, rc, rd), name)

@@ -96,6 +96,50 @@ def test_restatement_mip_levels_match_the_defined_rsqrt_reference(restatement, n
     assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
 
 
+def _point_scenes():
+    sc = {
+        "colour_near": (S.random_triangles(900, 320, 240, seed=3, alpha=None, near_cross=True, centre_range=1.3), None),
+        "colour_viewport": (S.random_triangles(900, 320, 240, seed=4, alpha=None), (13, 7, 150, 90)),
+        "textured": (S.random_triangles(900, 320, 240, seed=6, textured=True), None),
+        "matrix": (S.grid_mesh(30, 333, 211, alpha=0.5, use_matrix=True), None),
+    }
+    for scene, vp in sc.values():
+        scene.viewport = vp
+        if scene.indices is not None:
+            scene.vertices, scene.indices = scene.deindexed(), None
+    return {k: v[0] for k, v in sc.items()}
+
+
+@pytest.mark.parametrize("name", ["colour_near", "colour_viewport", "textured", "matrix"])
+def test_restatement_points_match_compiled_reference(restatement, reference, name):
+    """GL_POINTS (swgl.c:3496-3608; swglo_draw_points): 100 triangles first -- the reference only allocates a program's
+    fragment inputs when a triangle is shaded -- then every other vertex of the stream as a point."""
+    scene = _point_scenes()[name]
+    kw = dict(count=300, points=(300, len(scene.vertices) - 300))
+    c1, d1, _ = restatement.render(scene, **kw)
+    c2, d2 = reference.render(scene, **kw)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+    t1, _, _ = restatement.render(scene, count=300)
+    assert int((t1 != c1).sum()) > 300            # the points are really there
+
+
+def test_restatement_points_sample_with_the_last_triangles_level(restatement):
+    """Under the defined level of detail a point samples with the level the last triangle left (a global, swgl.c:3314)."""
+    try:
+        ref = O.Reference(defined_rsqrt=True)
+    except Exception as e:                                  # pragma: no cover
+        pytest.skip(f"oracle/_ref/libswgl_ref_lod.so not available: {e}")
+    scene = _point_scenes()["textured"]
+    kw = dict(count=300, points=(300, len(scene.vertices) - 300), mipmaps=True)
+    c1, d1, _ = restatement.render(scene, **kw)
+    c2, d2 = ref.render(scene, **kw)
+    cmp = O.compare(c1, d1, c2, d2)
+    assert cmp["depth_mismatch"] == 0 and cmp["coverage_mismatch"] == 0 and cmp["color_mismatch"] == 0, cmp
+    base, _, _ = restatement.render(scene, count=300, points=(300, len(scene.vertices) - 300))
+    assert int((base != c1).sum()) > 10000
+
+
 def test_survey_kats():
     """SURVEY.md appendix C values, measured independently during the survey."""
     assert KATS["k0_single"]["color_fnv"] == "5e2ecfac3685e7ef" and KATS["k0_single"]["covered"] == 1008

@@ -10,9 +10,10 @@ from swgl_b200 import gl as G
 
 
 def gpu_render(api, scene, *, indexed=True, clear=True, fill=(0, 0.0), first=0, count=None,
-               options=None, stripe=None, draws=None, mipmaps=False):
+               options=None, stripe=None, draws=None, mipmaps=False, points=None):
     """Render ``scene`` with the CUDA library; returns (color, depth, stats dict, error str).
-    mipmaps: glGenerateMipmap on the scene's texture (sampled when options has mip_lod = 1)."""
+    mipmaps: glGenerateMipmap on the scene's texture (sampled when options has mip_lod = 1);
+    points = (first, count): glDrawArrays(GL_POINTS, ...) over the same vertex stream after the triangles."""
     api.glInit(scene.width, scene.height)
     err = api.swglGetLastError()
     assert not err, f"glInit failed: {err!r}"
@@ -33,6 +34,8 @@ def gpu_render(api, scene, *, indexed=True, clear=True, fill=(0, 0.0), first=0, 
             api.glDrawElements(G.GL_TRIANGLES, k, G.GL_UNSIGNED_INT, C.c_void_p(4 * f))
         else:
             api.glDrawArrays(G.GL_TRIANGLES, f, k)
+    if points is not None:
+        api.glDrawArrays(G.GL_POINTS, points[0], points[1])
     H, W = scene.height, scene.width
     col = G.frame_color(api, W, H)
     dep = np.ctypeslib.as_array(api.swglGetDepthPtr(), shape=(H, W)).copy()
