@@ -2963,7 +2963,14 @@ static int group_draw_folded(swgldev_ctx* c, const swgldev_draw* d)
 	/* the members' bands of the assembled mirror are out of date: their next read-back copies them */
 	for (int i = 0; i < n; i++) c->group[i]->mirror_synced = 0;
 	/* the draw's counters are the leader's: the other members still hold those of their last own draw */
-	group_each(c, [&](int i, swgldev_ctx* m) { if (i) cudaMemsetAsync(m->ctr, 0, sizeof(Counters), m->stream); return 0; });
+	group_each(c, [&](int i, swgldev_ctx* m)
+	{
+		if (!i) return 0;
+		cudaMemsetAsync(m->ctr, 0, sizeof(Counters), m->stream);
+		/* ... and the level of detail the draw's last triangle left (k_last_level ran on the leader only) */
+		if (c->opt_mip_lod) cudaMemcpyPeerAsync(m->d_last_level, m->device, c->d_last_level, c->device, sizeof(float), m->stream);
+		return 0;
+	});
 	cudaSetDevice(c->device);
 	if (rc) set_err(c, "folded draw on a device group failed", cudaGetLastError());
 	return rc ? -1 : 0;
