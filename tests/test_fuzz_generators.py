@@ -64,3 +64,34 @@ def test_random_shaders_are_accepted_by_the_front_end_and_compile():
     for seed in (900, 903, 905):                            # three of the programs tests/test_api_fuzz_gpu.py pools
         vs, fs, _ = make(seed)
         assert _compile(api, vs, fs) == 0, api.swglGetLastError().decode()
+
+
+def test_generator_modes_keep_their_promises():
+    for seed in range(200):
+        ops = F.make_ops(seed, inside=True)
+        H = ops[0][4]
+        assert not any(o[0] == "viewport" and (o[2] < 0 or o[2] + o[4] > H) for o in ops), seed
+        # under `lod` an image never has more floats per texel than the levels its texture object already carries
+        ops = F.make_ops(seed, lod=True)
+        bound, cur, levels = 1, {0: 4, 1: 4}, {1: 4}
+        for o in ops[2:]:
+            if o[0] == "bindtex":
+                bound = o[2]
+            elif o[0] == "teximage":
+                assert o[2].shape[2] <= levels.get(bound, 4), seed
+                cur[bound] = o[2].shape[2]
+            elif o[0] == "mipmap":
+                levels[bound] = min(levels.get(bound, 4), cur[bound])
+        # draws stay inside the array they read (a partial last triple is read whole)
+        arrays = [a for a in F.make_ops(seed)[0][1]]
+        vao = 0
+        for o in F.make_ops(seed)[1:]:
+            if o[0] == "vao":
+                vao = o[1]
+            elif o[0] == "respecify":
+                vao, arrays[o[1]] = o[1], o[2]
+            elif o[0] == "draw":
+                n = len(arrays[vao][0]) if arrays[vao][1] is None else len(arrays[vao][1])
+                assert o[1] + 3 * ((o[2] + 2) // 3) <= n, (seed, o, n)
+            elif o[0] == "points":
+                assert arrays[vao][1] is None and o[1] + o[2] <= len(arrays[vao][0]), (seed, o)
