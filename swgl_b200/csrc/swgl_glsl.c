@@ -15,7 +15,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define BIG 0x7FFFFFFF
+/* "not found" of the scanners.  Far beyond any source (swgl_glsl_compile refuses longer ones) and small enough that the
+ * `cursor = position + 1` of a caller that has not looked at it yet cannot overflow: the cursor then lies behind the end
+ * of the text, every scanner loop is empty and ch() reads as 0. */
+#define BIG 0x3FFFFFFF
 
 /* ------------------------------------------------------------------------------------------
  * literals (swgl.c:18-88)
@@ -988,6 +991,7 @@ swgl_shader* swgl_glsl_compile(const char* source)
 
 	/* swgl.c:1839-1843: newlines and tabs are deleted, no blank is inserted */
 	size_t len = strlen(source);
+	if (len >= (size_t)BIG - 16) { free(sh); free(p); return NULL; }
 	p->code = (char*)calloc(len + 16, 1);
 	if (!p->code) { free(sh); free(p); return NULL; }
 	for (size_t i = 0; i < len; i++)
