@@ -136,7 +136,21 @@ static int draw(swgldev_ctx* c, const swgldev_draw* d)
 }
 int swgldev_draw_triangles(swgldev_ctx* c, const swgldev_draw* d) { return draw(c, d); }
 int swgldev_draw_points(swgldev_ctx* c, const swgldev_draw* d) { return draw(c, d); }
+#ifdef STUB_WITH_JIT
+/* the real code generator + NVRTC (swgl_jit.cpp, built with the sanitizers too): generate and compile, load nothing */
+#include "swgl_jit.h"
+int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t msg_len)
+{
+	(void)c;
+	if (msg_len) msg[0] = 0;
+	const int want_v = d->vs_kind == SWVS_GENERIC, want_r = d->fs_kind == SWFS_GENERIC;
+	if (!want_v && !want_r) return 0;
+	swgljit_kernels k;
+	return swgljit_get(-1, d, want_v, want_r, &k, msg, msg_len);
+}
+#else
 int swgldev_precompile(swgldev_ctx* c, const swgldev_draw* d, char* msg, size_t msg_len) { (void)c; (void)d; if (msg_len) msg[0] = 0; return 0; }
+#endif
 
 uint32_t* swgldev_map_color(swgldev_ctx* c) { return c->color; }
 float* swgldev_map_depth(swgldev_ctx* c) { return c->depth; }

@@ -41,3 +41,32 @@ def test_call_sequences_through_the_sanitized_host_layer(sanitized_host):
 def test_nonsense_arguments_through_the_sanitized_host_layer(sanitized_host, seed):
     run = subprocess.run([sys.executable, os.path.join(FUZZ, "hostile_calls.py"), str(seed), "8000"], env=sanitized_host, capture_output=True, timeout=900)
     assert run.returncode == 0 and b"hostile calls: 8000" in run.stdout, (run.stdout[-500:], run.stderr[-3000:])
+
+
+def test_code_generator_of_the_run_time_compiler_under_the_sanitizers(sanitized_host, tmp_path):
+    """swgl_jit.cpp (IR -> CUDA C++, NVRTC for sm_100a, no device) built with the sanitizers as well: the twelve shader
+    cases and ten random programs are generated and compiled."""
+    from swgl_b200 import build as B
+    gxx, gcc = shutil.which("g++"), shutil.which("gcc")
+    cuda = os.path.dirname(os.path.dirname(B.NVCC))
+    if not gxx or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no g++ / CUDA headers")
+    B._write_jit_sources(str(tmp_path / "swgl_jit_sources.inc"))
+    san = ["-O1", "-g", "-fPIC", "-w", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", str(tmp_path), "-I", os.path.join(cuda, "include")]
+    objs = []
+    for cc, std, src, extra in ((gxx, "-std=c++17", os.path.join(CSRC, "swgl_jit.cpp"), []), (gcc, "-std=gnu11", os.path.join(CSRC, "swgl_host.c"), ["-ffp-contract=off"]),
+                                (gcc, "-std=gnu11", os.path.join(CSRC, "swgl_glsl.c"), ["-ffp-contract=off"]), (gcc, "-std=gnu11", os.path.join(FUZZ, "stub_dev.c"), ["-DSTUB_WITH_JIT"])):
+        obj = str(tmp_path / (os.path.basename(src) + ".o"))
+        r = subprocess.run([cc, std] + san + extra + inc + ["-c", src, "-o", obj], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        objs.append(obj)
+    so = str(tmp_path / "libswgl_host_jit_asan.so")
+    r = subprocess.run([gxx, "-shared", "-fsanitize=address,undefined", "-o", so] + objs + ["-L" + os.path.join(cuda, "lib64"), "-Wl,-rpath," + os.path.join(cuda, "lib64"),
+                                                                                           "-lcudart", "-ldl", "-lpthread", "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(sanitized_host, SWGL_B200_LIB=so, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:protect_shadow_gap=0")
+    run = subprocess.run([sys.executable, os.path.join(FUZZ, "jit_programs.py"), "0", "10"], env=env, capture_output=True, timeout=1200)
+    if b"libnvrtc" in run.stdout + run.stderr and run.returncode == 3:
+        pytest.skip("NVRTC not available")
+    assert run.returncode == 0 and b"programs generated and compiled: 22" in run.stdout, (run.stdout[-800:], run.stderr[-3000:])
