@@ -95,3 +95,29 @@ def test_generator_modes_keep_their_promises():
                 assert o[1] + 3 * ((o[2] + 2) // 3) <= n, (seed, o, n)
             elif o[0] == "points":
                 assert arrays[vao][1] is None and o[1] + o[2] <= len(arrays[vao][0]), (seed, o)
+
+
+def test_object_ids_and_uniform_locations_match_the_compiled_reference(reference):
+    """Every shader case and 25 random programs, created in the same order in both libraries: shader / program / vertex
+    array / buffer / texture ids, the glGen* return values and the location of 25 names (uniforms of both stages, names
+    that are not uniforms, names that do not exist) must be the same numbers (no device needed)."""
+    from shader_cases import CASES
+    names = [b"tint", b"k", b"freq", b"A", b"B", b"N", b"R", b"uTex", b"u1", b"u2", b"u3", b"u4", b"uM", b"steps", b"shift", b"gain",
+             b"offs", b"nope", b"", b"vCol", b"aPos", b"gl_Position", b"FragColor", b"t0", b"res"]
+    progs = [(vs, fs) for vs, fs, _ in CASES.values()] + [make(k)[:2] for k in range(25)]
+    rows = []
+    for api in (swgl_b200.load(), reference.api):
+        api.glInit(32, 32)                       # (without a device the library's glInit only resets the object tables)
+        out = []
+        for vs, fs in progs:
+            v = api.glCreateShader(G.GL_VERTEX_SHADER); api.glShaderSource(v, vs.encode()); api.glCompileShader(v)
+            f = api.glCreateShader(G.GL_FRAGMENT_SHADER); api.glShaderSource(f, fs.encode()); api.glCompileShader(f)
+            p = api.glCreateProgram(); api.glAttachShader(p, v); api.glAttachShader(p, f); api.glLinkProgram(p)
+            vao, vbo, tex = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+            r1, r2 = api.glGenVertexArrays(1, C.byref(vao)), api.glGenBuffers(1, C.byref(vbo))
+            api.glGenTextures(1, C.byref(tex))
+            out.append((v, f, p, vao.value, vbo.value, tex.value, r1, r2, tuple(api.glGetUniformLocation(p, n) for n in names)))
+        rows.append(out)
+    swgl_b200.load().swglGetLastError()
+    assert rows[0] == rows[1]
+    assert any(loc >= 0 for row in rows[1] for loc in row[8]) and any(loc == -1 for row in rows[1] for loc in row[8])
